@@ -1,0 +1,505 @@
+// Bound-constrained limited-memory BFGS for tiny problems (n <= 3), host+device.
+//
+// The reference's pore-centre optimiser (utilities.py:400-426) and window z-stage (utilities.py:1301)
+// are `scipy.optimize.minimize(..., bounds=...)`, i.e. L-BFGS-B (Byrd, Lu, Nocedal, Zhu 1995; Zhu et
+// al. 1997; Morales & Nocedal 2011) with scipy's defaults m=10, ftol=2.22e-9, gtol=1e-5, maxls=20 and
+// 2-point forward-difference gradients with absolute step 1e-8 that flip direction at bounds
+// (scipy/optimize/_numdiff.py:_adjust_scheme_to_bounds).  The reference's answer is *where this
+// algorithm stops*, not the true optimum, so the algorithm is restated here:
+// generalized Cauchy point -> subspace minimisation with projection -> More-Thuente line search
+// (dcsrch/dcstep) -> BFGS pair update with the same skip / restart / termination rules.
+//
+// Design for n <= 3: the compact representation B = theta*I - W M W^T (2m x 2m middle matrix) is
+// replaced by the *same* matrix formed densely: B0 = theta*I followed by the stored (s, y) BFGS
+// updates, oldest first.  This is algebraically identical (Byrd-Nocedal-Schnabel 1994, Thm 2.3) and
+// keeps all state in registers / a 480-byte ring instead of the 1100-double workspace.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define PWB_HD __host__ __device__ __forceinline__
+#define PWB_HDN __host__ __device__
+#else
+#define PWB_HD inline
+#define PWB_HDN
+#endif
+
+namespace pwb {
+
+constexpr int LB_M = 10;
+constexpr double LB_EPSMCH = 2.220446049250313e-16;
+constexpr double LB_FD_STEP = 1e-8;
+
+enum LbStatus {
+  LB_CONV_PGTOL = 0,
+  LB_CONV_FTOL = 1,
+  LB_ABNORMAL = 2,
+  LB_MAXITER = 3,
+};
+
+// scipy _numdiff.py: absolute step h adjusted to the box so that x+h stays feasible.
+PWB_HD double lb_fd_step(double x, int nbd, double lo, double hi) {
+  double h = LB_FD_STEP;
+  if (nbd == 0) return h;
+  const double INF = 1.0 / 0.0;
+  double lb = (nbd == 1 || nbd == 2) ? lo : -INF;
+  double ub = (nbd == 2 || nbd == 3) ? hi : INF;
+  double lower_dist = x - lb, upper_dist = ub - x;
+  double xt = x + h;
+  bool violated = (xt < lb) || (xt > ub);
+  bool fitting = fabs(h) <= fmax(lower_dist, upper_dist);
+  if (violated && fitting) h = -h;
+  if (!fitting) h = (upper_dist >= lower_dist) ? upper_dist : -lower_dist;
+  return h;
+}
+
+// ---- More-Thuente safeguarded step (MINPACK-2 dcstep; scipy/optimize/_dcsrch.py:dcstep)
+PWB_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy,
+                      double& stp, double fp, double dp, bool& brackt, double stpmin, double stpmax) {
+  double sgn_dp = (dp > 0) - (dp < 0), sgn_dx = (dx > 0) - (dx < 0);
+  double sgnd = sgn_dp * sgn_dx;
+  double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+  if (fp > fx) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    p = (gamma - dx) + theta;
+    q = ((gamma - dx) + gamma) + dp;
+    r = p / q;
+    stpc = stx + r * (stp - stx);
+    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    stpf = (fabs(stpc - stx) <= fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
+    brackt = true;
+  } else if (sgnd < 0.0) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = ((gamma - dp) + gamma) + dx;
+    r = p / q;
+    stpc = stp + r * (stx - stp);
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+    brackt = true;
+  } else if (fabs(dp) < fabs(dx)) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = (gamma + (dx - dp)) + gamma;
+    r = p / q;
+    if (r < 0 && gamma != 0) stpc = stp + r * (stx - stp);
+    else if (stp > stx) stpc = stpmax;
+    else stpc = stpmin;
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      stpf = (fabs(stpc - stp) < fabs(stpq - stp)) ? stpc : stpq;
+      if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+      else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+    } else {
+      stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+      stpf = fmin(fmax(stpf, stpmin), stpmax);
+    }
+  } else {
+    if (brackt) {
+      theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+      s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
+      gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      p = (gamma - dp) + theta;
+      q = ((gamma - dp) + gamma) + dy;
+      r = p / q;
+      stpc = stp + r * (sty - stp);
+      stpf = stpc;
+    } else if (stp > stx) stpf = stpmax;
+    else stpf = stpmin;
+  }
+  if (fp > fx) {
+    sty = stp; fy = fp; dy = dp;
+  } else {
+    if (sgnd < 0) { sty = stx; fy = fx; dy = dx; }
+    stx = stp; fx = fp; dx = dp;
+  }
+  stp = stpf;
+}
+
+// ---- dcsrch as a resumable state machine (MINPACK-2; scipy/optimize/_dcsrch.py:_iterate)
+struct LbLineSearch {
+  double ftol, gtol, xtol, stpmin, stpmax;
+  bool brackt;
+  int stage;
+  double finit, ginit, gtest, width, width1, stx, fx, gx, sty, fy, gy, stmin, stmax;
+  enum Task { FG = 0, CONV = 1, WARN = 2, ERR = 3 };
+
+  PWB_HD int start(double& stp, double f, double g) {
+    if (stp < stpmin || stp > stpmax || g >= 0 || stpmax < stpmin) return ERR;
+    brackt = false; stage = 1; finit = f; ginit = g; gtest = ftol * ginit;
+    width = stpmax - stpmin; width1 = width / 0.5;
+    stx = 0; fx = finit; gx = ginit; sty = 0; fy = finit; gy = ginit;
+    stmin = 0; stmax = stp + 4.0 * stp;
+    return FG;
+  }
+  PWB_HD int iterate(double& stp, double f, double g) {
+    double ftest = finit + stp * gtest;
+    if (stage == 1 && f <= ftest && g >= 0) stage = 2;
+    int task = FG;
+    if (brackt && (stp <= stmin || stp >= stmax)) task = WARN;
+    if (brackt && stmax - stmin <= xtol * stmax) task = WARN;
+    if (stp == stpmax && f <= ftest && g <= gtest) task = WARN;
+    if (stp == stpmin && (f > ftest || g >= gtest)) task = WARN;
+    if (f <= ftest && fabs(g) <= gtol * -ginit) task = CONV;
+    if (task != FG) return task;
+    if (stage == 1 && f <= fx && f > ftest) {
+      double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
+      double gm = g - gtest, gxm = gx - gtest, gym = gy - gtest;
+      lb_dcstep(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
+      fx = fxm + stx * gtest; fy = fym + sty * gtest; gx = gxm + gtest; gy = gym + gtest;
+    } else {
+      lb_dcstep(stx, fx, gx, sty, fy, gy, stp, f, g, brackt, stmin, stmax);
+    }
+    if (brackt) {
+      if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
+      width1 = width;
+      width = fabs(sty - stx);
+    }
+    if (brackt) { stmin = fmin(stx, sty); stmax = fmax(stx, sty); }
+    else { stmin = stp + 1.1 * (stp - stx); stmax = stp + 4.0 * (stp - stx); }
+    stp = fmin(fmax(stp, stpmin), stpmax);
+    if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= xtol * stmax)) stp = stx;
+    return FG;
+  }
+};
+
+template <int N>
+struct LbHistory {
+  double S[LB_M][N], Y[LB_M][N];
+  int col, head;   // head = slot of the oldest pair
+};
+
+// B = theta*I, then BFGS updates with the stored pairs (oldest -> newest).
+template <int N>
+PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double (&B)[N][N]) {
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) B[i][j] = (i == j) ? theta : 0.0;
+  for (int k = 0; k < H.col; k++) {
+    int p = (H.head + k) % LB_M;
+    double Bs[N], sBs = 0, ys = 0;
+    for (int i = 0; i < N; i++) {
+      double a = 0;
+      for (int j = 0; j < N; j++) a += B[i][j] * H.S[p][j];
+      Bs[i] = a;
+    }
+    for (int i = 0; i < N; i++) { sBs += H.S[p][i] * Bs[i]; ys += H.Y[p][i] * H.S[p][i]; }
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] / ys - Bs[i] * Bs[j] / sBs;
+  }
+}
+
+// Solve A d = b for the leading nf x nf SPD system by Cholesky; false if not positive definite.
+template <int N>
+PWB_HD bool lb_spd_solve(int nf, double (&A)[N][N], double* b) {
+  double Lm[N][N];
+  for (int i = 0; i < nf; i++) {
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j];
+      for (int k = 0; k < j; k++) s -= Lm[i][k] * Lm[j][k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        Lm[i][i] = sqrt(s);
+      } else Lm[i][j] = s / Lm[j][j];
+    }
+  }
+  for (int i = 0; i < nf; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= Lm[i][k] * b[k];
+    b[i] = s / Lm[i][i];
+  }
+  for (int i = nf - 1; i >= 0; i--) {
+    double s = b[i];
+    for (int k = i + 1; k < nf; k++) s -= Lm[k][i] * b[k];
+    b[i] = s / Lm[i][i];
+  }
+  return true;
+}
+
+template <int N>
+PWB_HD double lb_projgr(const double* x, const double* g, const double* lo, const double* hi, const int* nbd) {
+  double sb = 0;
+  for (int i = 0; i < N; i++) {
+    double gi = g[i];
+    if (nbd[i] != 0) {
+      if (gi < 0) { if (nbd[i] >= 2) gi = fmax(x[i] - hi[i], gi); }
+      else { if (nbd[i] <= 2) gi = fmin(x[i] - lo[i], gi); }
+    }
+    sb = fmax(sb, fabs(gi));
+  }
+  return sb;
+}
+
+// Generalized Cauchy point along the projected steepest-descent path (cauchy in L-BFGS-B 3.0).
+template <int N>
+PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const int* nbd, const double* g,
+                      int* iwhere, const double (&B)[N][N], double theta, double sbgnrm, double* z) {
+  for (int i = 0; i < N; i++) z[i] = x[i];
+  if (sbgnrm <= 0) return;
+  bool bnded = true;
+  int nbreak = 0, nunb = 0;
+  double d[N], tb[N];
+  bool isb[N], fixed[N];
+  double f1 = 0;
+  for (int i = 0; i < N; i++) {
+    double neggi = -g[i], tl = 0, tu = 0;
+    isb[i] = false; fixed[i] = false; tb[i] = 0;
+    if (iwhere[i] != 3 && iwhere[i] != -1) {
+      if (nbd[i] <= 2) tl = x[i] - lo[i];
+      if (nbd[i] >= 2) tu = hi[i] - x[i];
+      bool xlower = nbd[i] <= 2 && tl <= 0, xupper = nbd[i] >= 2 && tu <= 0;
+      iwhere[i] = 0;
+      if (xlower) { if (neggi <= 0) iwhere[i] = 1; }
+      else if (xupper) { if (neggi >= 0) iwhere[i] = 2; }
+      else { if (fabs(neggi) <= 0) iwhere[i] = -3; }
+    }
+    if (iwhere[i] != 0 && iwhere[i] != -1) d[i] = 0;
+    else {
+      d[i] = neggi;
+      f1 -= neggi * neggi;
+      if (nbd[i] <= 2 && nbd[i] != 0 && neggi < 0) { isb[i] = true; tb[i] = tl / (-neggi); nbreak++; }
+      else if (nbd[i] >= 2 && neggi > 0) { isb[i] = true; tb[i] = tu / neggi; nbreak++; }
+      else { nunb++; if (fabs(neggi) > 0) bnded = false; }
+    }
+  }
+  if (nbreak == 0 && nunb == 0) return;
+  double f2_org = -theta * f1;
+  double f2 = 0;
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) f2 += d[i] * B[i][j] * d[j];
+  double dtm = -f1 / f2, tsum = 0;
+  if (nbreak > 0) {
+    int nleft = nbreak;
+    double tj = 0;
+    while (true) {
+      double tj0 = tj;
+      int ibp = -1;
+      for (int i = 0; i < N; i++)
+        if (isb[i] && (ibp < 0 || tb[i] < tb[ibp])) ibp = i;
+      tj = tb[ibp];
+      double dt = tj - tj0;
+      if (dtm < dt) break;
+      tsum += dt;
+      nleft--;
+      isb[ibp] = false;
+      double dibp = d[ibp];
+      d[ibp] = 0;
+      fixed[ibp] = true;
+      if (dibp > 0) { z[ibp] = hi[ibp]; iwhere[ibp] = 2; }
+      else { z[ibp] = lo[ibp]; iwhere[ibp] = 1; }
+      if (nleft == 0 && nbreak == N) return;   // every variable sits on a bound
+      double zz[N], Bz[N];
+      for (int i = 0; i < N; i++) zz[i] = fixed[i] ? z[i] - x[i] : tsum * d[i];
+      f1 = 0; f2 = 0;
+      for (int i = 0; i < N; i++) {
+        double a = 0, b = 0;
+        for (int j = 0; j < N; j++) { a += B[i][j] * zz[j]; b += B[i][j] * d[j]; }
+        Bz[i] = a;
+        f1 += d[i] * (g[i] + Bz[i]);
+        f2 += d[i] * b;
+      }
+      f2 = fmax(LB_EPSMCH * f2_org, f2);
+      if (nleft > 0) { dtm = -f1 / f2; continue; }
+      if (bnded) { f1 = 0; f2 = 0; dtm = 0; }
+      else dtm = -f1 / f2;
+      break;
+    }
+  }
+  if (dtm <= 0) dtm = 0;
+  tsum += dtm;
+  for (int i = 0; i < N; i++)
+    if (!fixed[i]) z[i] = x[i] + tsum * d[i];
+}
+
+// Subspace minimisation over the variables free at the Cauchy point (cmprlb + subsm, 3.0 projection).
+// Returns false if the reduced Hessian is not positive definite (caller refreshes the memory).
+template <int N>
+PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const double* hi, const int* nbd,
+                     const int* iwhere, const double (&B)[N][N], double* z) {
+  int ind[N], nf = 0;
+  for (int i = 0; i < N; i++) if (iwhere[i] <= 0) ind[nf++] = i;
+  if (nf == 0) return true;
+  double zx[N], rr[N], A[N][N];
+  for (int i = 0; i < N; i++) zx[i] = z[i] - x[i];
+  for (int a = 0; a < nf; a++) {
+    int i = ind[a];
+    double s = g[i];
+    for (int j = 0; j < N; j++) s += B[i][j] * zx[j];
+    rr[a] = -s;
+    for (int b = 0; b < nf; b++) A[a][b] = B[i][ind[b]];
+  }
+  if (!lb_spd_solve<N>(nf, A, rr)) return false;   // rr now holds d on the free set
+  double xp[N];
+  for (int i = 0; i < N; i++) xp[i] = z[i];
+  bool iword = false;
+  for (int a = 0; a < nf; a++) {
+    int k = ind[a];
+    double dk = rr[a], xk = z[k];
+    if (nbd[k] != 0) {
+      if (nbd[k] == 1) { z[k] = fmax(lo[k], xk + dk); if (z[k] == lo[k]) iword = true; }
+      else if (nbd[k] == 2) {
+        xk = fmax(lo[k], xk + dk); z[k] = fmin(hi[k], xk);
+        if (z[k] == lo[k] || z[k] == hi[k]) iword = true;
+      } else { z[k] = fmin(hi[k], xk + dk); if (z[k] == hi[k]) iword = true; }
+    } else z[k] = xk + dk;
+  }
+  if (!iword) return true;
+  double ddp = 0;
+  for (int i = 0; i < N; i++) ddp += (z[i] - x[i]) * g[i];
+  if (ddp > 0) {
+    for (int i = 0; i < N; i++) z[i] = xp[i];
+    double alpha = 1, temp1 = 1;
+    int ibd = -1;
+    for (int a = 0; a < nf; a++) {
+      int k = ind[a];
+      double dk = rr[a];
+      if (nbd[k] != 0) {
+        if (dk < 0 && nbd[k] <= 2) {
+          double t2 = lo[k] - z[k];
+          if (t2 >= 0) temp1 = 0; else if (dk * alpha < t2) temp1 = t2 / dk;
+        } else if (dk > 0 && nbd[k] >= 2) {
+          double t2 = hi[k] - z[k];
+          if (t2 <= 0) temp1 = 0; else if (dk * alpha > t2) temp1 = t2 / dk;
+        }
+        if (temp1 < alpha) { alpha = temp1; ibd = a; }
+      }
+    }
+    if (alpha < 1 && ibd >= 0) {
+      double dk = rr[ibd];
+      int k = ind[ibd];
+      if (dk > 0) { z[k] = hi[k]; rr[ibd] = 0; }
+      else if (dk < 0) { z[k] = lo[k]; rr[ibd] = 0; }
+    }
+    for (int a = 0; a < nf; a++) z[ind[a]] += alpha * rr[a];
+  }
+  return true;
+}
+
+// Obj must provide:  void fg(const double* x, double& f, double* g);
+// (f and the bound-aware forward-difference gradient; on device it is warp-cooperative and every
+// lane runs this routine redundantly with identical data, so control flow is warp-uniform.)
+template <int N, class Obj>
+PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd,
+                            double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out) {
+  double g[N], f;
+  int iwhere[N];
+  bool cnstnd = false, boxed = true;
+  for (int i = 0; i < N; i++) {
+    if (nbd[i] > 0) {
+      if (nbd[i] <= 2 && x[i] <= lo[i]) { if (x[i] < lo[i]) x[i] = lo[i]; }
+      else if (nbd[i] >= 2 && x[i] >= hi[i]) { if (x[i] > hi[i]) x[i] = hi[i]; }
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    if (nbd[i] != 2) boxed = false;
+    if (nbd[i] == 0) iwhere[i] = -1;
+    else { cnstnd = true; iwhere[i] = (nbd[i] == 2 && hi[i] - lo[i] <= 0) ? 3 : 0; }
+  }
+  obj.fg(x, f, g);
+  double sbgnrm = lb_projgr<N>(x, g, lo, hi, nbd);
+  int iter = 0, status = LB_MAXITER;
+  LbHistory<N> H;
+  H.col = 0; H.head = 0;
+  double theta = 1.0;
+  if (sbgnrm <= pgtol) { *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }
+
+  double z[N], d[N], t[N], r[N], B[N][N];
+  while (true) {
+    lb_build_B<N>(H, theta, B);
+    if (!cnstnd && H.col > 0) { for (int i = 0; i < N; i++) z[i] = x[i]; }
+    else lb_cauchy<N>(x, lo, hi, nbd, g, iwhere, B, theta, sbgnrm, z);
+    int nfree = 0;
+    for (int i = 0; i < N; i++) if (iwhere[i] <= 0) nfree++;
+    if (nfree != 0 && H.col != 0) {
+      if (!lb_subsm<N>(x, g, lo, hi, nbd, iwhere, B, z)) { H.col = 0; H.head = 0; theta = 1.0; continue; }
+    }
+    // ---- line search (lnsrlb)
+    double dtd = 0;
+    for (int i = 0; i < N; i++) { d[i] = z[i] - x[i]; dtd += d[i] * d[i]; }
+    double dnorm = sqrt(dtd), stpmx = 1e10;
+    if (cnstnd) {
+      if (iter == 0) stpmx = 1.0;
+      else {
+        for (int i = 0; i < N; i++) {
+          double a1 = d[i];
+          if (nbd[i] != 0) {
+            if (a1 < 0 && nbd[i] <= 2) {
+              double a2 = lo[i] - x[i];
+              if (a2 >= 0) stpmx = 0; else if (a1 * stpmx < a2) stpmx = a2 / a1;
+            } else if (a1 > 0 && nbd[i] >= 2) {
+              double a2 = hi[i] - x[i];
+              if (a2 <= 0) stpmx = 0; else if (a1 * stpmx > a2) stpmx = a2 / a1;
+            }
+          }
+        }
+      }
+    }
+    double stp = (iter == 0 && !boxed) ? fmin(1.0 / dnorm, stpmx) : 1.0;
+    for (int i = 0; i < N; i++) { t[i] = x[i]; r[i] = g[i]; }
+    double fold = f, gd = 0, gdold = 0;
+    int ifun = 0, iback = 0, info = 0;
+    LbLineSearch ls;
+    ls.ftol = 1e-3; ls.gtol = 0.9; ls.xtol = 0.1; ls.stpmin = 0; ls.stpmax = stpmx;
+    bool started = false, newx = false;
+    while (true) {
+      gd = 0;
+      for (int i = 0; i < N; i++) gd += g[i] * d[i];
+      if (ifun == 0) {
+        gdold = gd;
+        if (gd >= 0) { info = -4; break; }
+      }
+      int task;
+      if (!started) { task = ls.start(stp, f, gd); started = true; }
+      else task = ls.iterate(stp, f, gd);
+      if (task == LbLineSearch::CONV || task == LbLineSearch::WARN) { newx = true; break; }
+      ifun++;
+      iback = ifun - 1;
+      if (stp == 1.0) { for (int i = 0; i < N; i++) x[i] = z[i]; }
+      else { for (int i = 0; i < N; i++) x[i] = stp * d[i] + t[i]; }
+      if (iback >= maxls) break;
+      obj.fg(x, f, g);
+    }
+    if (!newx) {
+      for (int i = 0; i < N; i++) { x[i] = t[i]; g[i] = r[i]; }
+      f = fold;
+      if (H.col == 0) { status = LB_ABNORMAL; iter++; break; }
+      H.col = 0; H.head = 0; theta = 1.0;
+      (void)info;
+      continue;
+    }
+    iter++;
+    sbgnrm = lb_projgr<N>(x, g, lo, hi, nbd);
+    if (sbgnrm <= pgtol) { status = LB_CONV_PGTOL; break; }
+    double ddum = fmax(fmax(fabs(fold), fabs(f)), 1.0);
+    if ((fold - f) <= ftol * ddum) { status = LB_CONV_FTOL; break; }
+    if (iter >= maxiter) { status = LB_MAXITER; break; }
+    double rr = 0, dr;
+    for (int i = 0; i < N; i++) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
+    if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+    else {
+      dr = (gd - gdold) * stp;
+      for (int i = 0; i < N; i++) d[i] *= stp;
+      ddum = -gdold * stp;
+    }
+    if (dr <= LB_EPSMCH * ddum) continue;       // skip the BFGS update
+    int slot;
+    if (H.col < LB_M) { slot = (H.head + H.col) % LB_M; H.col++; }
+    else { slot = H.head; H.head = (H.head + 1) % LB_M; }
+    for (int i = 0; i < N; i++) { H.S[slot][i] = d[i]; H.Y[slot][i] = r[i]; }
+    theta = rr / dr;
+  }
+  *f_out = f;
+  *nit_out = iter;
+  return status;
+}
+
+}  // namespace pwb
