@@ -1,0 +1,160 @@
+/* pwb.h -- C ABI of libpwb.so: B200 (sm_100a) kernels for pywindow's per-frame pore-geometry path.
+ *
+ * The reference (marcinmiklitz/pywindow) is pure Python and has no FFI layer; the seam this library
+ * plugs into is the Python function boundary between `pywindow/_internal/molecular.py` (callers) and
+ * `pywindow/_internal/utilities.py` (geometry functions), see molecular.py:29-44, and the per-frame
+ * loop of `Trajectory.analysis` (trajectory.py:473-586).  Each entry point below names the
+ * reference function(s) it replaces.  All pointers in `pwb_batch` are DEVICE pointers unless the
+ * entry point says "host"; the caller owns every buffer (inputs, workspace, outputs); the library
+ * keeps no global state except the explicit context.  Every call is asynchronous on `stream`
+ * except the `_host` variant, which synchronises the stream before returning.
+ *
+ * A "batch" is F independent items (one molecule in one frame each).  Item i owns atoms
+ * [item_off[i], item_off[i+1]) of `coords`.  Atoms carry a small integer *type* (one per element);
+ * per-type van-der-Waals radius / mass tables replace the reference's per-atom dict lookups
+ * (tables.py:22-197).  If `shared_types` != 0 every item has the same atom order and
+ * `atom_type` has max_atoms entries (trajectory of one molecule); otherwise it is indexed like
+ * `coords` (one entry per atom of the batch).
+ */
+#ifndef PWB_H
+#define PWB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWB_ABI_VERSION 1
+#define PWB_MAX_TYPES 16
+
+/* ---- result record: `rec_stride` doubles per item (>= PWB_REC_WIN0 + 4*win_cap) --------------- */
+enum {
+  PWB_REC_STATUS = 0,    /* bit flags PWB_ST_* stored as a double                                */
+  PWB_REC_NATOMS = 1,    /* properties["no_of_atoms"]                         molecular.py:131   */
+  PWB_REC_COM = 2,       /* [3] centre_of_mass                                utilities.py:127   */
+  PWB_REC_MAXD = 5,      /* maximum_diameter.diameter                         utilities.py:355   */
+  PWB_REC_MAXD_A1 = 6,   /* maximum_diameter.atom_1                                              */
+  PWB_REC_MAXD_A2 = 7,   /* maximum_diameter.atom_2                                              */
+  PWB_REC_AVGD = 8,      /* average_diameter                                  utilities.py:1586  */
+  PWB_REC_PORE_D = 9,    /* pore_diameter.diameter                            utilities.py:375   */
+  PWB_REC_PORE_ATOM = 10,
+  PWB_REC_OPT_D = 11,    /* pore_diameter_opt.diameter                        utilities.py:400   */
+  PWB_REC_OPT_ATOM = 12,
+  PWB_REC_OPT_C = 13,    /* [3] pore_diameter_opt.centre_of_mass                                 */
+  PWB_REC_NRAYS = 16,    /* number of sampling rays P                         utilities.py:1409  */
+  PWB_REC_NCLEAR = 17,   /* rays that reach the sampling sphere unobstructed                     */
+  PWB_REC_NWIN = 18,     /* clusters (= window slots used)                    utilities.py:1478  */
+  PWB_REC_EPS = 19,      /* DBSCAN eps                                        utilities.py:1434  */
+  PWB_REC_OPT_NIT = 20,  /* L-BFGS-B iterations of the pore-centre search                        */
+  PWB_REC_OPT_STOP = 21, /* its stop reason (0 pgtol, 1 ftol, 2 line search, 3 maxiter)          */
+  PWB_REC_RADIUS = 22,   /* sampling-sphere radius used for windows                              */
+  PWB_REC_NSURV = 23,    /* rays that survive the line-sphere pre-test                           */
+  PWB_REC_WIN0 = 24      /* then win_cap x {diameter, cx, cy, cz}; diameter NaN = window dropped */
+};
+
+enum {
+  PWB_ST_OPT_BOUNDS = 1,     /* pore_diameter(COM) < 0: reference raises ValueError (scipy bounds)  */
+  PWB_ST_NO_CLEAR_RAY = 2,   /* find_windows returns None                      utilities.py:1473    */
+  PWB_ST_RAY_CAP = 4,        /* P > ray_cap: windows not analysed, enlarge ray_cap                  */
+  PWB_ST_WIN_CAP = 8,        /* more clusters than win_cap                                          */
+  PWB_ST_WIN_DROPPED = 16,   /* a window's 0.1 A rescan was obstructed         utilities.py:1226    */
+  PWB_ST_WIN_NEGATIVE = 32,  /* a window diameter < 0 (reference warns)        utilities.py:1546    */
+  PWB_ST_BAD_ITEM = 64       /* too many atoms / unknown type                                        */
+};
+
+/* stages (bit mask for pwb_batch.stages) */
+enum {
+  PWB_STAGE_SCALARS = 1,  /* COM, max_dim, pore_diameter                                          */
+  PWB_STAGE_AVGD = 2,     /* find_average_diameter                                                */
+  PWB_STAGE_OPT = 4,      /* opt_pore_diameter                                                    */
+  PWB_STAGE_RAYS = 8,     /* ray pre-test + path clearance (HOT LOOP 1 of find_windows)           */
+  PWB_STAGE_CLUSTER = 16, /* eps + DBSCAN + per-cluster arg-max ray                               */
+  PWB_STAGE_WINDOWS = 32, /* window_analysis per cluster (HOT LOOP 2)                             */
+  PWB_STAGE_ALL = 63
+};
+
+typedef struct pwb_ctx pwb_ctx; /* per-device context: k-NN/eps table for the golden-spiral ray sets */
+
+typedef struct pwb_batch {
+  /* sizes */
+  int32_t n_items;      /* F                                                                      */
+  int32_t max_atoms;    /* max atoms of any item (sizes shared memory)                            */
+  int32_t n_types;      /* <= PWB_MAX_TYPES                                                       */
+  int32_t shared_types; /* see above                                                              */
+  int32_t ray_cap;      /* capacity of per-item ray lists (>= largest P)                          */
+  int32_t win_cap;      /* window slots per record                                                */
+  int32_t rec_stride;   /* doubles per record                                                     */
+  int32_t stages;       /* PWB_STAGE_* mask                                                       */
+  /* parameters of find_windows / find_average_diameter (utilities.py:1364-1371, :1586-1591)      */
+  double adjust;        /* default 1.0                                                            */
+  double increment;     /* default 1.0                                                            */
+  double increment2;    /* default 0.1 (window_analysis)                                          */
+  int32_t pore_opt;     /* default 1                                                              */
+  int32_t total_atoms;  /* atoms in the whole batch = item_off[F]                               */
+  /* inputs */
+  const double* coords;      /* [total_atoms][3] float64                                          */
+  const int32_t* item_off;   /* [F+1]                                                             */
+  const int32_t* atom_type;  /* see shared_types                                                  */
+  const double* type_vdw;    /* [n_types]                                                         */
+  const double* type_mass;   /* [n_types]                                                         */
+  const double* centre_override; /* optional [F][3]: use instead of optimising (teacher forcing)  */
+  /* outputs / scratch */
+  double* records;           /* [F][rec_stride]                                                   */
+  void* workspace;           /* pwb_workspace_bytes() bytes                                       */
+  size_t workspace_bytes;
+} pwb_batch;
+
+/* layout of the per-item lists inside the workspace, for stage-wise tests */
+typedef struct pwb_ws_layout {
+  size_t atoms;      /* double[total_atoms_cap][4]: type-bucketed x,y,z,r_vdw                     */
+  size_t atom_idx;   /* int32[total_atoms_cap]: original index of each bucketed atom              */
+  size_t item_d;     /* double[F][16]                                                             */
+  size_t item_i;     /* int32[F][32]                                                              */
+  size_t clear_k;    /* int32[F][ray_cap]: ray index of each clear ray (ascending)                */
+  size_t clear_pos;  /* int32[F][ray_cap]: path step of the narrowest point                       */
+  size_t clear_a2;   /* double[F][ray_cap]: 2*min clearance along the ray (column 1 of the record)*/
+  size_t labels;     /* int32[F][ray_cap]: DBSCAN label of each clear ray                         */
+  size_t win_k;      /* int32[F][win_cap]: arg-max ray of each cluster                            */
+  size_t total;
+} pwb_ws_layout;
+
+int pwb_abi_version(void);
+const char* pwb_last_error(void);
+
+int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap);
+int pwb_ctx_destroy(pwb_ctx* ctx);
+
+/* bytes of workspace for a batch of n_items with total_atoms atoms */
+size_t pwb_workspace_bytes(int n_items, int total_atoms, int ray_cap, int win_cap);
+int pwb_workspace_layout(int n_items, int total_atoms, int ray_cap, int win_cap, pwb_ws_layout* out);
+
+/* upper bound of the ray count any item of the batch can need (bounding-box bound on max_dim);
+ * synchronises `stream`.  Replaces nothing in the reference: it sizes `ray_cap`.                  */
+int pwb_ray_capacity(pwb_ctx* ctx, const pwb_batch* b, void* stream, int* out_cap);
+
+/* stage entry points; each runs the stage named in its comment on the whole batch.                */
+int pwb_frame_scalars(pwb_ctx*, const pwb_batch*, void* stream);    /* center_of_mass :127, max_dim :355, pore_diameter :375 */
+int pwb_average_diameter(pwb_ctx*, const pwb_batch*, void* stream); /* find_average_diameter :1586 + vector_analysis_reversed :1556 */
+int pwb_opt_pore(pwb_ctx*, const pwb_batch*, void* stream);         /* opt_pore_diameter :400 */
+int pwb_ray_search(pwb_ctx*, const pwb_batch*, void* stream);       /* vector_preanalysis :1132 + vector_analysis :1100 over the ray set :1398-1423 */
+int pwb_cluster(pwb_ctx*, const pwb_batch*, void* stream);          /* eps :1427-1434 + DBSCAN :1478 + arg-max ray :1221 */
+int pwb_window_refine(pwb_ctx*, const pwb_batch*, void* stream);    /* window_analysis :1191 */
+
+/* Molecule.full_analysis (molecular.py:156-202) for every item: runs the stages in b->stages.     */
+int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
+
+/* Same, but `coords` and `records` are HOST pointers (pinned or pageable); `d_coords` is a device
+ * staging buffer of total_atoms*3 doubles and `d_records` one of F*rec_stride doubles (caller
+ * owned).  Copies in, analyses, copies the records out and synchronises `stream`.  This is what
+ * the per-frame loop of Trajectory.analysis (trajectory.py:473-586) binds to.                      */
+int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
+                           double* d_coords, double* d_records, int total_atoms, void* stream);
+
+/* number of kernel launches issued by this library since the context was created */
+long long pwb_launch_count(pwb_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

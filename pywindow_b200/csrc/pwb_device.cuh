@@ -1,0 +1,179 @@
+// Device helpers shared by the pore-geometry kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pwb.h"
+#include "lbfgsb_small.cuh"
+#include "neldermead2.cuh"
+
+namespace pwb {
+
+constexpr int ITEM_D = 16;   // doubles of per-item scratch
+constexpr int ITEM_I = 32;   // ints of per-item scratch
+// item_d slots
+constexpr int D_COM = 0, D_MAXD = 3, D_CENTRE = 4, D_RADIUS = 7, D_EPS = 8, D_ICOM = 9, D_SHIFT = 12;
+// item_i slots
+constexpr int I_STATUS = 0, I_P = 1, I_NSURV = 2, I_NCLEAR = 3, I_NWIN = 4, I_N = 5, I_CLS0 = 6;  // cls_start[17]
+
+constexpr double PWB_INF = 1e300;
+constexpr double GOLDEN_ANGLE = 2.399963229728653;  // pi*(3-sqrt(5)), utilities.py:1412
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// Python / numpy float floor division (fmod based), used for `norm // increment` utilities.py:1108
+__device__ __forceinline__ double py_floordiv(double a, double b) {
+  double mod = fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0.0 && ((b < 0) != (mod < 0))) div -= 1.0;
+  if (div != 0.0) {
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+  }
+  return 0.0;
+}
+
+// number of golden-spiral sampling points, utilities.py:1399-1409
+__device__ __forceinline__ int n_sampling_points(double radius, double adjust) {
+  // reference: 4*pi*r**2 -> (4*pi)*(r*r)
+  double area = __dmul_rn(4.0 * 3.141592653589793, __dmul_rn(radius, radius));
+  double v = __dmul_rn(__dmul_rn(log10(area), 250.0), adjust);
+  return (int)v;
+}
+
+// point k of the P-point golden spiral scaled to radius R, utilities.py:1412-1423 (numpy linspace
+// semantics: z_k = k*step + start with separate roundings, last element = stop exactly)
+__device__ __forceinline__ void spiral_point(int k, int P, double R, double& px, double& py, double& pz) {
+  double invP = 1.0 / (double)P;
+  double start = 1.0 - invP, stop = invP - 1.0;
+  double step = (stop - start) / (double)(P - 1);
+  double z = (k == P - 1 && P > 1) ? stop : __dadd_rn(__dmul_rn((double)k, step), start);
+  double rad = sqrt(__dadd_rn(1.0, -__dmul_rn(z, z)));
+  double s, c;
+  sincos(__dmul_rn(GOLDEN_ANGLE, (double)k), &s, &c);
+  px = __dmul_rn(__dmul_rn(rad, c), R);
+  py = __dmul_rn(__dmul_rn(rad, s), R);
+  pz = __dmul_rn(z, R);
+}
+
+// ---- (value, index) reductions with first-occurrence tie-breaks --------------------------------
+struct ValIdx { double v; int i; };
+__device__ __forceinline__ ValIdx vi_min(ValIdx a, ValIdx b) {   // smaller v, then smaller i
+  return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ValIdx vi_max(ValIdx a, ValIdx b) {   // larger v, then smaller i
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ValIdx warp_vi_min(ValIdx a) {
+  for (int m = 16; m; m >>= 1) {
+    ValIdx b; b.v = shfl_xor_d(a.v, m); b.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+    a = vi_min(a, b);
+  }
+  return a;
+}
+__device__ __forceinline__ ValIdx warp_vi_max(ValIdx a) {
+  for (int m = 16; m; m >>= 1) {
+    ValIdx b; b.v = shfl_xor_d(a.v, m); b.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+    a = vi_max(a, b);
+  }
+  return a;
+}
+__device__ __forceinline__ double warp_sum(double a) {
+  for (int m = 16; m; m >>= 1) a += shfl_xor_d(a, m);
+  return a;
+}
+__device__ __forceinline__ double warp_min(double a) {
+  for (int m = 16; m; m >>= 1) a = fmin(a, shfl_xor_d(a, m));
+  return a;
+}
+
+// block-wide reductions (blockDim.x multiple of 32, <= 1024); `red` is >= 32 entries of scratch
+__device__ __forceinline__ double block_sum(double a, double* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  a = warp_sum(a);
+  __syncthreads();
+  if (lane == 0) red[w] = a;
+  __syncthreads();
+  double t = 0;
+  for (int k = 0; k < nw; k++) t += red[k];
+  return t;
+}
+__device__ __forceinline__ ValIdx block_vi(ValIdx a, bool want_max, double* redv, int* redi) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  a = want_max ? warp_vi_max(a) : warp_vi_min(a);
+  __syncthreads();
+  if (lane == 0) { redv[w] = a.v; redi[w] = a.i; }
+  __syncthreads();
+  ValIdx t; t.v = redv[0]; t.i = redi[0];
+  for (int k = 1; k < nw; k++) {
+    ValIdx b; b.v = redv[k]; b.i = redi[k];
+    t = want_max ? vi_max(t, b) : vi_min(t, b);
+  }
+  return t;
+}
+
+// ---- type-bucketed atoms in shared memory -------------------------------------------------------
+// Atoms of one item sorted (stably) by type so that min_i(|x_i-q| - r_i) = min_c(sqrt(min_{i in c}
+// |x_i-q|^2) - r_c): the inner loop has no sqrt and the result is bit-identical because sqrt is
+// monotone.
+struct Bucketed {
+  const double* x; const double* y; const double* z;   // [n] shifted coordinates
+  const int* cls;                                      // [ncls+1] class starts
+  const double* cr;                                    // [ncls] class radius
+  int ncls;
+};
+
+__device__ __forceinline__ double min_clearance(const Bucketed& A, double qx, double qy, double qz) {
+  double best = PWB_INF;
+  for (int c = 0; c < A.ncls; c++) {
+    int b = A.cls[c], e = A.cls[c + 1];
+    if (b == e) continue;
+    double m = PWB_INF;
+    for (int i = b; i < e; i++) {
+      double dx = A.x[i] - qx, dy = A.y[i] - qy, dz = A.z[i] - qz;
+      double d2 = dx * dx + dy * dy + dz * dz;
+      m = fmin(m, d2);
+    }
+    best = fmin(best, sqrt(m) - A.cr[c]);
+  }
+  return best;
+}
+
+// ---- warp-cooperative pore objective (lanes stride over atoms) ---------------------------------
+struct WarpAtoms {
+  const double* x; const double* y; const double* z; const double* r;
+  int n, lane;
+};
+
+template <int K>
+__device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double* px, const double* py,
+                                               const double* pz, double* out) {
+  double m[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) m[k] = PWB_INF;
+  for (int i = A.lane; i < A.n; i += 32) {
+    double ax = A.x[i], ay = A.y[i], az = A.z[i], ar = A.r[i];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
+      m[k] = fmin(m[k], sqrt(dx * dx + dy * dy + dz * dz) - ar);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = warp_min(m[k]);
+}
+
+// pore_diameter with first-occurrence argmin over ORIGINAL atom indices (utilities.py:375-388)
+__device__ __forceinline__ ValIdx warp_pore_argmin(const WarpAtoms& A, const int* orig, double cx, double cy, double cz) {
+  ValIdx b; b.v = PWB_INF; b.i = 0x7fffffff;
+  for (int i = A.lane; i < A.n; i += 32) {
+    double dx = A.x[i] - cx, dy = A.y[i] - cy, dz = A.z[i] - cz;
+    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i]; c.i = orig[i];
+    b = vi_min(b, c);
+  }
+  return warp_vi_min(b);
+}
+
+}  // namespace pwb

@@ -1,0 +1,939 @@
+// pwb_kernels.cu -- sm_100a kernels for pywindow's per-frame pore-geometry path.
+//
+// One batch = F independent molecule-frames.  Stage kernels (all float64 in this revision):
+//   k_prepare   CTA/item  : type-bucket atoms, centre of mass, pore diameter, max dimension,
+//                           average diameter                    (utilities.py:127,355,375,1586)
+//   k_opt_pore  warp/item : pore-centre search (L-BFGS-B)       (utilities.py:400)
+//   k_rays      CTA/item  : golden-spiral ray pre-test + stepped path clearance
+//                                                               (utilities.py:1132,1100,1398-1470)
+//   k_knn_fill  CTA/P     : mean 10-NN distance of the unit P-point spiral (eps table, :1427-1434)
+//   k_cluster   CTA/item  : DBSCAN of clear rays + arg-max ray per cluster (:1478, :1221)
+//   k_windows   warp/(item,window): window_analysis            (utilities.py:1191)
+#include <stdio.h>
+
+#include "pwb_device.cuh"
+
+namespace pwb {
+
+struct Ws {   // resolved workspace pointers
+  double* atoms;   // [total][4]
+  int* atom_idx;   // [total]
+  double* item_d;  // [F][ITEM_D]
+  int* item_i;     // [F][ITEM_I]
+  int* clear_k;    // [F][ray_cap]
+  int* clear_pos;
+  double* clear_a2;
+  int* labels;
+  int* win_k;      // [F][win_cap]
+};
+
+struct Ctx {
+  int device;
+  int table_cap;
+  double* knn_unit;  // [table_cap] mean 10-NN distance on the unit sphere, 0 = not computed
+  int* knn_need;     // [table_cap]
+  long long launches;
+};
+
+// =================================================================================================
+// k_prepare
+// =================================================================================================
+constexpr int PREP_THREADS = 256;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prepare(pwb_batch b, Ws ws, int do_avg) {
+  extern __shared__ double sm[];
+  const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int off = b.item_off[item];
+  const int n = b.item_off[item + 1] - off;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  const int NA = b.max_atoms;
+  double* sx = sm;            // original order
+  double* sy = sx + NA;
+  double* sz = sy + NA;
+  double* sr = sz + NA;
+  double* sw = sr + NA;       // mass, later scratch
+  double* red = sw + NA;      // 64 doubles
+  int* redi = (int*)(red + 64);     // 64 ints
+  int* stype = redi + 64;           // [NA]
+  int* cnt = stype + NA;            // [PWB_MAX_TYPES + 1]
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
+  for (int c = tid; c <= PWB_MAX_TYPES; c += nt) cnt[c] = 0;
+  __syncthreads();
+  if (n <= 0 || n > NA) {
+    if (tid == 0) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
+    return;
+  }
+  const int* tp = b.atom_type + (b.shared_types ? 0 : off);
+  for (int a = tid; a < n; a += nt) {
+    const double* p = b.coords + (size_t)(off + a) * 3;
+    sx[a] = p[0]; sy[a] = p[1]; sz[a] = p[2];
+    int t = tp[a];
+    if (t < 0 || t >= b.n_types) { s_bad = 1; t = 0; }
+    stype[a] = t;
+    sr[a] = b.type_vdw[t];
+    sw[a] = b.type_mass[t];
+    atomicAdd(&cnt[t + 1], 1);
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
+    return;
+  }
+  if (tid == 0) {
+    for (int c = 1; c <= PWB_MAX_TYPES; c++) cnt[c] += cnt[c - 1];   // cnt[c] = start of class c
+    for (int c = 0; c <= PWB_MAX_TYPES; c++) iiv[I_CLS0 + c] = cnt[c < b.n_types ? c : b.n_types];
+    iiv[I_N] = n;
+    iiv[I_STATUS] = 0;
+  }
+  __syncthreads();
+  // stable bucket scatter to the workspace (x, y, z, r) + original index
+  for (int a = tid; a < n; a += nt) {
+    int t = stype[a], rank = 0;
+    for (int j = 0; j < a; j++) rank += (stype[j] == t);
+    int pos = cnt[t] + rank;
+    double* q = ws.atoms + (size_t)(off + pos) * 4;
+    q[0] = sx[a]; q[1] = sy[a]; q[2] = sz[a]; q[3] = sr[a];
+    ws.atom_idx[off + pos] = a;
+  }
+  // ---- centre of mass (utilities.py:127-148)
+  double mx = 0, my = 0, mz = 0, mt = 0;
+  for (int a = tid; a < n; a += nt) { double m = sw[a]; mx += sx[a] * m; my += sy[a] * m; mz += sz[a] * m; mt += m; }
+  mx = block_sum(mx, red); my = block_sum(my, red); mz = block_sum(mz, red); mt = block_sum(mt, red);
+  const double cx = mx / mt, cy = my / mt, cz = mz / mt;
+  // ---- pore diameter at the centre of mass (utilities.py:375-388)
+  ValIdx pb; pb.v = PWB_INF; pb.i = 0x7fffffff;
+  for (int a = tid; a < n; a += nt) {
+    double dx = sx[a] - cx, dy = sy[a] - cy, dz = sz[a] - cz;
+    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - sr[a]; c.i = a;
+    pb = vi_min(pb, c);
+  }
+  pb = block_vi(pb, false, red, redi);
+  // ---- maximum dimension (utilities.py:355-372): upper triangle incl. diagonal, first arg-max
+  ValIdx mb; mb.v = -PWB_INF; mb.i = 0x7fffffff;
+  for (int p = tid; p < n * n; p += nt) {
+    int i = p / n, j = p - i * n;
+    if (j < i) continue;
+    double dx = sx[i] - sx[j], dy = sy[i] - sy[j], dz = sz[i] - sz[j];
+    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) + (sr[i] + sr[j]); c.i = p;
+    mb = vi_max(mb, c);
+  }
+  mb = block_vi(mb, true, red, redi);
+  const double D = mb.v;
+  if (tid == 0) {
+    rec[PWB_REC_STATUS] = 0;
+    rec[PWB_REC_NATOMS] = n;
+    rec[PWB_REC_COM] = cx; rec[PWB_REC_COM + 1] = cy; rec[PWB_REC_COM + 2] = cz;
+    rec[PWB_REC_MAXD] = D; rec[PWB_REC_MAXD_A1] = mb.i / n; rec[PWB_REC_MAXD_A2] = mb.i % n;
+    rec[PWB_REC_PORE_D] = 2.0 * pb.v; rec[PWB_REC_PORE_ATOM] = pb.i;
+    idv[D_COM] = cx; idv[D_COM + 1] = cy; idv[D_COM + 2] = cz; idv[D_MAXD] = D;
+  }
+  if (!do_avg) return;
+  // ---- average diameter (utilities.py:1586-1650, :1556-1583): sphere radius = D (not D/2)
+  __syncthreads();
+  double ox = 0, oy = 0, oz = 0;
+  for (int a = tid; a < n; a += nt) {
+    sx[a] -= cx; sy[a] -= cy; sz[a] -= cz;          // shift_com with com_adjust = 0
+    ox += sx[a]; oy += sy[a]; oz += sz[a];
+  }
+  ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
+  for (int a = tid; a < n; a += nt) {
+    double lx = sx[a] - ox, ly = sy[a] - oy, lz = sz[a] - oz;
+    sx[a] = lx; sy[a] = ly; sz[a] = lz;
+    sw[a] = lx * lx + ly * ly + lz * lz;            // |L|^2
+    sr[a] = sr[a] * sr[a];                          // r^2
+  }
+  __syncthreads();
+  const int P = n_sampling_points(D, b.adjust);
+  double acc = 0, hits = 0;
+  for (int k = tid; k < P; k += nt) {
+    double px, py, pz;
+    spiral_point(k, P, D, px, py, pz);
+    double nr = sqrt(px * px + py * py + pz * pz);
+    double nx = px / nr, ny = py / nr, nz = pz / nr;
+    double far = -1.0;
+    for (int a = 0; a < n; a++) {
+      double t = sx[a] * nx + sy[a] * ny + sz[a] * nz;
+      double q = sw[a] - t * t;                     // d^2 (reference takes sqrt, NaN if < 0)
+      double under = sr[a] - q;
+      if (q >= 0 && under > 0) {
+        double h = sqrt(under);
+        double t0 = t - h, t1 = t + h;
+        double ax = ox + t0 * nx, ay = oy + t0 * ny, az = oz + t0 * nz;
+        double bx = ox + t1 * nx, by = oy + t1 * ny, bz = oz + t1 * nz;
+        double n0 = sqrt(ax * ax + ay * ay + az * az), n1 = sqrt(bx * bx + by * by + bz * bz);
+        if (n0 < n1) far = fmax(far, n1);
+      }
+    }
+    if (far >= 0) { acc += far; hits += 1.0; }
+  }
+  acc = block_sum(acc, red); hits = block_sum(hits, red);
+  if (tid == 0) rec[PWB_REC_AVGD] = 2.0 * (acc / hits);
+}
+
+// =================================================================================================
+// k_opt_pore
+// =================================================================================================
+constexpr int OPT_WARPS = 4;
+
+struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-point differences
+  WarpAtoms A; const double* lo; const double* hi; const int* nbd;
+  __device__ void fg(const double* x, double& f, double* g) {
+    double px[4], py[4], pz[4], h[3], m[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], nbd[i], lo[i], hi[i]);
+    px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
+    warp_min_clear<4>(A, px, py, pz, m);
+    f = -(m[0] * 2.0);
+#pragma unroll
+    for (int i = 0; i < 3; i++) g[i] = (-(m[i + 1] * 2.0) - f) / ((x[i] + h[i]) - x[i]);
+  }
+};
+
+__global__ void __launch_bounds__(OPT_WARPS * 32)
+k_opt_pore(pwb_batch b, Ws ws) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int item = blockIdx.x * OPT_WARPS + w;
+  if (item >= b.n_items) return;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
+  const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
+  double* x = sm + (size_t)w * NA * 4;
+  double* y = x + NA; double* z = y + NA; double* r = z + NA;
+  for (int a = lane; a < n; a += 32) {
+    const double* q = ws.atoms + (size_t)(off + a) * 4;
+    x[a] = q[0]; y[a] = q[1]; z[a] = q[2]; r[a] = q[3];
+  }
+  __syncwarp();
+  WarpAtoms A{x, y, z, r, n, lane};
+  const int* orig = ws.atom_idx + off;
+  double c[3] = {idv[D_COM], idv[D_COM + 1], idv[D_COM + 2]};
+  double fopt = 0; int nit = 0, st = 0;
+  if (b.centre_override) {
+    const double* o = b.centre_override + (size_t)item * 3;
+    c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+    st = -1;
+  } else {
+    double pore_r = rec[PWB_REC_PORE_D] / 2.0;
+    if (pore_r < 0) {   // scipy raises on inverted bounds; the reference has no handler
+      if (lane == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+      return;
+    }
+    double lo[3], hi[3];
+    int nbd[3] = {2, 2, 2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
+    DevPoreObj3 obj{A, lo, hi, nbd};
+    st = lbfgsb_minimize<3>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit);
+  }
+  ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
+  if (lane == 0) {
+    idv[D_CENTRE] = c[0]; idv[D_CENTRE + 1] = c[1]; idv[D_CENTRE + 2] = c[2];
+    rec[PWB_REC_OPT_D] = 2.0 * pa.v; rec[PWB_REC_OPT_ATOM] = pa.i;
+    rec[PWB_REC_OPT_C] = c[0]; rec[PWB_REC_OPT_C + 1] = c[1]; rec[PWB_REC_OPT_C + 2] = c[2];
+    rec[PWB_REC_OPT_NIT] = nit; rec[PWB_REC_OPT_STOP] = st;
+  }
+}
+
+// =================================================================================================
+// k_rays
+// =================================================================================================
+constexpr int RAY_THREADS = 256;
+constexpr int RAY_TILE = 1024;   // rays per pass
+
+// Exclusive block scan of one int per thread; returns this thread's offset, `total` for all.
+__device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+  for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  __syncthreads();
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int k = 0; k < nw; k++) { int s = wsum[k]; if (k < w) base += s; tot += s; }
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(RAY_THREADS)
+k_rays(pwb_batch b, Ws ws, Ctx ctx) {
+  extern __shared__ double sm[];
+  const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  const int status0 = iiv[I_STATUS];
+  if (status0 & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS)) return;
+  const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
+  double* ax = sm; double* ay = ax + NA; double* az = ay + NA;     // shifted, bucketed
+  double* lx = az + NA; double* ly = lx + NA; double* lz = ly + NA;  // relative to the centroid
+  double* l2 = lz + NA; double* r2 = l2 + NA;
+  double* red = r2 + NA;                    // 64
+  double* cr = red + 64;                    // [PWB_MAX_TYPES]
+  double* sa2 = cr + PWB_MAX_TYPES;         // [RAY_TILE] 2*min clearance of survivors
+  int* cls = (int*)(sa2 + RAY_TILE);        // [PWB_MAX_TYPES+1]
+  int* wsum = cls + PWB_MAX_TYPES + 1;      // [32]
+  int* surv = wsum + 32;                    // [RAY_TILE] ray index of survivors in this tile
+  int* spos = surv + RAY_TILE;              // [RAY_TILE] arg-min path step (or -1)
+
+  // shift exactly as find_windows does (utilities.py:1379-1393)
+  const double cmx = idv[D_COM], cmy = idv[D_COM + 1], cmz = idv[D_COM + 2];
+  double shx, shy, shz, icx, icy, icz;
+  if (b.pore_opt) {
+    double adx = cmx - idv[D_CENTRE], ady = cmy - idv[D_CENTRE + 1], adz = cmz - idv[D_CENTRE + 2];
+    icx = cmx - adx; icy = cmy - ady; icz = cmz - adz;      // initial_com - com_adjust
+    shx = cmx - adx; shy = cmy - ady; shz = cmz - adz;      // COM - com_adjust
+  } else { icx = cmx; icy = cmy; icz = cmz; shx = cmx; shy = cmy; shz = cmz; }
+  for (int c = tid; c <= PWB_MAX_TYPES; c += nt) cls[c] = iiv[I_CLS0 + c];
+  for (int c = tid; c < PWB_MAX_TYPES; c += nt) cr[c] = c < b.n_types ? b.type_vdw[c] : 0.0;
+  double ox = 0, oy = 0, oz = 0;
+  for (int a = tid; a < n; a += nt) {
+    const double* q = ws.atoms + (size_t)(off + a) * 4;
+    double x = q[0] - shx, y = q[1] - shy, z = q[2] - shz;
+    ax[a] = x; ay[a] = y; az[a] = z; r2[a] = q[3] * q[3];
+    ox += x; oy += y; oz += z;
+  }
+  ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
+  for (int a = tid; a < n; a += nt) {
+    double x = ax[a] - ox, y = ay[a] - oy, z = az[a] - oz;
+    lx[a] = x; ly[a] = y; lz[a] = z; l2[a] = x * x + y * y + z * z;
+  }
+  const double R = idv[D_MAXD] / 2.0;     // max_dim is translation invariant: reuse (utilities.py:1398)
+  const int P = n_sampling_points(R, b.adjust);
+  __syncthreads();
+  Bucketed B{ax, ay, az, cls, cr, b.n_types};
+  if (tid == 0) {
+    idv[D_RADIUS] = R; idv[D_ICOM] = icx; idv[D_ICOM + 1] = icy; idv[D_ICOM + 2] = icz;
+    idv[D_SHIFT] = shx; idv[D_SHIFT + 1] = shy; idv[D_SHIFT + 2] = shz;
+    iiv[I_P] = P;
+    rec[PWB_REC_NRAYS] = P; rec[PWB_REC_RADIUS] = R;
+    if (P >= 2 && P < ctx.table_cap) ctx.knn_need[P] = 1;
+  }
+  if (P > b.ray_cap || P >= ctx.table_cap || P < 2) {
+    if (tid == 0) { iiv[I_STATUS] |= PWB_ST_RAY_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; iiv[I_NCLEAR] = 0; iiv[I_NSURV] = 0; }
+    return;
+  }
+  int* out_k = ws.clear_k + (size_t)item * b.ray_cap;
+  int* out_pos = ws.clear_pos + (size_t)item * b.ray_cap;
+  double* out_a2 = ws.clear_a2 + (size_t)item * b.ray_cap;
+  int n_clear = 0, n_surv_total = 0;
+  for (int base = 0; base < P; base += RAY_TILE) {
+    // ---- pre-test (utilities.py:1132-1161): 4 rays per thread, survivors compacted in ray order
+    int mine[RAY_TILE / RAY_THREADS];
+    int cntm = 0;
+#pragma unroll
+    for (int u = 0; u < RAY_TILE / RAY_THREADS; u++) {
+      int k = base + tid * (RAY_TILE / RAY_THREADS) + u;     // contiguous rays per thread keeps order
+      mine[u] = -1;
+      if (k < P) {
+        double px, py, pz;
+        spiral_point(k, P, R, px, py, pz);
+        double nr = sqrt(px * px + py * py + pz * pz);
+        double nx = px / nr, ny = py / nr, nz = pz / nr;
+        bool blocked = false;
+        for (int a = 0; a < n; a++) {
+          double t = lx[a] * nx + ly[a] * ny + lz[a] * nz;
+          double q = l2[a] - t * t;
+          double under = r2[a] - q;
+          if (q >= 0 && under > 0) {
+            double h = sqrt(under);
+            double t0 = t - h, t1 = t + h;
+            double x0 = ox + t0 * nx, y0 = oy + t0 * ny, z0 = oz + t0 * nz;
+            double x1 = ox + t1 * nx, y1 = oy + t1 * ny, z1 = oz + t1 * nz;
+            if (sqrt(x0 * x0 + y0 * y0 + z0 * z0) < sqrt(x1 * x1 + y1 * y1 + z1 * z1)) { blocked = true; break; }
+          }
+        }
+        if (!blocked) { mine[u] = k; cntm++; }
+      }
+    }
+    int nsurv;
+    int o = block_excl_scan(cntm, wsum, nsurv);
+#pragma unroll
+    for (int u = 0; u < RAY_TILE / RAY_THREADS; u++) if (mine[u] >= 0) surv[o++] = mine[u];
+    __syncthreads();
+    n_surv_total += nsurv;
+    // ---- stepped path clearance (utilities.py:1100-1129), one survivor per thread
+    for (int s = tid; s < nsurv; s += nt) {
+      int k = surv[s];
+      double px, py, pz;
+      spiral_point(k, P, R, px, py, pz);
+      double nr = sqrt(px * px + py * py + pz * pz);
+      int chunks = (int)py_floordiv(nr, b.increment);
+      double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
+      double best = PWB_INF; int bestj = 0; bool clear = true;
+      for (int j = 0; j <= chunks; j++) {
+        double a = min_clearance(B, cxs * j, cys * j, czs * j);
+        if (!(a > 0)) { clear = false; break; }
+        if (a < best) { best = a; bestj = j; }
+      }
+      spos[s] = clear ? bestj : -1;
+      sa2[s] = best * 2.0;
+    }
+    __syncthreads();
+    // ---- ordered compaction of the clear rays into the global lists
+    for (int s0 = 0; s0 < nsurv; s0 += nt) {
+      int s = s0 + tid;
+      int ok = (s < nsurv && spos[s] >= 0) ? 1 : 0;
+      int tot;
+      int oo = block_excl_scan(ok, wsum, tot);
+      if (ok) { out_k[n_clear + oo] = surv[s]; out_pos[n_clear + oo] = spos[s]; out_a2[n_clear + oo] = sa2[s]; }
+      n_clear += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    iiv[I_NCLEAR] = n_clear; iiv[I_NSURV] = n_surv_total;
+    rec[PWB_REC_NCLEAR] = n_clear; rec[PWB_REC_NSURV] = n_surv_total;
+    if (n_clear == 0) { iiv[I_STATUS] |= PWB_ST_NO_CLEAR_RAY; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+  }
+}
+
+// =================================================================================================
+// k_knn_fill: m_unit(P) = mean over the P unit-sphere spiral points of their 10 smallest distances
+// (self included), i.e. KDTree.query(k=10) of utilities.py:1427-1433 divided by the radius.
+// =================================================================================================
+constexpr int KNN_THREADS = 256;
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn_fill(Ctx ctx) {
+  extern __shared__ double sm[];
+  const int P = blockIdx.x + 2;
+  if (P >= ctx.table_cap) return;
+  if (!ctx.knn_need[P] || ctx.knn_unit[P] != 0.0) return;
+  double* ux = sm; double* uy = ux + ctx.table_cap; double* uz = uy + ctx.table_cap;
+  __shared__ double red[64];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) spiral_point(i, P, 1.0, ux[i], uy[i], uz[i]);
+  __syncthreads();
+  double acc = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    double xi = ux[i], yi = uy[i], zi = uz[i];
+    double best[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) best[q] = PWB_INF;
+    for (int j = 0; j < P; j++) {
+      double dx = xi - ux[j], dy = yi - uy[j], dz = zi - uz[j];
+      double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < best[9]) {
+        best[9] = d2;
+#pragma unroll
+        for (int q = 9; q > 0; q--)
+          if (best[q] < best[q - 1]) { double t = best[q]; best[q] = best[q - 1]; best[q - 1] = t; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 10; q++) acc += sqrt(best[q]);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) ctx.knn_unit[P] = acc / (10.0 * P);
+}
+
+// =================================================================================================
+// k_cluster: DBSCAN label semantics of sklearn (min_samples = 5, dist <= eps), order-free rule:
+// core = #neighbours (self included) >= 5; clusters = components of the core-core graph numbered
+// by their smallest core index; border point -> smallest cluster among adjacent cores; else noise.
+// Then per cluster the first arg-max of column 1 (2*min clearance), utilities.py:1221.
+// =================================================================================================
+constexpr int CL_THREADS = 256;
+
+__device__ __forceinline__ int uf_find(volatile int* parent, int i) {
+  int p = parent[i];
+  while (p != parent[p]) p = parent[p];
+  return p;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {   // smaller index becomes the root
+  while (true) {
+    a = uf_find(parent, a); b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { int t = a; a = b; b = t; }
+    int old = atomicCAS(&parent[b], b, a);
+    if (old == b) return;
+  }
+}
+
+__global__ void __launch_bounds__(CL_THREADS)
+k_cluster(pwb_batch b, Ws ws, Ctx ctx) {
+  extern __shared__ double sm[];
+  const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  const int st = iiv[I_STATUS];
+  if (st & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP)) { if (tid == 0) iiv[I_NWIN] = 0; return; }
+  const int S = iiv[I_NCLEAR], P = iiv[I_P];
+  const double R = idv[D_RADIUS];
+  const double m = R * ctx.knn_unit[P];
+  const double eps = m + sqrt(m);
+  if (tid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; }
+  if (S == 0) return;
+  const int cap = b.ray_cap;
+  double* px = sm; double* py = px + cap; double* pz = py + cap;
+  unsigned long long* cbest = (unsigned long long*)(pz + cap);   // [win_cap] best a2 bits per cluster
+  int* parent = (int*)(cbest + b.win_cap);                       // [cap]
+  int* label = parent + cap;                                     // [cap]
+  int* cidx = label + cap;                                       // [win_cap] arg-max member per cluster
+  int* wsum = cidx + b.win_cap;                                  // [32]
+  unsigned char* core = (unsigned char*)(wsum + 32);             // [cap]
+  const int* ck = ws.clear_k + (size_t)item * cap;
+  const double* ca2 = ws.clear_a2 + (size_t)item * cap;
+  for (int i = tid; i < S; i += nt) {
+    double x, y, z;
+    spiral_point(ck[i], P, R, x, y, z);
+    px[i] = x; py[i] = y; pz[i] = z;
+    parent[i] = i;
+  }
+  __syncthreads();
+  const double eps2 = eps * eps;
+  for (int i = tid; i < S; i += nt) {
+    double x = px[i], y = py[i], z = pz[i];
+    int c = 0;
+    for (int j = 0; j < S; j++) {
+      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
+      c += (dx * dx + dy * dy + dz * dz <= eps2);
+    }
+    core[i] = c >= 5;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    if (!core[i]) continue;
+    double x = px[i], y = py[i], z = pz[i];
+    for (int j = 0; j < i; j++) {
+      if (!core[j]) continue;
+      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
+      if (dx * dx + dy * dy + dz * dz <= eps2) uf_union(parent, i, j);
+    }
+  }
+  __syncthreads();
+  // roots in ascending index order -> cluster numbers
+  int nclus = 0;
+  for (int s0 = 0; s0 < S; s0 += nt) {
+    int i = s0 + tid;
+    int isroot = (i < S && core[i] && parent[i] == i) ? 1 : 0;
+    int tot;
+    int o = block_excl_scan(isroot, wsum, tot);
+    if (isroot) label[i] = nclus + o;
+    nclus += tot;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt)
+    if (core[i] && parent[i] != i) label[i] = label[uf_find(parent, i)];
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    if (core[i]) continue;
+    double x = px[i], y = py[i], z = pz[i];
+    int best = 0x7fffffff;
+    for (int j = 0; j < S; j++) {
+      if (!core[j]) continue;
+      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
+      if (dx * dx + dy * dy + dz * dz <= eps2) best = min(best, label[j]);
+    }
+    parent[i] = (best == 0x7fffffff) ? -1 : best;     // reuse parent[] as the border label
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) if (!core[i]) label[i] = parent[i];
+  const int W = min(nclus, b.win_cap);
+  for (int c = tid; c < b.win_cap; c += nt) { cbest[c] = 0ull; cidx[c] = 0x7fffffff; }
+  __syncthreads();
+  int* glabel = ws.labels + (size_t)item * cap;
+  for (int i = tid; i < S; i += nt) {
+    int l = label[i];
+    glabel[i] = l;
+    if (l >= 0 && l < W) atomicMax(&cbest[l], (unsigned long long)__double_as_longlong(ca2[i]));  // a2 > 0
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    int l = label[i];
+    if (l >= 0 && l < W && (unsigned long long)__double_as_longlong(ca2[i]) == cbest[l]) atomicMin(&cidx[l], i);
+  }
+  __syncthreads();
+  int* wk = ws.win_k + (size_t)item * b.win_cap;
+  for (int c = tid; c < W; c += nt) wk[c] = ck[cidx[c]];
+  if (tid == 0) {
+    iiv[I_NWIN] = W; rec[PWB_REC_NWIN] = W;
+    if (nclus > b.win_cap) { iiv[I_STATUS] |= PWB_ST_WIN_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+  }
+}
+
+// =================================================================================================
+// k_windows: window_analysis (utilities.py:1191-1361), one warp per (item, window)
+// =================================================================================================
+constexpr int WIN_WARPS = 4;
+
+struct DevZObj {   // optimise_z, utilities.py:1174-1188
+  WarpAtoms A; double lo;
+  __device__ void fg(const double* x, double& f, double* g) {
+    double h = lb_fd_step(x[0], 1, lo, 0.0);
+    double px[2] = {0.0, 0.0}, py[2] = {0.0, 0.0}, pz[2] = {x[0], x[0] + h}, m[2];
+    warp_min_clear<2>(A, px, py, pz, m);
+    f = m[0] * 2.0;
+    g[0] = (m[1] * 2.0 - f) / ((x[0] + h) - x[0]);
+  }
+};
+struct DevXYObj {  // optimise_xy, utilities.py:1164-1171
+  WarpAtoms A; double z;
+  __device__ double f2(double x, double y) {
+    double m[1];
+    warp_min_clear<1>(A, &x, &y, &z, m);
+    return -(m[0] * 2.0);
+  }
+};
+
+__device__ __forceinline__ double angle_between(double x0, double x1, double x2, double y0, double y1, double y2) {
+  double first = fabs(x0 * y0 + x1 * y1 + x2 * y2) /
+                 (sqrt(x0 * x0 + x1 * x1 + x2 * x2) * sqrt(y0 * y0 + y1 * y1 + y2 * y2));
+  return acos(first);
+}
+
+__global__ void __launch_bounds__(WIN_WARPS * 32)
+k_windows(pwb_batch b, Ws ws) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gw = blockIdx.x * WIN_WARPS + w;
+  const int item = gw / b.win_cap, win = gw - item * b.win_cap;
+  if (item >= b.n_items) return;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  if (win >= iiv[I_NWIN]) return;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  double* out = rec + PWB_REC_WIN0 + 4 * win;
+  const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
+  double* x = sm + (size_t)w * (NA * 4 + PWB_MAX_TYPES + 16);
+  double* y = x + NA; double* z = y + NA; double* r = z + NA;
+  double* cr = r + NA;                       // [PWB_MAX_TYPES]
+  int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1] (fits in 8 doubles + slack)
+  const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
+  for (int a = lane; a < n; a += 32) {
+    const double* q = ws.atoms + (size_t)(off + a) * 4;
+    x[a] = q[0] - shx; y[a] = q[1] - shy; z[a] = q[2] - shz; r[a] = q[3];
+  }
+  if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
+  if (lane < PWB_MAX_TYPES) cr[lane] = lane < b.n_types ? b.type_vdw[lane] : 0.0;
+  __syncwarp();
+  Bucketed B{x, y, z, cls, cr, b.n_types};
+  const int P = iiv[I_P];
+  const double R = idv[D_RADIUS];
+  // ---- rescan of the arg-max ray with increment2 (utilities.py:1221-1227)
+  double vx, vy, vz;
+  spiral_point(ws.win_k[(size_t)item * b.win_cap + win], P, R, vx, vy, vz);
+  const double nr = sqrt(vx * vx + vy * vy + vz * vz);
+  const int chunks = (int)py_floordiv(nr, b.increment2);
+  const double cxs = vx / chunks, cys = vy / chunks, czs = vz / chunks;
+  ValIdx bj; bj.v = PWB_INF; bj.i = 0x7fffffff;
+  int bad = 0;
+  for (int j = lane; j <= chunks; j += 32) {
+    double a = min_clearance(B, cxs * j, cys * j, czs * j);
+    if (!(a > 0)) bad = 1;
+    ValIdx c; c.v = a; c.i = j;
+    bj = vi_min(bj, c);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad) {
+    if (lane == 0) {
+      out[0] = nan(""); out[1] = out[2] = out[3] = nan("");
+      atomicOr(&iiv[I_STATUS], PWB_ST_WIN_DROPPED);
+    }
+    return;
+  }
+  bj = warp_vi_min(bj);
+  const double qx = cxs * bj.i, qy = cys * bj.i, qz = czs * bj.i;
+  const double new_z = sqrt(qx * qx + qy * qy + qz * qz);
+  // ---- rotation angles, octant table (utilities.py:1235-1259)
+  double a1 = angle_between(vx, vy, 0.0, 1.0, 0.0, 0.0);
+  double a2 = angle_between(vx, vy, vz, 0.0, 0.0, 1.0);
+  const double PI = 3.141592653589793;
+  const bool gx = vx >= 0, gy = vy >= 0, gz = vz >= 0;
+  if (gx && gy && gz) { a1 = -a1; a2 = -a2; }
+  if (!gx && gy && gz) { a1 = PI * 2 + a1; }
+  if (gx && !gy && gz) { a2 = -a2; }
+  if (!gx && !gy && gz) { a1 = PI * 2 - a1; }
+  if (gx && gy && !gz) { a1 = -a1; a2 = PI + a2; }
+  if (!gx && gy && !gz) { a2 = PI - a2; }
+  if (gx && !gy && !gz) { a2 = a2 + PI; }
+  if (!gx && !gy && !gz) { a1 = -a1; a2 = PI - a2; }
+  double s1, c1, s2, c2;
+  sincos(a1, &s1, &c1);
+  sincos(a2, &s2, &c2);
+  for (int a = lane; a < n; a += 32) {
+    double X0 = x[a], Y0 = y[a], Z0 = z[a];
+    double X1 = c1 * X0 + (-s1) * Y0, Y1 = s1 * X0 + c1 * Y0, Z1 = Z0;         // Rz(a1)
+    double X2 = c2 * X1 + s2 * Z1, Y2 = Y1, Z2 = (-s2) * X1 + c2 * Z1;          // Ry(a2)
+    x[a] = X2; y[a] = Y2; z[a] = Z2 - new_z;
+  }
+  __syncwarp();
+  WarpAtoms A{x, y, z, r, n, lane};
+  double m0[1], zero = 0.0;
+  warp_min_clear<1>(A, &zero, &zero, &zero, m0);
+  const double d0 = m0[0] * 2.0;
+  // ---- z stage: L-BFGS-B from 0 with lower bound -new_z (utilities.py:1296-1305)
+  double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nbd1[1] = {1}, nitz;
+  DevZObj zo{A, -new_z};
+  lbfgsb_minimize<1>(zo, zc, zlo, zhi, nbd1, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz);
+  const double wz = zc[0];
+  // ---- xy stage: 20x20 brute grid (first arg-min, row-major) + Nelder-Mead (utilities.py:1307-1316)
+  const double glo = -d0 / 2, ghi = d0 / 2;
+  const double gstep = (ghi - glo) / 19.0;
+  ValIdx gb; gb.v = PWB_INF; gb.i = 0x7fffffff;
+  for (int g = lane; g < 400; g += 32) {
+    int ix = g / 20, iy = g - ix * 20;
+    double gxp = __dadd_rn(__dmul_rn((double)ix, gstep), glo), gyp = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+    ValIdx c; c.v = -(min_clearance(B, gxp, gyp, wz) * 2.0); c.i = g;
+    gb = vi_min(gb, c);
+  }
+  gb = warp_vi_min(gb);
+  const int ix = gb.i / 20, iy = gb.i - ix * 20;
+  const double x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo), y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+  DevXYObj xo{A, wz};
+  double xy[2], fxy; int nfev;
+  nelder_mead2(xo, x0, y0, 1e-4, 1e-4, 400, 400, xy, &fxy, &nfev);
+  double mf[1];
+  warp_min_clear<1>(A, &xy[0], &xy[1], &wz, mf);
+  const double diam = mf[0] * 2.0;
+  // ---- back to the molecule frame (utilities.py:1337-1360) + initial_com (:1529-1535)
+  double wx = xy[0], wy = xy[1], wzz = wz + new_z;
+  double s2m, c2m, s1m, c1m;
+  sincos(-a2, &s2m, &c2m);
+  sincos(-a1, &s1m, &c1m);
+  double X1 = c2m * wx + s2m * wzz, Y1 = wy, Z1 = (-s2m) * wx + c2m * wzz;
+  double X2 = c1m * X1 + (-s1m) * Y1, Y2 = s1m * X1 + c1m * Y1, Z2 = Z1;
+  if (lane == 0) {
+    out[0] = diam;
+    out[1] = X2 + idv[D_ICOM]; out[2] = Y2 + idv[D_ICOM + 1]; out[3] = Z2 + idv[D_ICOM + 2];
+    if (diam < 0) atomicOr(&iiv[I_STATUS], PWB_ST_WIN_NEGATIVE);
+  }
+}
+
+// final status word (window kernels OR flags into item_i after the record status was written)
+__global__ void k_finish(pwb_batch b, Ws ws) {
+  int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= b.n_items) return;
+  b.records[(size_t)item * b.rec_stride + PWB_REC_STATUS] = ws.item_i[(size_t)item * ITEM_I + I_STATUS];
+}
+
+// bounding-box bound on the ray count (sizes ray_cap); one block, result in out[0]
+__global__ void k_ray_capacity(pwb_batch b, int* out) {
+  __shared__ int smax;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  double rmax = 0;
+  for (int t = 0; t < b.n_types; t++) rmax = fmax(rmax, b.type_vdw[t]);
+  int local = 0;
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < b.n_items; item += gridDim.x * blockDim.x) {
+    int off = b.item_off[item], n = b.item_off[item + 1] - off;
+    double lo[3] = {PWB_INF, PWB_INF, PWB_INF}, hi[3] = {-PWB_INF, -PWB_INF, -PWB_INF};
+    for (int a = 0; a < n; a++)
+      for (int d = 0; d < 3; d++) { double v = b.coords[(size_t)(off + a) * 3 + d]; lo[d] = fmin(lo[d], v); hi[d] = fmax(hi[d], v); }
+    double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    double D = sqrt(dx * dx + dy * dy + dz * dz) + 2 * rmax;
+    local = max(local, max(n_sampling_points(D / 2, b.adjust), n_sampling_points(D, b.adjust)));
+  }
+  atomicMax(&smax, local);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicMax(out, smax);
+}
+
+}  // namespace pwb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace pwb;
+
+struct pwb_ctx { Ctx c; int* d_tmp; int max_smem; };
+
+static thread_local char g_err[512] = "";
+static int fail(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+  return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+template <class K>
+static int set_smem(K kern, size_t bytes, int max_smem) {
+  if ((int)bytes > max_smem) { snprintf(g_err, sizeof g_err, "shared memory %zu > device limit %d (too many atoms)", bytes, max_smem); return 1; }
+  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+extern "C" {
+
+int pwb_abi_version(void) { return PWB_ABI_VERSION; }
+const char* pwb_last_error(void) { return g_err; }
+
+int pwb_workspace_layout(int F, int total_atoms, int ray_cap, int win_cap, pwb_ws_layout* L) {
+  size_t o = 0;
+  L->atoms = o; o = align_up(o + (size_t)total_atoms * 4 * sizeof(double));
+  L->atom_idx = o; o = align_up(o + (size_t)total_atoms * sizeof(int));
+  L->item_d = o; o = align_up(o + (size_t)F * ITEM_D * sizeof(double));
+  L->item_i = o; o = align_up(o + (size_t)F * ITEM_I * sizeof(int));
+  L->clear_k = o; o = align_up(o + (size_t)F * ray_cap * sizeof(int));
+  L->clear_pos = o; o = align_up(o + (size_t)F * ray_cap * sizeof(int));
+  L->clear_a2 = o; o = align_up(o + (size_t)F * ray_cap * sizeof(double));
+  L->labels = o; o = align_up(o + (size_t)F * ray_cap * sizeof(int));
+  L->win_k = o; o = align_up(o + (size_t)F * win_cap * sizeof(int));
+  L->total = o;
+  return 0;
+}
+size_t pwb_workspace_bytes(int F, int total_atoms, int ray_cap, int win_cap) {
+  pwb_ws_layout L;
+  pwb_workspace_layout(F, total_atoms, ray_cap, win_cap, &L);
+  return L.total;
+}
+
+int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
+  CK(cudaSetDevice(device));
+  pwb_ctx* c = new pwb_ctx();
+  c->c.device = device;
+  c->c.table_cap = ray_table_cap;
+  c->c.launches = 0;
+  CK(cudaMalloc(&c->c.knn_unit, sizeof(double) * ray_table_cap));
+  CK(cudaMalloc(&c->c.knn_need, sizeof(int) * ray_table_cap));
+  CK(cudaMalloc(&c->d_tmp, sizeof(int) * 4));
+  CK(cudaMemset(c->c.knn_unit, 0, sizeof(double) * ray_table_cap));
+  CK(cudaMemset(c->c.knn_need, 0, sizeof(int) * ray_table_cap));
+  CK(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  *out = c;
+  return 0;
+}
+int pwb_ctx_destroy(pwb_ctx* c) {
+  if (!c) return 0;
+  cudaFree(c->c.knn_unit); cudaFree(c->c.knn_need); cudaFree(c->d_tmp);
+  delete c;
+  return 0;
+}
+long long pwb_launch_count(pwb_ctx* c) { return c->c.launches; }
+
+static int resolve(const pwb_batch* b, Ws* w) {
+  if (!b->workspace) { snprintf(g_err, sizeof g_err, "workspace is null"); return 1; }
+  pwb_ws_layout L;
+  pwb_workspace_layout(b->n_items, b->total_atoms, b->ray_cap, b->win_cap, &L);
+  if (b->workspace_bytes < L.total) { snprintf(g_err, sizeof g_err, "workspace too small: %zu < %zu", b->workspace_bytes, L.total); return 1; }
+  char* p = (char*)b->workspace;
+  w->atoms = (double*)(p + L.atoms); w->atom_idx = (int*)(p + L.atom_idx);
+  w->item_d = (double*)(p + L.item_d); w->item_i = (int*)(p + L.item_i);
+  w->clear_k = (int*)(p + L.clear_k); w->clear_pos = (int*)(p + L.clear_pos);
+  w->clear_a2 = (double*)(p + L.clear_a2); w->labels = (int*)(p + L.labels); w->win_k = (int*)(p + L.win_k);
+  return 0;
+}
+
+static int check(const pwb_batch* b) {
+  if (b->n_items <= 0) { snprintf(g_err, sizeof g_err, "n_items must be positive"); return 1; }
+  if (b->n_types < 1 || b->n_types > PWB_MAX_TYPES) { snprintf(g_err, sizeof g_err, "n_types out of range"); return 1; }
+  if (b->rec_stride < PWB_REC_WIN0 + 4 * b->win_cap) { snprintf(g_err, sizeof g_err, "rec_stride too small"); return 1; }
+  if (b->ray_cap > 4096) { snprintf(g_err, sizeof g_err, "ray_cap > 4096 not supported by this revision"); return 1; }
+  return 0;
+}
+
+static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s, int do_avg) {
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + 64) + sizeof(int) * (64 + b->max_atoms + PWB_MAX_TYPES + 1);
+  if (set_smem(k_prepare, sm, c->max_smem)) return 1;
+  k_prepare<<<b->n_items, PREP_THREADS, sm, s>>>(*b, w, do_avg);
+  c->c.launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
+  size_t sm = sizeof(double) * (size_t)b->max_atoms * 4 * OPT_WARPS;
+  if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
+  k_opt_pore<<<(b->n_items + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, sm, s>>>(*b, w);
+  c->c.launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_TILE) +
+              sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE);
+  if (set_smem(k_rays, sm, c->max_smem)) return 1;
+  k_rays<<<b->n_items, RAY_THREADS, sm, s>>>(*b, w, c->c);
+  c->c.launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
+  size_t smk = sizeof(double) * 3 * (size_t)c->c.table_cap;
+  if (set_smem(k_knn_fill, smk, c->max_smem)) return 1;
+  k_knn_fill<<<c->c.table_cap - 2, KNN_THREADS, smk, s>>>(c->c);
+  c->c.launches++;
+  size_t sm = sizeof(double) * (size_t)b->ray_cap * 3 + sizeof(unsigned long long) * b->win_cap +
+              sizeof(int) * ((size_t)b->ray_cap * 2 + b->win_cap + 32) + (size_t)b->ray_cap + 16;
+  if (set_smem(k_cluster, sm, c->max_smem)) return 1;
+  k_cluster<<<b->n_items, CL_THREADS, sm, s>>>(*b, w, c->c);
+  c->c.launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + PWB_MAX_TYPES + 16) * WIN_WARPS + 64;
+  if (set_smem(k_windows, sm, c->max_smem)) return 1;
+  long long warps = (long long)b->n_items * b->win_cap;
+  k_windows<<<(unsigned)((warps + WIN_WARPS - 1) / WIN_WARPS), WIN_WARPS * 32, sm, s>>>(*b, w);
+  k_finish<<<(b->n_items + 255) / 256, 256, 0, s>>>(*b, w);
+  c->c.launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int pwb_ray_capacity(pwb_ctx* c, const pwb_batch* b, void* stream, int* out_cap) {
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(c->d_tmp, 0, sizeof(int), s));
+  int blocks = (b->n_items + 127) / 128;
+  if (blocks > 1184) blocks = 1184;
+  k_ray_capacity<<<blocks, 128, 0, s>>>(*b, c->d_tmp);
+  c->c.launches++;
+  int v = 0;
+  CK(cudaMemcpyAsync(&v, c->d_tmp, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *out_cap = v;
+  return 0;
+}
+
+int pwb_full_analysis_batch(pwb_ctx* c, const pwb_batch* b, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check(b)) return 1;
+  Ws w;
+  if (resolve(b, &w)) return 1;
+  if (b->stages & (PWB_STAGE_SCALARS | PWB_STAGE_AVGD)) {
+    CK(cudaMemsetAsync(b->records, 0, sizeof(double) * (size_t)b->n_items * b->rec_stride, s));
+  }
+  if (b->stages & (PWB_STAGE_SCALARS | PWB_STAGE_AVGD))
+    if (run_prepare(c, b, w, s, (b->stages & PWB_STAGE_AVGD) ? 1 : 0)) return 1;
+  if (b->stages & PWB_STAGE_OPT) if (run_opt(c, b, w, s)) return 1;
+  if (b->stages & PWB_STAGE_RAYS) if (run_rays(c, b, w, s)) return 1;
+  if (b->stages & PWB_STAGE_CLUSTER) if (run_cluster(c, b, w, s)) return 1;
+  if (b->stages & PWB_STAGE_WINDOWS) if (run_windows(c, b, w, s)) return 1;
+  return 0;
+}
+
+static int run_stage(pwb_ctx* c, const pwb_batch* b, void* stream, int stages) {
+  pwb_batch t = *b;
+  t.stages = stages;
+  return pwb_full_analysis_batch(c, &t, stream);
+}
+int pwb_frame_scalars(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_SCALARS); }
+int pwb_average_diameter(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_SCALARS | PWB_STAGE_AVGD); }
+int pwb_opt_pore(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_OPT); }
+int pwb_ray_search(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_RAYS); }
+int pwb_cluster(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_CLUSTER); }
+int pwb_window_refine(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_WINDOWS); }
+
+int pwb_full_analysis_host(pwb_ctx* c, const pwb_batch* b, const double* h_coords, double* h_records,
+                           double* d_coords, double* d_records, int total_atoms, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  pwb_batch t = *b;
+  t.coords = d_coords;
+  t.records = d_records;
+  CK(cudaMemcpyAsync(d_coords, h_coords, sizeof(double) * 3 * (size_t)total_atoms, cudaMemcpyHostToDevice, s));
+  if (pwb_full_analysis_batch(c, &t, stream)) return 1;
+  CK(cudaMemcpyAsync(h_records, d_records, sizeof(double) * (size_t)b->n_items * b->rec_stride, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // extern "C"

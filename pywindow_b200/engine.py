@@ -1,0 +1,296 @@
+"""Batched GPU driver for the pore-geometry path.
+
+``Engine`` owns one ``pwb_ctx`` (device context) and turns batches of molecule-frames into result
+records through the C ABI (``include/pwb.h``).  torch is used only for device memory and streams.
+There is no CPU fallback: without a CUDA device or without ``libpwb.so`` construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .tables import atomic_mass, atomic_vdw_radius
+
+logger = logging.getLogger("pywindow")
+
+DEFAULT_WIN_CAP = 16
+
+
+class PwbNoDeviceError(RuntimeError):
+    pass
+
+
+def element_types(elements):
+    """Map element symbols to small integer types + per-type vdW radius / mass tables
+    (replaces the per-atom dict lookups of utilities.py:96-148, :358-364, :382)."""
+    up = [str(e).upper() for e in elements]
+    uniq = sorted(set(up))
+    if len(uniq) > _lib.MAX_TYPES:
+        raise ValueError(f"more than {_lib.MAX_TYPES} distinct elements in one batch")
+    idx = {e: i for i, e in enumerate(uniq)}
+    try:
+        vdw = np.array([atomic_vdw_radius[e] for e in uniq], dtype=np.float64)
+        mass = np.array([atomic_mass[e] for e in uniq], dtype=np.float64)
+    except KeyError as exc:
+        raise KeyError(f"unknown element {exc.args[0]!r}") from None
+    return np.array([idx[e] for e in up], dtype=np.int32), vdw, mass
+
+
+class BatchResult:
+    """Records of one batch plus views of the per-stage lists in the workspace."""
+
+    def __init__(self, records, workspace, layout, n_items, total_atoms, ray_cap, win_cap):
+        self.records = records            # torch [F, rec_stride] float64 (device)
+        self._ws = workspace
+        self._layout = layout
+        self.n_items, self.total_atoms, self.ray_cap, self.win_cap = n_items, total_atoms, ray_cap, win_cap
+
+    def _view(self, off, dtype, shape):
+        n = int(np.prod(shape))
+        item = torch.empty((), dtype=dtype).element_size()
+        return self._ws[off: off + n * item].view(dtype).view(*shape)
+
+    @property
+    def clear_k(self):
+        return self._view(self._layout.clear_k, torch.int32, (self.n_items, self.ray_cap))
+
+    @property
+    def clear_pos(self):
+        return self._view(self._layout.clear_pos, torch.int32, (self.n_items, self.ray_cap))
+
+    @property
+    def clear_a2(self):
+        return self._view(self._layout.clear_a2, torch.float64, (self.n_items, self.ray_cap))
+
+    @property
+    def labels(self):
+        return self._view(self._layout.labels, torch.int32, (self.n_items, self.ray_cap))
+
+    @property
+    def win_k(self):
+        return self._view(self._layout.win_k, torch.int32, (self.n_items, self.win_cap))
+
+    @property
+    def item_d(self):
+        return self._view(self._layout.item_d, torch.float64, (self.n_items, 16))
+
+    def host_records(self):
+        return self.records.cpu().numpy()
+
+
+class Engine:
+    def __init__(self, device=None, table_cap=4096, win_cap=DEFAULT_WIN_CAP):
+        if not torch.cuda.is_available():
+            raise PwbNoDeviceError("pywindow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.win_cap = win_cap
+        self.table_cap = table_cap
+        self._ctx = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pwb_ctx_create(ctypes.byref(self._ctx), self.device.index, table_cap))
+        self._pinned = {}
+
+    def close(self):
+        if self._ctx:
+            self.lib.pwb_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.pwb_launch_count(self._ctx))
+
+    @property
+    def rec_stride(self):
+        return _lib.REC_WIN0 + 4 * self.win_cap
+
+    # ------------------------------------------------------------------ batch construction
+    def _dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def _make_batch(self, coords, item_off, atom_type, type_vdw, type_mass, shared_types, max_atoms,
+                    centre_override, stages, adjust, increment, increment2, pore_opt, ray_cap):
+        F = int(item_off.numel() - 1)
+        total = int(coords.shape[0])
+        b = _lib.Batch()
+        b.n_items, b.max_atoms, b.n_types = F, int(max_atoms), int(type_vdw.numel())
+        b.shared_types, b.win_cap, b.rec_stride = int(bool(shared_types)), self.win_cap, self.rec_stride
+        b.stages = int(stages)
+        b.adjust, b.increment, b.increment2 = float(adjust), float(increment), float(increment2)
+        b.pore_opt, b.total_atoms = int(bool(pore_opt)), total
+        b.coords, b.item_off, b.atom_type = coords.data_ptr(), item_off.data_ptr(), atom_type.data_ptr()
+        b.type_vdw, b.type_mass = type_vdw.data_ptr(), type_mass.data_ptr()
+        b.centre_override = centre_override.data_ptr() if centre_override is not None else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if ray_cap is None:
+            cap = ctypes.c_int(0)
+            b.ray_cap = 0
+            _lib.check(self.lib.pwb_ray_capacity(self._ctx, ctypes.byref(b), stream, ctypes.byref(cap)))
+            ray_cap = max(64, (cap.value + 63) // 64 * 64)
+        if ray_cap > self.table_cap - 1:
+            raise ValueError(f"ray capacity {ray_cap} exceeds the engine's table_cap {self.table_cap}")
+        b.ray_cap = int(ray_cap)
+        return b, stream, F, total
+
+    def analyse(self, coords, item_off, atom_type, type_vdw, type_mass, *, shared_types, max_atoms,
+                centre_override=None, stages=_lib.STAGE_ALL, adjust=1.0, increment=1.0, increment2=0.1,
+                pore_opt=True, ray_cap=None):
+        """Run the stages on a batch whose inputs are (or are moved to) device tensors."""
+        with torch.cuda.device(self.device):
+            coords = self._dev(coords, torch.float64).view(-1, 3)
+            item_off = self._dev(item_off, torch.int32)
+            atom_type = self._dev(atom_type, torch.int32)
+            type_vdw = self._dev(type_vdw, torch.float64)
+            type_mass = self._dev(type_mass, torch.float64)
+            if centre_override is not None:
+                centre_override = self._dev(centre_override, torch.float64).view(-1, 3)
+            b, stream, F, total = self._make_batch(coords, item_off, atom_type, type_vdw, type_mass,
+                                                   shared_types, max_atoms, centre_override, stages, adjust,
+                                                   increment, increment2, pore_opt, ray_cap)
+            layout = _lib.WsLayout()
+            self.lib.pwb_workspace_layout(F, total, b.ray_cap, self.win_cap, ctypes.byref(layout))
+            ws = torch.empty(layout.total, dtype=torch.uint8, device=self.device)
+            rec = torch.empty((F, self.rec_stride), dtype=torch.float64, device=self.device)
+            b.records, b.workspace, b.workspace_bytes = rec.data_ptr(), ws.data_ptr(), layout.total
+            _lib.check(self.lib.pwb_full_analysis_batch(self._ctx, ctypes.byref(b), stream))
+            res = BatchResult(rec, ws, layout, F, total, b.ray_cap, self.win_cap)
+            res._keep = (coords, item_off, atom_type, type_vdw, type_mass, centre_override)
+            return res
+
+    def analyse_frames(self, coords, elements, **kw):
+        """``coords``: [F, N, 3] (numpy or torch), one molecule with atom order ``elements``."""
+        F, N = int(coords.shape[0]), int(coords.shape[1])
+        types, vdw, mass = element_types(elements)
+        off = torch.arange(0, (F + 1) * N, N, dtype=torch.int32)
+        flat = coords.reshape(F * N, 3)
+        return self.analyse(flat, off, types, vdw, mass, shared_types=True, max_atoms=N, **kw)
+
+    def analyse_molecules(self, mols, **kw):
+        """``mols``: list of (elements, coords[N_i,3]) with arbitrary sizes / compositions."""
+        all_el = [e for el, _ in mols for e in el]
+        types, vdw, mass = element_types(all_el)
+        sizes = [len(el) for el, _ in mols]
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 3) for _, c in mols])
+        return self.analyse(flat, off, types, vdw, mass, shared_types=False, max_atoms=max(sizes), **kw)
+
+    # ------------------------------------------------------------------ host-buffer path (e2e)
+    def analyse_frames_host(self, coords_host, elements, *, ray_cap, out=None, stages=_lib.STAGE_ALL,
+                            adjust=1.0, increment=1.0, increment2=0.1, pore_opt=True, state=None):
+        """Host numpy/pinned [F,N,3] in, host records out: H2D + kernels + D2H inside the call
+        (``pwb_full_analysis_host``).  ``state`` caches device staging buffers between calls."""
+        F, N = int(coords_host.shape[0]), int(coords_host.shape[1])
+        with torch.cuda.device(self.device):
+            st = state if state is not None else {}
+            key = (F, N, ray_cap, tuple(str(e) for e in elements[:8]))
+            if st.get("key") != key:
+                types, vdw, mass = element_types(elements)
+                st.clear()
+                st["key"] = key
+                st["types"] = self._dev(types, torch.int32)
+                st["vdw"] = self._dev(vdw, torch.float64)
+                st["mass"] = self._dev(mass, torch.float64)
+                st["off"] = torch.arange(0, (F + 1) * N, N, dtype=torch.int32, device=self.device)
+                st["d_coords"] = torch.empty((F * N, 3), dtype=torch.float64, device=self.device)
+                st["d_rec"] = torch.empty((F, self.rec_stride), dtype=torch.float64, device=self.device)
+                layout = _lib.WsLayout()
+                self.lib.pwb_workspace_layout(F, F * N, ray_cap, self.win_cap, ctypes.byref(layout))
+                st["layout"] = layout
+                st["ws"] = torch.empty(layout.total, dtype=torch.uint8, device=self.device)
+                st["h_rec"] = torch.empty((F, self.rec_stride), dtype=torch.float64).pin_memory()
+            if isinstance(coords_host, torch.Tensor):
+                h_ptr = coords_host.data_ptr()
+            else:
+                coords_host = np.ascontiguousarray(coords_host, dtype=np.float64)
+                h_ptr = coords_host.ctypes.data
+            h_rec = st["h_rec"] if out is None else out
+            b, stream, _, _ = self._make_batch(st["d_coords"], st["off"], st["types"], st["vdw"], st["mass"],
+                                               True, N, None, stages, adjust, increment, increment2, pore_opt,
+                                               ray_cap)
+            b.workspace, b.workspace_bytes = st["ws"].data_ptr(), st["layout"].total
+            _lib.check(self.lib.pwb_full_analysis_host(self._ctx, ctypes.byref(b), h_ptr, h_rec.data_ptr(),
+                                                       st["d_coords"].data_ptr(), st["d_rec"].data_ptr(),
+                                                       F * N, stream))
+            return h_rec
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+# ---------------------------------------------------------------------- record -> reference types
+def sphere_volume(sphere_radius):
+    """utilities.py:429-431."""
+    return float(4 / 3 * np.pi * sphere_radius ** 3)
+
+
+def record_windows(rec, warn=True):
+    """(diameters[W], centres[W,3]) | None from one record, with find_windows' semantics
+    (utilities.py:1473, :1515-1553): None if no ray is clear, dropped windows removed (warning),
+    negative diameters kept (warning)."""
+    status = int(rec[_lib.REC_STATUS])
+    if status & _lib.ST_NO_CLEAR_RAY:
+        return None
+    nw = int(rec[_lib.REC_NWIN])
+    w = np.asarray(rec[_lib.REC_WIN0: _lib.REC_WIN0 + 4 * nw], dtype=np.float64).reshape(nw, 4)
+    keep = ~np.isnan(w[:, 0])
+    if warn:
+        for _ in range(int((~keep).sum())):
+            logger.warning("Warning. One of the analysed windows has returned as None. See manual.")
+        for _ in range(int((w[keep, 0] < 0).sum())):
+            logger.warning("Warning. One of the analysed windows has a vdW corrected diameter smaller than 0. "
+                           "See manual.")
+    w = w[keep]
+    return w[:, 0].copy(), w[:, 1:4].copy()
+
+
+def check_record(rec):
+    status = int(rec[_lib.REC_STATUS])
+    if status & _lib.ST_BAD_ITEM:
+        raise ValueError("molecule rejected by the GPU path (too many atoms for shared memory or unknown type)")
+    if status & _lib.ST_RAY_CAP:
+        raise RuntimeError("ray capacity exceeded (internal sizing error)")
+    if status & _lib.ST_WIN_CAP:
+        warnings.warn("more windows than win_cap; extra clusters were not analysed", RuntimeWarning, stacklevel=2)
+    return status
+
+
+def record_to_properties(rec, full=True):
+    """Rebuild ``Molecule.properties`` (molecular.py:131-351) from one result record."""
+    status = check_record(rec)
+    p = {"no_of_atoms": int(rec[_lib.REC_NATOMS]),
+         "centre_of_mass": np.array(rec[_lib.REC_COM:_lib.REC_COM + 3], dtype=np.float64),
+         "maximum_diameter": {"diameter": float(rec[_lib.REC_MAXD]), "atom_1": int(rec[_lib.REC_MAXD_A1]),
+                              "atom_2": int(rec[_lib.REC_MAXD_A2])},
+         "average_diameter": float(rec[_lib.REC_AVGD]),
+         "pore_diameter": {"diameter": float(rec[_lib.REC_PORE_D]), "atom": int(rec[_lib.REC_PORE_ATOM])},
+         "pore_volume": sphere_volume(float(rec[_lib.REC_PORE_D]) / 2)}
+    if status & _lib.ST_OPT_BOUNDS:
+        # scipy's message for the inverted box the reference builds at utilities.py:415-420
+        raise ValueError("An upper bound is less than the corresponding lower bound.")
+    p["pore_diameter_opt"] = {"diameter": float(rec[_lib.REC_OPT_D]), "atom_1": int(rec[_lib.REC_OPT_ATOM]),
+                              "centre_of_mass": np.array(rec[_lib.REC_OPT_C:_lib.REC_OPT_C + 3], dtype=np.float64)}
+    p["pore_volume_opt"] = sphere_volume(float(rec[_lib.REC_OPT_D]) / 2)
+    w = record_windows(rec)
+    p["windows"] = ({"diameters": None, "centre_of_mass": None} if w is None
+                    else {"diameters": w[0], "centre_of_mass": w[1]})
+    return p
