@@ -151,6 +151,10 @@ int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
 int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream);
 
+/* Measurement utility: sustained FMA throughput of the FP32 (fp64 = 0) or FP64 (fp64 = 1) pipe in
+ * TFLOP/s, timed with CUDA events (the roofline denominator of this compute-bound path).          */
+int pwb_fma_peak(pwb_ctx*, int fp64, void* stream, double* tflops);
+
 /* number of kernel launches issued by this library since the context was created */
 long long pwb_launch_count(pwb_ctx*);
 

@@ -737,6 +737,21 @@ __global__ void k_ray_capacity(pwb_batch b, int* out) {
   if (threadIdx.x == 0) atomicMax(out, smax);
 }
 
+// FMA-pipe microbenchmark (roofline denominator for the FP32/FP64 pipes)
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
+  T v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      v0 = v0 * a + b; v1 = v1 * a + b; v2 = v2 * a + b; v3 = v3 * a + b;
+      v4 = v4 * a + b; v5 = v5 * a + b; v6 = v6 * a + b; v7 = v7 * a + b;
+    }
+  }
+  T s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+  if (s == (T)123456789) out[0] = s;
+}
+
 }  // namespace pwb
 
 // =================================================================================================
@@ -922,6 +937,29 @@ int pwb_opt_pore(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, 
 int pwb_ray_search(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_RAYS); }
 int pwb_cluster(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_CLUSTER); }
 int pwb_window_refine(pwb_ctx* c, const pwb_batch* b, void* s) { return run_stage(c, b, s, PWB_STAGE_WINDOWS); }
+
+int pwb_fma_peak(pwb_ctx* c, int fp64, void* stream, double* tflops) {
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int blocks = 148 * 8, iters = fp64 ? 4096 : 8192;
+  void* out = c->d_tmp;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, s));
+    if (fp64) k_fma_peak<double><<<blocks, 256, 0, s>>>((double*)c->c.knn_unit + 1, iters, 1.0000001, 1e-9);
+    else k_fma_peak<float><<<blocks, 256, 0, s>>>((float*)out, iters, 1.0000001f, 1e-9f);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  c->c.launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
 
 int pwb_full_analysis_host(pwb_ctx* c, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream) {
