@@ -151,6 +151,28 @@ int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
 int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream);
 
+/* ---- periodic cells -------------------------------------------------------------------------
+ * discrete_molecules (utilities.py:820-1085) for F cell-frames of N atoms each; with `rebuild` the
+ * 27-image supercell of create_supercell (utilities.py:768-810) is implied and molecules are rebuilt
+ * across the periodic boundary and filtered by their centre of mass (utilities.py:1062-1077).
+ * Device pointers.  coords [F][N][3]; lattice [F][9] row-major (one matrix if lattice_shared, NULL =
+ * non-periodic system); atom_type [N] with per-type covalent radius / mass / "terminal element" flag
+ * (H, halogens, noble gases never expand, utilities.py:933); max_cov = largest covalent radius
+ * present.  Outputs per frame f: n_mol[f] molecules; molecule k owns output atoms
+ * [mol_off[f][k], mol_off[f][k+1]) whose source atom index is out_src[f][.] and whose (rebuilt,
+ * 8-decimal rounded) coordinates are out_xyz[f][.][3], in the reference's atom order.
+ * status[f]: 1 bond-table overflow, 2 output overflow (raise out_cap), 4 molecule overflow.          */
+typedef struct pwb_dm_layout { size_t frame_d, frac, xr, adj, deg, vis, rem, front, total; } pwb_dm_layout;
+size_t pwb_dm_workspace_bytes(int n_frames, int n_atoms, int out_cap);
+int pwb_dm_workspace_layout(int n_frames, int n_atoms, int out_cap, pwb_dm_layout* out);
+int pwb_discrete_molecules(int n_frames, int n_atoms, int rebuild, double tol, double max_cov,
+                           const double* coords, const double* lattice, int lattice_shared,
+                           const int32_t* atom_type, int n_types, const double* type_cov,
+                           const double* type_mass, const int32_t* type_terminal, int out_cap, int mol_cap,
+                           int32_t* n_mol, int32_t* mol_off, int32_t* out_src, double* out_xyz,
+                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+void pwb_set_error(const char* msg);
+
 /* Measurement utility: sustained FMA throughput of the FP32 (fp64 = 0) or FP64 (fp64 = 1) pipe in
  * TFLOP/s, timed with CUDA events (the roofline denominator of this compute-bound path).          */
 int pwb_fma_peak(pwb_ctx*, int fp64, void* stream, double* tflops);

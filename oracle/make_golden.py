@@ -92,11 +92,21 @@ def analyse(pw, util, elements, coords, name, windows=True, scalars=True, avg=Tr
     print(f"{name}: N={len(elements)} windows={nw}", flush=True)
 
 
-def periodic(pw, name, path):
-    """discrete_molecules / rebuild fixtures (utilities.py:820-1085, molecular.py:672-824)."""
+def periodic(pw, name, path, noise_seed=None):
+    """discrete_molecules / rebuild fixtures (utilities.py:820-1085, molecular.py:672-824).
+    With ``noise_seed`` the cell gets N(0, 0.05 A) noise rounded to 3 decimals (a PDB-precision MD
+    frame): tie-free, so atom and molecule ORDER is pinned as well."""
+    import copy
     out = {"versions": versions()}
     ms = pw.MolecularSystem.load_file(path)
     sysd = ms.system
+    if noise_seed is not None:
+        rng = np.random.default_rng(noise_seed)
+        sysd["coordinates"] = np.round(sysd["coordinates"] + rng.normal(0, 0.05, sysd["coordinates"].shape), 3)
+    base = copy.deepcopy(sysd)
+    _load = pw.MolecularSystem.load_file
+    pw.MolecularSystem.load_file = classmethod(lambda cls, p: cls.load_system(copy.deepcopy(base), "noisy")) \
+        if noise_seed is not None else _load
     out["elements"] = np.asarray(sysd["elements"]).astype("U4")
     out["coords"] = np.asarray(sysd["coordinates"], dtype=np.float64)
     out["unit_cell"] = np.asarray(sysd["unit_cell"], dtype=np.float64)
@@ -112,6 +122,7 @@ def periodic(pw, name, path):
     rb = ms.rebuild_system()
     out["rebuilt_elements"] = np.asarray(rb.system["elements"]).astype("U4")
     out["rebuilt_coords"] = np.asarray(rb.system["coordinates"], dtype=np.float64)
+    pw.MolecularSystem.load_file = _load
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(f"{name}: N={len(out['elements'])} molecules={out['rebuild_count']} / {out['norebuild_count']}", flush=True)
 
@@ -155,6 +166,10 @@ def main():
     for nm, fn in (("pudxes_cell", "PUDXES_no_solvent.pdb"), ("epirur_cell", "EPIRUR_no_solvent.pdb"),
                    ("tatver_cell", "TATVER_no_solvent.pdb")):
         jobs.append(("per_" + nm, lambda nm=nm, fn=fn: periodic(pw, "per_" + nm, os.path.join(inp, fn))))
+
+    for nm, fn, sd in (("pudxes_noise1", "PUDXES_no_solvent.pdb", 20261017), ("pudxes_noise2", "PUDXES_no_solvent.pdb", 20261018),
+                       ("epirur_noise", "EPIRUR_no_solvent.pdb", 20261019)):
+        jobs.append(("per_" + nm, lambda nm=nm, fn=fn, sd=sd: periodic(pw, "per_" + nm, os.path.join(inp, fn), noise_seed=sd)))
 
     for name, job in jobs:
         if a.only is None or a.only in name:

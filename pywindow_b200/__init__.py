@@ -1,12 +1,22 @@
 """pywindow_b200 -- B200 (sm_100a) implementation of pywindow's per-frame pore-geometry path.
 
-Drop-in for the reference's public names on that path (``pywindow/__init__.py:3-19``); see DESIGN.md.
+Drop-in for the reference's public names on that path (``pywindow/__init__.py:3-19``): ``DLPOLY``,
+``PDB``, ``XYZ``, ``Input``, ``MolecularSystem``, ``Molecule``, ``compare_properties_dict``,
+``make_supercell``, ``periodic_table``.  See DESIGN.md / INTEGRATION.md.
 """
-__all__ = ["Engine", "default_engine"]
+_LAZY = {
+    "Engine": "engine", "default_engine": "engine",
+    "MolecularSystem": "molecular", "Molecule": "molecular",
+    "DLPOLY": "trajectory", "PDB": "trajectory", "XYZ": "trajectory", "make_supercell": "trajectory",
+    "Input": "io_tools", "Output": "io_tools",
+    "compare_properties_dict": "utilities",
+    "periodic_table": "tables",
+}
+__all__ = sorted(_LAZY)
 
 
 def __getattr__(name):
-    if name in ("Engine", "default_engine"):
-        from . import engine
-        return getattr(engine, name)
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
     raise AttributeError(name)

@@ -779,6 +779,7 @@ static int set_smem(K kern, size_t bytes, int max_smem) {
 
 extern "C" {
 
+void pwb_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); }
 int pwb_abi_version(void) { return PWB_ABI_VERSION; }
 const char* pwb_last_error(void) { return g_err; }
 

@@ -1,0 +1,389 @@
+// pwb_periodic.cu -- periodic decomposition on the GPU: create_supercell (utilities.py:768-810) and
+// discrete_molecules (utilities.py:820-1085) for batches of cell-frames.
+//
+// The reference grows molecules with value-equality list operations over a 27-image supercell; the
+// same result is obtained here from (1) a periodic bond table of the cell atoms -- for every
+// non-terminal atom a, every bonded (atom b, integer image offset m), sorted by (m, b) -- and (2) an
+// ordered, level-synchronous flood fill over nodes (atom, image) whose visiting order reproduces the
+// reference's atom order (see oracle/pw_periodic_oracle.py for the rule and its derivation).
+//   k_dm_prepare  CTA/frame      : inverse lattice, fractional + rounded coordinates, COM, boundary
+//   k_dm_bonds    thread/(frame,atom): bond table, 27 candidate images around the minimum image
+//   k_dm_fill     warp/frame     : seeds, flood fill, centre-of-mass filter, output
+#include <stdio.h>
+
+#include "pwb_device.cuh"
+
+namespace pwb {
+
+constexpr int DM_ADJ_CAP = 12;
+constexpr int DM_FRAME_D = 32;   // per-frame doubles: lattice[9], inv[9], pseudo[3], com[3], boundary[2]
+
+__device__ __forceinline__ double round8(double v) { return rint(v * 1e8) / 1e8; }
+
+struct DmArgs {
+  int F, N, rebuild, periodic, n_types, out_cap, mol_cap;
+  double tol;
+  const double* coords;    // [F][N][3]
+  const double* lattice;   // [F][9] row-major (or [1][9] if lattice_shared)
+  int lattice_shared;
+  const int* atom_type;    // [N]
+  const double* type_cov;  // [n_types]
+  const double* type_mass;
+  const int* type_terminal;
+  // workspace
+  double* frame_d;   // [F][DM_FRAME_D]
+  double* frac;      // [F][N][3]
+  double* xr;        // [F][N][3] coordinates rounded to 8 decimals
+  unsigned* adj;     // [F][N][DM_ADJ_CAP] packed (image key << 20 | atom)
+  int* deg;          // [F][N]
+  unsigned* vis;     // [F][ceil(27N/32)]
+  unsigned char* rem;  // [F][N]
+  int* front;        // [F][2][out_cap]
+  // outputs
+  int* n_mol;        // [F]
+  int* mol_off;      // [F][mol_cap+1]
+  int* out_src;      // [F][out_cap] source atom index
+  double* out_xyz;   // [F][out_cap][3]
+  int* status;       // [F] bit 1: adjacency overflow, 2: output overflow, 4: molecule overflow
+};
+
+__global__ void __launch_bounds__(128)
+k_dm_prepare(DmArgs A) {
+  const int f = blockIdx.x, tid = threadIdx.x;
+  __shared__ double red[64];
+  __shared__ double inv[9], lat[9];
+  double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
+  const double* X = A.coords + (size_t)f * A.N * 3;
+  if (tid == 0) {
+    A.status[f] = 0;
+    if (A.periodic) {
+      const double* L = A.lattice + (A.lattice_shared ? 0 : (size_t)f * 9);
+      for (int i = 0; i < 9; i++) lat[i] = L[i];
+      double a = L[0], b = L[1], c = L[2], d = L[3], e = L[4], g = L[5], h = L[6], i2 = L[7], j = L[8];
+      double det = a * (e * j - g * i2) - b * (d * j - g * h) + c * (d * i2 - e * h);
+      inv[0] = (e * j - g * i2) / det; inv[1] = (c * i2 - b * j) / det; inv[2] = (b * g - c * e) / det;
+      inv[3] = (g * h - d * j) / det; inv[4] = (a * j - c * h) / det; inv[5] = (c * d - a * g) / det;
+      inv[6] = (d * i2 - e * h) / det; inv[7] = (b * h - a * i2) / det; inv[8] = (a * e - b * d) / det;
+      for (int i = 0; i < 9; i++) { fd[i] = lat[i]; fd[9 + i] = inv[i]; }
+    }
+  }
+  __syncthreads();
+  double mx = 0, my = 0, mz = 0, mt = 0;
+  for (int a = tid; a < A.N; a += blockDim.x) {
+    double x = X[3 * a], y = X[3 * a + 1], z = X[3 * a + 2];
+    double m = A.type_mass[A.atom_type[a]];
+    mx += x * m; my += y * m; mz += z * m; mt += m;
+    double* xr = A.xr + ((size_t)f * A.N + a) * 3;
+    xr[0] = round8(x); xr[1] = round8(y); xr[2] = round8(z);
+    if (A.periodic) {
+      double* fr = A.frac + ((size_t)f * A.N + a) * 3;
+      fr[0] = inv[0] * x + inv[1] * y + inv[2] * z;
+      fr[1] = inv[3] * x + inv[4] * y + inv[5] * z;
+      fr[2] = inv[6] * x + inv[7] * y + inv[8] * z;
+    }
+    A.rem[(size_t)f * A.N + a] = 1;
+  }
+  mx = block_sum(mx, red); my = block_sum(my, red); mz = block_sum(mz, red); mt = block_sum(mt, red);
+  if (tid == 0) {
+    double cx = mx / mt, cy = my / mt, cz = mz / mt;
+    fd[21] = cx; fd[22] = cy; fd[23] = cz;
+    if (A.periodic) {
+      // pseudo origin = lattice * (0.26, 0.25, 0.25)   (utilities.py:905-906)
+      fd[18] = lat[0] * 0.26 + lat[1] * 0.25 + lat[2] * 0.25;
+      fd[19] = lat[3] * 0.26 + lat[4] * 0.25 + lat[5] * 0.25;
+      fd[20] = lat[6] * 0.26 + lat[7] * 0.25 + lat[8] * 0.25;
+      // np.allclose(com, [0.01, 0, 0], atol=1): |a-b| <= atol + rtol*|b|  (utilities.py:919-923)
+      bool near = fabs(cx - 0.01) <= 1.0 + 1e-5 * 0.01 && fabs(cy) <= 1.0 && fabs(cz) <= 1.0;
+      fd[24] = near ? -0.5 : 0.0; fd[25] = near ? 0.5 : 1.0;
+    } else {
+      fd[18] = cx + 0.01; fd[19] = cy; fd[20] = cz;       // utilities.py:925-927
+    }
+  }
+}
+
+// bond table: one thread per (frame, parent atom); tiles of atoms staged in shared memory
+constexpr int DM_TILE = 128;
+__global__ void __launch_bounds__(DM_TILE)
+k_dm_bonds(DmArgs A, double max_dist) {
+  const int f = blockIdx.y, a = blockIdx.x * DM_TILE + threadIdx.x;
+  __shared__ double sfx[DM_TILE], sfy[DM_TILE], sfz[DM_TILE], sx[DM_TILE], sy[DM_TILE], sz[DM_TILE], sc[DM_TILE];
+  const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
+  const double* frac = A.frac + (size_t)f * A.N * 3;
+  const double* xr = A.xr + (size_t)f * A.N * 3;
+  double L[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) L[i] = A.periodic ? fd[i] : 0.0;
+  const bool active = a < A.N && !A.type_terminal[A.atom_type[a < A.N ? a : 0]];
+  double ax = 0, ay = 0, az = 0, afx = 0, afy = 0, afz = 0, acov = 0;
+  if (a < A.N) {
+    ax = xr[3 * a]; ay = xr[3 * a + 1]; az = xr[3 * a + 2];
+    acov = A.type_cov[A.atom_type[a]];
+    if (A.periodic) { afx = frac[3 * a]; afy = frac[3 * a + 1]; afz = frac[3 * a + 2]; }
+  }
+  unsigned list[DM_ADJ_CAP];
+  int n = 0, overflow = 0;
+  const bool images = A.rebuild != 0;
+  for (int t0 = 0; t0 < A.N; t0 += DM_TILE) {
+    int b = t0 + threadIdx.x;
+    __syncthreads();
+    if (b < A.N) {
+      sx[threadIdx.x] = xr[3 * b]; sy[threadIdx.x] = xr[3 * b + 1]; sz[threadIdx.x] = xr[3 * b + 2];
+      sc[threadIdx.x] = A.type_cov[A.atom_type[b]];
+      if (A.periodic) { sfx[threadIdx.x] = frac[3 * b]; sfy[threadIdx.x] = frac[3 * b + 1]; sfz[threadIdx.x] = frac[3 * b + 2]; }
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int lim = min(DM_TILE, A.N - t0);
+    for (int j = 0; j < lim; j++) {
+      const int bb = t0 + j;
+      const double rs = acov + sc[j];
+      if (!images) {
+        double dx = ax - sx[j], dy = ay - sy[j], dz = az - sz[j];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
+          if (n < DM_ADJ_CAP) list[n++] = ((unsigned)(4 * 81 + 4 * 9 + 4) << 20) | (unsigned)bb; else overflow = 1;
+        }
+        continue;
+      }
+      // minimum image offset, then the 27 offsets around it
+      const double m0x = rint(afx - sfx[j]), m0y = rint(afy - sfy[j]), m0z = rint(afz - sfz[j]);
+      // cheap reject: nearest image already farther than the cut-off in every candidate? (keep exact)
+      for (int ia = -1; ia <= 1; ia++)
+        for (int ib = -1; ib <= 1; ib++)
+          for (int ic = -1; ic <= 1; ic++) {
+            const double ma = m0x + ia, mb = m0y + ib, mc = m0z + ic;
+            double X, Y, Z;
+            if (ma == 0 && mb == 0 && mc == 0) { X = sx[j]; Y = sy[j]; Z = sz[j]; }
+            else {
+              double fx = sfx[j] + ma, fy = sfy[j] + mb, fz = sfz[j] + mc;
+              X = round8(L[0] * fx + L[1] * fy + L[2] * fz);
+              Y = round8(L[3] * fx + L[4] * fy + L[5] * fz);
+              Z = round8(L[6] * fx + L[7] * fy + L[8] * fz);
+            }
+            double dx = ax - X, dy = ay - Y, dz = az - Z;
+            double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 >= max_dist * max_dist) continue;
+            double d = sqrt(d2);
+            if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
+              int ka = (int)ma + 4, kb = (int)mb + 4, kc = (int)mc + 4;
+              if (ka < 0 || ka > 8 || kb < 0 || kb > 8 || kc < 0 || kc > 8) continue;   // > 4 cells away: unreachable
+              unsigned key = ((unsigned)(ka * 81 + kb * 9 + kc) << 20) | (unsigned)bb;
+              if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
+            }
+          }
+    }
+  }
+  if (a >= A.N) return;
+  // sort by (image key, atom): ascending supercell index after translation
+  for (int i = 1; i < n; i++) {
+    unsigned v = list[i];
+    int j = i - 1;
+    while (j >= 0 && list[j] > v) { list[j + 1] = list[j]; j--; }
+    list[j + 1] = v;
+  }
+  unsigned* out = A.adj + ((size_t)f * A.N + a) * DM_ADJ_CAP;
+  for (int i = 0; i < n; i++) out[i] = list[i];
+  A.deg[(size_t)f * A.N + a] = n;
+  if (overflow) atomicOr(&A.status[f], 1);
+}
+
+// flood fill: one warp per frame; lane 0 walks the graph, all lanes do the O(N) steps
+constexpr int DM_FILL_WARPS = 4;
+__global__ void __launch_bounds__(DM_FILL_WARPS * 32)
+k_dm_fill(DmArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * DM_FILL_WARPS + (threadIdx.x >> 5);
+  if (f >= A.F) return;
+  const int N = A.N;
+  const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
+  const double* xr = A.xr + (size_t)f * N * 3;
+  const double* frac = A.frac + (size_t)f * N * 3;
+  const unsigned* adj = A.adj + (size_t)f * N * DM_ADJ_CAP;
+  const int* deg = A.deg + (size_t)f * N;
+  const int nimg = A.rebuild ? 27 : 1;
+  const int vis_words = (nimg * N + 31) / 32;
+  unsigned* vis = A.vis + (size_t)f * ((27 * N + 31) / 32);
+  unsigned char* rem = A.rem + (size_t)f * N;
+  int* fr0 = A.front + (size_t)f * 2 * A.out_cap;
+  int* fr1 = fr0 + A.out_cap;
+  int* osrc = A.out_src + (size_t)f * A.out_cap;
+  double* oxyz = A.out_xyz + (size_t)f * A.out_cap * 3;
+  int* moff = A.mol_off + (size_t)f * (A.mol_cap + 1);
+  const int cimg = A.rebuild ? 13 : 0;           // image index of the cell itself
+  const double psx = fd[18], psy = fd[19], psz = fd[20];
+  const double yy = __dadd_rn(__dadd_rn(__dmul_rn(psx, psx), __dmul_rn(psy, psy)), __dmul_rn(psz, psz));
+  int nout = 0, nmol = 0, st = 0;
+  if (lane == 0) moff[0] = 0;
+  while (true) {
+    // ---- seed: remaining non-terminal atom closest to the pseudo origin, first arg-min, with
+    // sklearn's euclidean_distances operation order (utilities.py:944-953)
+    ValIdx best; best.v = PWB_INF; best.i = 0x7fffffff;
+    for (int a = lane; a < N; a += 32) {
+      if (!rem[a] || A.type_terminal[A.atom_type[a]]) continue;
+      double x = xr[3 * a], y = xr[3 * a + 1], z = xr[3 * a + 2];
+      double dot = __dadd_rn(__dadd_rn(__dmul_rn(x, psx), __dmul_rn(y, psy)), __dmul_rn(z, psz));
+      double xx = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+      double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), xx), yy);
+      ValIdx c; c.v = sqrt(fmax(d2, 0.0)); c.i = a;
+      best = vi_min(best, c);
+    }
+    best = warp_vi_min(best);
+    if (best.i == 0x7fffffff) break;
+    for (int w = lane; w < vis_words; w += 32) vis[w] = 0u;
+    __syncwarp();
+    const int start = nout;
+    int overflow = 0;
+    if (lane == 0) {
+      int* cur = fr0; int* nxt = fr1;
+      int ncur = 1, seed = cimg * N + best.i;
+      cur[0] = seed;
+      vis[seed >> 5] |= 1u << (seed & 31);
+      while (ncur > 0) {
+        int nn = 0;
+        for (int q = 0; q < ncur; q++) {
+          const int p = cur[q];
+          const int a = p % N, img = p / N;
+          if (nout < A.out_cap) osrc[nout] = p; else overflow = 1;   // node id for now; resolved below
+          nout++;
+          if (A.type_terminal[A.atom_type[a]]) continue;
+          int sa = 0, sb = 0, sc = 0;
+          if (A.rebuild) { sa = img / 9 - 1; sb = (img / 3) % 3 - 1; sc = img % 3 - 1; }
+          const int dg = deg[a];
+          for (int pass = 0; pass < (A.rebuild ? 2 : 1); pass++) {
+            for (int e = 0; e < dg; e++) {
+              const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
+              const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
+              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
+              int node;
+              bool central;
+              if (A.rebuild) {
+                if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) continue;
+                const int im = (ma + 1) * 9 + (mb + 1) * 3 + (mc + 1);
+                node = im * N + b;
+                central = im == 13;
+              } else { node = b; central = true; }
+              const bool cellpath = central && rem[b];
+              if ((pass == 0) != cellpath) continue;     // pass 0: remaining cell atoms; pass 1: the rest
+              const unsigned bit = 1u << (node & 31);
+              if (vis[node >> 5] & bit) continue;
+              vis[node >> 5] |= bit;
+              if (nn < A.out_cap) nxt[nn] = node; else overflow = 1;
+              nn++;
+            }
+          }
+        }
+        for (int q = 0; q < ncur; q++) {
+          const int p = cur[q];
+          if (p / N == cimg) rem[p % N] = 0;
+        }
+        int* t = cur; cur = nxt; nxt = t;
+        ncur = min(nn, A.out_cap);
+      }
+    }
+    nout = __shfl_sync(0xffffffffu, nout, 0);
+    overflow = __shfl_sync(0xffffffffu, overflow, 0);
+    __syncwarp();
+    if (overflow || nout > A.out_cap) { st |= 2; break; }
+    // ---- resolve nodes to (source atom, coordinates); centre of mass for the filter
+    double mx = 0, my = 0, mz = 0, mt = 0;
+    for (int q = start + lane; q < nout; q += 32) {
+      const int p = osrc[q];
+      const int a = p % N, img = p / N;
+      double X, Y, Z;
+      if (!A.rebuild || img == 13) { X = xr[3 * a]; Y = xr[3 * a + 1]; Z = xr[3 * a + 2]; }
+      else {
+        double fx = frac[3 * a] + (img / 9 - 1), fy = frac[3 * a + 1] + ((img / 3) % 3 - 1), fz = frac[3 * a + 2] + (img % 3 - 1);
+        X = round8(fd[0] * fx + fd[1] * fy + fd[2] * fz);
+        Y = round8(fd[3] * fx + fd[4] * fy + fd[5] * fz);
+        Z = round8(fd[6] * fx + fd[7] * fy + fd[8] * fz);
+      }
+      oxyz[3 * q] = X; oxyz[3 * q + 1] = Y; oxyz[3 * q + 2] = Z;
+      osrc[q] = a;
+      double m = A.type_mass[A.atom_type[a]];
+      mx += X * m; my += Y * m; mz += Z * m; mt += m;
+    }
+    mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz); mt = warp_sum(mt);
+    bool keep = true;
+    if (A.rebuild) {   // utilities.py:1062-1077
+      double cx = mx / mt, cy = my / mt, cz = mz / mt;
+      double f0 = round8(fd[9] * cx + fd[10] * cy + fd[11] * cz);
+      double f1 = round8(fd[12] * cx + fd[13] * cy + fd[14] * cz);
+      double f2 = round8(fd[15] * cx + fd[16] * cy + fd[17] * cz);
+      const double lo = fd[24], hi = fd[25];
+      keep = f0 >= lo && f0 < hi && f1 >= lo && f1 < hi && f2 >= lo && f2 < hi;
+    }
+    if (keep) {
+      if (nmol >= A.mol_cap) { st |= 4; break; }
+      nmol++;
+      if (lane == 0) moff[nmol] = nout;
+    } else nout = start;
+    __syncwarp();
+  }
+  if (lane == 0) { A.n_mol[f] = nmol; if (st) atomicOr(&A.status[f], st); }
+}
+
+}  // namespace pwb
+
+using namespace pwb;
+
+extern "C" {
+
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int pwb_dm_workspace_layout(int F, int N, int out_cap, pwb_dm_layout* L) {
+  size_t o = 0;
+  L->frame_d = o; o = up256(o + sizeof(double) * (size_t)F * DM_FRAME_D);
+  L->frac = o; o = up256(o + sizeof(double) * (size_t)F * N * 3);
+  L->xr = o; o = up256(o + sizeof(double) * (size_t)F * N * 3);
+  L->adj = o; o = up256(o + sizeof(unsigned) * (size_t)F * N * DM_ADJ_CAP);
+  L->deg = o; o = up256(o + sizeof(int) * (size_t)F * N);
+  L->vis = o; o = up256(o + sizeof(unsigned) * (size_t)F * ((27 * (size_t)N + 31) / 32));
+  L->rem = o; o = up256(o + (size_t)F * N);
+  L->front = o; o = up256(o + sizeof(int) * (size_t)F * 2 * out_cap);
+  L->total = o;
+  return 0;
+}
+size_t pwb_dm_workspace_bytes(int F, int N, int out_cap) {
+  pwb_dm_layout L;
+  pwb_dm_workspace_layout(F, N, out_cap, &L);
+  return L.total;
+}
+
+// discrete_molecules for F cell-frames of N atoms each (utilities.py:820-1085; with `rebuild` the
+// supercell of create_supercell, utilities.py:768-810, is implied).  All pointers are device pointers.
+//   coords [F][N][3]; lattice [F][9] row-major (one matrix if lattice_shared; NULL = non-periodic)
+//   atom_type [N]; type_cov/type_mass/type_terminal [n_types]
+//   outputs: n_mol [F]; mol_off [F][mol_cap+1]; out_src [F][out_cap]; out_xyz [F][out_cap][3];
+//            status [F] (1 bond-table overflow, 2 output overflow, 4 molecule overflow)
+int pwb_discrete_molecules(int F, int N, int rebuild, double tol, double max_cov,
+                           const double* coords, const double* lattice, int lattice_shared,
+                           const int* atom_type, int n_types, const double* type_cov, const double* type_mass,
+                           const int* type_terminal, int out_cap, int mol_cap,
+                           int* n_mol, int* mol_off, int* out_src, double* out_xyz, int* status,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  pwb_dm_layout L;
+  pwb_dm_workspace_layout(F, N, out_cap, &L);
+  if (workspace_bytes < L.total) { pwb_set_error("discrete_molecules: workspace too small"); return 1; }
+  if (N >= (1 << 20)) { pwb_set_error("discrete_molecules: too many atoms per cell"); return 1; }
+  if (rebuild && !lattice) { pwb_set_error("discrete_molecules: rebuild needs a lattice"); return 1; }
+  char* p = (char*)workspace;
+  DmArgs A;
+  A.F = F; A.N = N; A.rebuild = rebuild; A.periodic = lattice != nullptr; A.n_types = n_types;
+  A.out_cap = out_cap; A.mol_cap = mol_cap; A.tol = tol;
+  A.coords = coords; A.lattice = lattice; A.lattice_shared = lattice_shared;
+  A.atom_type = atom_type; A.type_cov = type_cov; A.type_mass = type_mass; A.type_terminal = type_terminal;
+  A.frame_d = (double*)(p + L.frame_d); A.frac = (double*)(p + L.frac); A.xr = (double*)(p + L.xr);
+  A.adj = (unsigned*)(p + L.adj); A.deg = (int*)(p + L.deg); A.vis = (unsigned*)(p + L.vis);
+  A.rem = (unsigned char*)(p + L.rem); A.front = (int*)(p + L.front);
+  A.n_mol = n_mol; A.mol_off = mol_off; A.out_src = out_src; A.out_xyz = out_xyz; A.status = status;
+  k_dm_prepare<<<F, 128, 0, s>>>(A);
+  dim3 g((N + DM_TILE - 1) / DM_TILE, F);
+  k_dm_bonds<<<g, DM_TILE, 0, s>>>(A, 2 * max_cov + tol);
+  k_dm_fill<<<(F + DM_FILL_WARPS - 1) / DM_FILL_WARPS, DM_FILL_WARPS * 32, 0, s>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pwb_set_error(cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // extern "C"

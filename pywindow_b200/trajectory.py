@@ -1,0 +1,342 @@
+"""Trajectory front-ends (DL_POLY HISTORY, XYZ, PDB) with the reference's interface
+(``pywindow/_internal/trajectory.py``: ``Trajectory.analysis`` :350-494, ``DLPOLY`` :589-833, ``XYZ``
+:836-931, ``PDB`` :934-1045) and a *batched* GPU analysis.
+
+Where the reference loops ``frame -> MolecularSystem -> Molecule.full_analysis`` (optionally fanned out
+over a ``multiprocessing.Pool``), ``analysis()`` here decodes the requested frames into one
+``[F, N, 3]`` array, analyses them in large GPU batches and rebuilds the same
+``analysis_output[frame][molecule] = properties`` dictionaries.  If ``torch.distributed`` is
+initialised, the frame list is sharded over the ranks (contiguous blocks) and the result records are
+gathered once at the end (NCCL over NVLink on GPUs).
+
+Known reference bugs at this boundary are superseded, not reproduced: ``frames=(a, b)`` works,
+PDB trajectory frames decode, XYZ frames are delimited by their atom-count lines.
+"""
+from __future__ import annotations
+
+import json
+import mmap
+import pathlib
+import re
+
+import numpy as np
+
+from . import _lib
+from . import utilities as U
+from .distributed import gather_records, shard_range, world
+from .engine import default_engine, record_to_properties
+from .molecular import MolecularSystem
+
+
+class _ParallelAnalysisError(Exception):
+    def __init__(self, message):
+        self.message = message
+
+
+class _TrajectoryError(Exception):
+    def __init__(self, message):
+        self.message = message
+
+
+class _FormatError(Exception):
+    def __init__(self, message):
+        self.message = message
+
+
+class _FunctionError(Exception):
+    def __init__(self, message):
+        self.message = message
+
+
+def make_supercell(system, matrix, supercell=(1, 1, 1)):
+    """Replicate a periodic system ``supercell`` times along a, b, c (trajectory.py:75-118)."""
+    from .periodic import create_supercell
+    user = [[0, int(s) - 1] for s in supercell]
+    sysd = dict(system)
+    sysd["lattice"] = matrix
+    out = create_supercell(sysd, supercell=user)
+    return MolecularSystem.load_system(out)
+
+
+class Trajectory:
+    """Shared machinery: frame selection, batched GPU analysis, result storage."""
+
+    batch_frames = 8192
+
+    def __init__(self, filepath):
+        self.filepath = pathlib.Path(filepath)
+        self.system_id = self.filepath.name.split(".")[0]
+        self.frames = {}
+        self.analysis_output = {}
+        self.trajectory_map = {}
+        self.no_of_frames = 0
+
+    # ---- to be provided by the format classes
+    def _decode_frame(self, frame_bytes):
+        raise NotImplementedError
+
+    def _frame_bytes(self, frame):
+        start, end = self.trajectory_map[frame]
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            return mm[start:end]
+
+    # ---- frame access (trajectory.py:121-249)
+    def _get_frame(self, frame_coordinates, frame_no, swap_atoms=None, forcefield=None, extract_data=True):  # noqa: FBT002
+        start, end = frame_coordinates
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            raw = mm[start:end]
+        if extract_data is False:
+            return raw.decode("utf-8")
+        molsys = MolecularSystem.load_system(self._decode_frame(raw), "_".join([self.system_id, str(frame_no)]))
+        if swap_atoms is not None:
+            molsys.swap_atom_keys(swap_atoms)
+        if forcefield is not None:
+            molsys.decipher_atom_keys(forcefield)
+        return molsys
+
+    def _select(self, frames):
+        if isinstance(frames, (int, np.integer)):
+            return [int(frames)]
+        if isinstance(frames, list):
+            if not all(isinstance(f, (int, np.integer)) for f in frames):
+                raise _FunctionError("The list should be populated with integers only.")
+            return [int(f) for f in frames]
+        if isinstance(frames, tuple):
+            if len(frames) != 2 or not all(isinstance(f, (int, np.integer)) for f in frames):
+                raise _FunctionError("The tuple should contain only two integers for the begining and the end "
+                                     "of the frames range.")
+            return list(range(frames[0], frames[1]))
+        if isinstance(frames, str):
+            if frames in ("all", "everything"):
+                return list(range(self.no_of_frames))
+            raise _FunctionError("Didn't recognise the keyword. (see manual)")
+        raise _FunctionError("frames must be an int, a list of ints, a (start, end) tuple or 'all'.")
+
+    def get_frames(self, frames="all", override=False, **kwargs):  # noqa: FBT002
+        if override is True:
+            self.frames = {}
+        out = {}
+        for f in self._select(frames):
+            if f not in self.frames:
+                self.frames[f] = self._get_frame(self.trajectory_map[f], f, **kwargs)
+            out[f] = self.frames[f]
+        return out
+
+    # ---- the batched analysis (replaces trajectory.py:350-586)
+    def analysis(self, frames="all", ncpus=1, ncpus_analysis=1, override=False, modular=False, rebuild=False,  # noqa: ARG002, FBT002, PLR0913
+                 swap_atoms=None, forcefield=None, **gpu_kwargs):
+        """Analyse frames; results go to ``analysis_output`` exactly as in the reference.
+        ``ncpus`` / ``ncpus_analysis`` are accepted and ignored (one GPU batch replaces the pools)."""
+        todo = self._select(frames)
+        if override is False:
+            todo = [f for f in todo if f not in self.analysis_output]
+        if not todo:
+            return
+        rank, size = world()
+        lo, hi = shard_range(len(todo), rank, size)
+        mine = todo[lo:hi]
+        if modular:
+            records, keys = self._analyse_modular(mine, rebuild, swap_atoms, forcefield, gpu_kwargs)
+        else:
+            records, keys = self._analyse_single(mine, swap_atoms, forcefield, gpu_kwargs)
+        if size > 1:
+            records, keys = gather_records(records, keys)
+        for (frame, mol_key), rec in zip(keys, records):
+            self.analysis_output.setdefault(frame, {})[mol_key] = record_to_properties(rec)
+
+    def _elements_of(self, frame, swap_atoms, forcefield):
+        ms = self._get_frame(self.trajectory_map[frame], frame, swap_atoms=swap_atoms, forcefield=forcefield)
+        if "elements" not in ms.system:
+            raise U._FunctionError(
+                "The 'elements' key is missing in the 'system' dictionary attribute of the MolecularSystem object. "
+                "Which means, you need to decipher the forcefield based atom keys first (see manual).")
+        return ms.system["elements"]
+
+    def _decode_coordinates(self, frames):
+        """[F, N, 3] float64 for the requested frames (atom order is frame invariant)."""
+        out = None
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            for k, f in enumerate(frames):
+                start, end = self.trajectory_map[f]
+                xyz = self._decode_xyz_only(mm[start:end])
+                if out is None:
+                    out = np.empty((len(frames),) + xyz.shape, dtype=np.float64)
+                if xyz.shape != out.shape[1:]:
+                    raise _TrajectoryError(f"frame {f} has {xyz.shape[0]} atoms, expected {out.shape[1]}")
+                out[k] = xyz
+        return out
+
+    def _decode_xyz_only(self, raw):
+        return np.asarray(self._decode_frame(raw)["coordinates"], dtype=np.float64)
+
+    def _analyse_single(self, frames, swap_atoms, forcefield, gpu_kwargs):
+        eng = default_engine()
+        if not frames:
+            return np.zeros((0, eng.rec_stride)), []
+        elements = self._elements_of(frames[0], swap_atoms, forcefield)
+        recs = []
+        for s in range(0, len(frames), self.batch_frames):
+            chunk = frames[s:s + self.batch_frames]
+            recs.append(eng.analyse_frames(self._decode_coordinates(chunk), elements, **gpu_kwargs).host_records())
+        return np.concatenate(recs), [(f, "0") for f in frames]
+
+    def _analyse_modular(self, frames, rebuild, swap_atoms, forcefield, gpu_kwargs):
+        eng = default_engine()
+        mols, keys = [], []
+        for f in frames:
+            ms = self._get_frame(self.trajectory_map[f], f, swap_atoms=swap_atoms, forcefield=forcefield)
+            ms.make_modular(rebuild=rebuild)
+            for k, m in ms.molecules.items():
+                mols.append((m.elements, m.coordinates))
+                keys.append((f, k))
+        if not mols:
+            return np.zeros((0, eng.rec_stride)), []
+        return eng.analyse_molecules(mols, **gpu_kwargs).host_records(), keys
+
+    # ---- output (trajectory.py:251-347)
+    def save_analysis(self, filepath=None, **kwargs):
+        if filepath is None:
+            filepath = pathlib.Path.cwd() / f"{self.system_id}_pywindow_analysis"
+        filepath = pathlib.Path(filepath)
+        if filepath.suffix != ".json":
+            filepath = pathlib.Path(str(filepath) + ".json")
+        out = {str(f): {str(k): v for k, v in mols.items()} for f, mols in self.analysis_output.items()}
+        with filepath.open("w") as fh:
+            json.dump(out, fh, default=U.to_list, **kwargs)
+
+    def save_frames(self, frames, filepath=None, filetype="pdb", **kwargs):
+        if filepath is None:
+            filepath = pathlib.Path.cwd() / str(self.system_id)
+        for f, ms in self.get_frames(frames).items():
+            ms.dump_system(filepath=pathlib.Path(f"{filepath}_{f}.{filetype}"), **kwargs)
+
+
+def _float_block(lines):
+    return np.array(b" ".join(lines).split(), dtype=np.float64)
+
+
+class DLPOLY(Trajectory):
+    """DL_POLY_C HISTORY file.  The file is indexed once (byte offsets of every ``timestep`` record);
+    frames are decoded on demand from the memory map."""
+
+    _imcon = {0: "nonperiodic", 1: "cubic", 2: "orthorhombic", 3: "parallelepiped", 4: "truncated octahedral",
+              5: "rhombic dodecahedral", 6: "x-y parallelogram", 7: "hexagonal prism"}
+    _keytrj = {0: "coordinates", 1: "coordinates and velocities", 2: "coordinates, velocities and forces"}
+
+    def __init__(self, filepath):
+        super().__init__(filepath)
+        self._map_history()
+
+    def _map_history(self):
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            starts = [m.start() for m in re.finditer(rb"^timestep", mm, flags=re.MULTILINE)]
+            size = len(mm)
+            if not starts:
+                raise _TrajectoryError("no 'timestep' record found: not a DL_POLY HISTORY file")
+            head = mm[:starts[0]].decode("utf-8").split("\n")
+        header = [int(i) for i in head[1].split()]
+        self.trajectory_map = {"header": header}
+        self.content_type = self._keytrj[header[0]]
+        self.periodic_boundary = self._imcon[header[1]]
+        self.no_of_atoms = header[2]
+        bounds = starts + [size]
+        for k in range(len(starts)):
+            self.trajectory_map[k] = [bounds[k], bounds[k + 1]]
+        self.no_of_frames = len(starts)
+        self.check_log = ""
+
+    def _layout(self, lines):
+        info = lines[0].split()
+        keytrj, imcon = int(info[3]), int(info[4])
+        first = 4 if imcon in (1, 2, 3) else 1
+        return info, keytrj, imcon, first, keytrj + 2
+
+    def _decode_frame(self, raw):
+        lines = [ln for ln in bytes(raw).split(b"\n") if ln.strip()]
+        info, keytrj, imcon, first, stride = self._layout(lines)
+        frame = {"frame_info": {"nstep": int(info[1]), "natms": int(info[2]), "keytrj": keytrj, "imcon": imcon,
+                                "tstep": float(info[5])}}
+        if first == 4:
+            frame["lattice"] = _float_block(lines[1:4]).reshape(3, 3).T
+            frame["unit_cell"] = U.lattice_array_to_unit_cell(frame["lattice"])
+        body = lines[first:]
+        frame["atom_ids"] = np.array([ln.split()[0].decode("utf-8") for ln in body[0::stride]])
+        frame["coordinates"] = _float_block(body[1::stride]).reshape(-1, 3)
+        if keytrj >= 1:
+            frame["velocities"] = _float_block(body[2::stride]).reshape(-1, 3)
+        if keytrj >= 2:
+            frame["forces"] = _float_block(body[3::stride]).reshape(-1, 3)
+        return frame
+
+    def _decode_xyz_only(self, raw):
+        lines = [ln for ln in bytes(raw).split(b"\n") if ln.strip()]
+        _, _, _, first, stride = self._layout(lines)
+        return _float_block(lines[first + 1::stride]).reshape(-1, 3)
+
+
+class XYZ(Trajectory):
+    """Multi-frame XYZ file: every frame is ``natoms`` / comment / natoms atom lines."""
+
+    def __init__(self, filepath):
+        super().__init__(filepath)
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            pos, size, k = 0, len(mm), 0
+            while pos < size:
+                eol = mm.find(b"\n", pos)
+                eol = size if eol < 0 else eol
+                tok = mm[pos:eol].split()
+                if not tok:
+                    pos = eol + 1
+                    continue
+                try:
+                    natoms = int(tok[0])
+                except ValueError:
+                    raise _FormatError(f"expected an atom count at byte {pos} of {self.filepath}") from None
+                end = eol
+                for _ in range(natoms + 1):
+                    nxt = mm.find(b"\n", end + 1)
+                    end = size if nxt < 0 else nxt
+                self.trajectory_map[k] = [pos, min(end + 1, size)]
+                k += 1
+                pos = end + 1
+        self.no_of_frames = k
+
+    def _decode_frame(self, raw):
+        lines = bytes(raw).decode("utf-8").split("\n")
+        natoms = int(lines[0].split()[0])
+        tokens = [ln.split() for ln in lines[2:2 + natoms]]
+        return {"remarks": lines[1], "atom_ids": np.array([t[0] for t in tokens]),
+                "elements": np.array([t[0] for t in tokens]),
+                "coordinates": np.array([[float(t[1]), float(t[2]), float(t[3])] for t in tokens])}
+
+
+class PDB(Trajectory):
+    """Multi-model PDB file: frames end with an ``END`` record."""
+
+    def __init__(self, filepath):
+        super().__init__(filepath)
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            start, k, size = 0, 0, len(mm)
+            for m in re.finditer(rb"^END[^D\n]*\n?", mm, flags=re.MULTILINE):
+                if mm[start:m.start()].strip():
+                    self.trajectory_map[k] = [start, m.end()]
+                    k += 1
+                start = m.end()
+            if start < size and b"ATOM" in mm[start:size] or (start < size and b"HETATM" in mm[start:size]):
+                self.trajectory_map[k] = [start, size]
+                k += 1
+        self.no_of_frames = k
+
+    def _decode_frame(self, raw):
+        lines = bytes(raw).decode("utf-8").split("\n")
+        atoms = [ln for ln in lines if ln[:6] in ("HETATM", "ATOM  ")]
+        frame = {"remarks": [ln for ln in lines if ln[:6] == "REMARK"]}
+        cell = [float(ln[a:b]) for ln in lines if ln[:6] == "CRYST1"
+                for a, b in ((6, 15), (15, 24), (24, 33), (33, 40), (40, 47), (47, 54))]
+        if cell:
+            frame["unit_cell"] = np.array(cell)
+            frame["lattice"] = U.unit_cell_to_lattice_array(frame["unit_cell"])
+        frame["atom_ids"] = np.array([ln[12:16].strip() for ln in atoms], dtype="<U8")
+        frame["elements"] = np.array([ln[76:78].strip() for ln in atoms], dtype="<U8")
+        frame["coordinates"] = np.array([[float(ln[30:38]), float(ln[38:46]), float(ln[46:54])] for ln in atoms])
+        return frame

@@ -1,0 +1,126 @@
+"""CPU tests of the host side: C-ABI symbols, trajectory file mapping / decoding, frame selection,
+sharding arithmetic, atom-key deciphering, comparator.  No GPU compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_abi_exports_every_declared_symbol():
+    """libpwb.so loads and exports every function include/pwb.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "pwb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pwb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    so = os.path.join(ROOT, "pywindow_b200", "csrc", "libpwb.so")
+    assert os.path.exists(so), "run python __graft_entry__.py"
+    lib = ctypes.CDLL(so)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    lib.pwb_abi_version.restype = ctypes.c_int
+    assert lib.pwb_abi_version() == 1
+    from pywindow_b200 import _lib
+    assert set(_lib.EXPORTS) <= declared
+
+
+def test_workspace_layout_is_consistent():
+    from pywindow_b200 import _lib
+    L = _lib.load()
+    lay = _lib.WsLayout()
+    L.pwb_workspace_layout(10, 1680, 896, 16, ctypes.byref(lay))
+    assert lay.total == L.pwb_workspace_bytes(10, 1680, 896, 16)
+    offs = [lay.atoms, lay.atom_idx, lay.item_d, lay.item_i, lay.clear_k, lay.clear_pos, lay.clear_a2, lay.labels, lay.win_k]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+
+
+def test_engine_refuses_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pywindow_b200.engine import Engine, PwbNoDeviceError
+    with pytest.raises(PwbNoDeviceError):
+        Engine()
+
+
+@pytest.fixture()
+def md(tmp_path):
+    from pywindow_b200 import synthetic
+    g = [load_golden(f"md_frame{i:02d}") for i in range(3)]
+    X = np.stack([x["coords"] for x in g])
+    el = g[0]["elements"]
+    return tmp_path, el, X, synthetic
+
+
+def test_dlpoly_mapping_and_decode(md):
+    tmp, el, X, syn = md
+    from pywindow_b200.trajectory import DLPOLY
+    p = tmp / "HISTORY"
+    lat = np.diag([30.0, 31.0, 32.0])
+    syn.write_history(p, list(el), X, lattice=lat)
+    t = DLPOLY(p)
+    assert t.no_of_frames == 3 and t.no_of_atoms == len(el) and t.periodic_boundary == "parallelepiped"
+    fr = t._decode_frame(t._frame_bytes(1))
+    np.testing.assert_allclose(fr["coordinates"], X[1], rtol=1e-10)
+    np.testing.assert_allclose(fr["lattice"], lat)
+    assert list(fr["atom_ids"]) == list(el)
+    np.testing.assert_allclose(t._decode_coordinates([0, 2]), X[[0, 2]], rtol=1e-10)
+    ms = t.get_frames(2)[2]
+    assert ms.system["coordinates"].shape == (len(el), 3)
+
+
+def test_xyz_and_pdb_trajectories(md):
+    tmp, el, X, syn = md
+    from pywindow_b200.trajectory import PDB, XYZ
+    syn.write_xyz_trajectory(tmp / "t.xyz", el, X)
+    t = XYZ(tmp / "t.xyz")
+    assert t.no_of_frames == 3
+    np.testing.assert_allclose(t._decode_coordinates([1])[0], X[1], atol=1e-7)
+    syn.write_pdb_trajectory(tmp / "t.pdb", el, X, unit_cell=[30, 30, 30, 90, 90, 90])
+    t = PDB(tmp / "t.pdb")
+    assert t.no_of_frames == 3
+    fr = t._decode_frame(t._frame_bytes(2))
+    np.testing.assert_allclose(fr["coordinates"], X[2], atol=6e-4)
+    assert list(fr["elements"]) == list(el) and fr["unit_cell"].shape == (6,)
+
+
+def test_frame_selection_rules(md):
+    tmp, el, X, syn = md
+    from pywindow_b200.trajectory import DLPOLY, _FunctionError
+    syn.write_history(tmp / "H", list(el), X)
+    t = DLPOLY(tmp / "H")
+    assert t._select("all") == [0, 1, 2] and t._select(1) == [1] and t._select([2, 0]) == [2, 0]
+    assert t._select((0, 2)) == [0, 1]          # the reference raises here; superset
+    for bad in ("some", [0, "a"], (0, 1, 2)):
+        with pytest.raises(_FunctionError):
+            t._select(bad)
+
+
+def test_shard_ranges_cover_everything():
+    from pywindow_b200.distributed import shard_range
+    for n in (0, 1, 7, 8, 100, 100001):
+        for size in (1, 2, 3, 8):
+            r = [shard_range(n, k, size) for k in range(size)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(size - 1))
+            assert max(b - a for a, b in r) <= -(-n // size)
+
+
+def test_atom_key_deciphering_and_comparator():
+    from pywindow_b200 import utilities as U
+    assert U.decipher_atom_key("C1", "DLF") == "C" and U.decipher_atom_key("Cl12", "dl_f") == "Cl"
+    assert U.decipher_atom_key("ca", "opls") == "C" and U.decipher_atom_key("ni", "OPLSAA") == "N"
+    with pytest.raises(U._AtomKeyConflictError):
+        U.decipher_atom_key("he", "opls")
+    with pytest.raises(U._ForceFieldError):
+        U.decipher_atom_key("C1", "amber")
+    a = {"no_of_atoms": 3, "pore_diameter": {"diameter": 1.0, "atom": 2}, "windows": {"diameters": None, "centre_of_mass": None}}
+    b = {"no_of_atoms": 3, "pore_diameter": {"diameter": 1.0 + 1e-12, "atom": 2}, "windows": {"diameters": None, "centre_of_mass": None}}
+    assert U.compare_properties_dict(a, b) == (True, "none")
+    b["pore_diameter"]["atom"] = 1
+    assert U.compare_properties_dict(a, b) == (False, "pore_diameter.atom")
+    lat = U.unit_cell_to_lattice_array([10, 11, 12, 80, 95, 100])
+    np.testing.assert_allclose(U.lattice_array_to_unit_cell(lat), [10, 11, 12, 80, 95, 100])
