@@ -50,7 +50,8 @@ enum {
   PWB_REC_OPT_STOP = 21, /* its stop reason (0 pgtol, 1 ftol, 2 line search, 3 maxiter)          */
   PWB_REC_RADIUS = 22,   /* sampling-sphere radius used for windows                              */
   PWB_REC_NSURV = 23,    /* rays that survive the line-sphere pre-test                           */
-  PWB_REC_WIN0 = 24      /* then win_cap x {diameter, cx, cy, cz}; diameter NaN = window dropped */
+  PWB_REC_OPT_NFEV = 24, /* objective evaluations of the pore-centre search (4 per gradient)     */
+  PWB_REC_WIN0 = 28      /* then win_cap x {diameter, cx, cy, cz}; diameter NaN = window dropped */
 };
 
 enum {

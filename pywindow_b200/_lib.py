@@ -16,7 +16,8 @@ MAX_TYPES = 16
 REC_STATUS, REC_NATOMS, REC_COM, REC_MAXD, REC_MAXD_A1, REC_MAXD_A2, REC_AVGD = 0, 1, 2, 5, 6, 7, 8
 REC_PORE_D, REC_PORE_ATOM, REC_OPT_D, REC_OPT_ATOM, REC_OPT_C = 9, 10, 11, 12, 13
 REC_NRAYS, REC_NCLEAR, REC_NWIN, REC_EPS, REC_OPT_NIT, REC_OPT_STOP, REC_RADIUS, REC_NSURV = 16, 17, 18, 19, 20, 21, 22, 23
-REC_WIN0 = 24
+REC_OPT_NFEV = 24
+REC_WIN0 = 28
 ST_OPT_BOUNDS, ST_NO_CLEAR_RAY, ST_RAY_CAP, ST_WIN_CAP, ST_WIN_DROPPED, ST_WIN_NEGATIVE, ST_BAD_ITEM = 1, 2, 4, 8, 16, 32, 64
 STAGE_SCALARS, STAGE_AVGD, STAGE_OPT, STAGE_RAYS, STAGE_CLUSTER, STAGE_WINDOWS, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 

@@ -193,8 +193,9 @@ PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double (&B)[N][N]) {
       Bs[i] = a;
     }
     for (int i = 0; i < N; i++) { sBs += H.S[p][i] * Bs[i]; ys += H.Y[p][i] * H.S[p][i]; }
+    const double iys = 1.0 / ys, isBs = 1.0 / sBs;
     for (int i = 0; i < N; i++)
-      for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] / ys - Bs[i] * Bs[j] / sBs;
+      for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] * iys - Bs[i] * Bs[j] * isBs;
   }
 }
 

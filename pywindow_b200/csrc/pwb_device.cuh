@@ -120,49 +120,89 @@ __device__ __forceinline__ ValIdx block_vi(ValIdx a, bool want_max, double* redv
 // monotone.
 struct Bucketed {
   const double* x; const double* y; const double* z;   // [n] shifted coordinates
+  const double* w;                                     // [n] |x|^2
   const int* cls;                                      // [ncls+1] class starts
   const double* cr;                                    // [ncls] class radius
   int ncls;
 };
 
-__device__ __forceinline__ double min_clearance(const Bucketed& A, double qx, double qy, double qz) {
-  double best = PWB_INF;
-  for (int c = 0; c < A.ncls; c++) {
-    int b = A.cls[c], e = A.cls[c + 1];
-    if (b == e) continue;
-    double m = PWB_INF;
-    for (int i = b; i < e; i++) {
-      double dx = A.x[i] - qx, dy = A.y[i] - qy, dz = A.z[i] - qz;
-      double d2 = dx * dx + dy * dy + dz * dz;
-      m = fmin(m, d2);
-    }
-    best = fmin(best, sqrt(m) - A.cr[c]);
+// min_i(|x_i - q| - r_i) for K points at once.  |x-q|^2 = |x|^2 - 2 x.q + |q|^2: three FMAs and one
+// min per atom and point, |q|^2 and the sqrt once per class.
+template <int K>
+__device__ __forceinline__ void min_clearance_k(const Bucketed& A, const double* qx, const double* qy,
+                                                const double* qz, double* out) {
+  double ax[K], ay[K], az[K], qq[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    qq[k] = qx[k] * qx[k] + qy[k] * qy[k] + qz[k] * qz[k];
+    ax[k] = -2.0 * qx[k]; ay[k] = -2.0 * qy[k]; az[k] = -2.0 * qz[k];
+    out[k] = PWB_INF;
   }
-  return best;
+  for (int c = 0; c < A.ncls; c++) {
+    const int b = A.cls[c], e = A.cls[c + 1];
+    if (b == e) continue;
+    double m[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) m[k] = PWB_INF;
+    for (int i = b; i < e; i++) {
+      const double X = A.x[i], Y = A.y[i], Z = A.z[i], W = A.w[i];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = fmin(m[k], fma(ax[k], X, fma(ay[k], Y, fma(az[k], Z, W))));
+    }
+    const double rc = A.cr[c];
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = fmin(out[k], sqrt(fmax(m[k] + qq[k], 0.0)) - rc);
+  }
+}
+
+__device__ __forceinline__ double min_clearance(const Bucketed& A, double qx, double qy, double qz) {
+  double o[1];
+  min_clearance_k<1>(A, &qx, &qy, &qz, o);
+  return o[0];
 }
 
 // ---- warp-cooperative pore objective (lanes stride over atoms) ---------------------------------
 struct WarpAtoms {
   const double* x; const double* y; const double* z; const double* r;
   int n, lane;
+  const int* cls;      // [ncls+1] class starts of the type-bucketed atoms
+  int ncls;
 };
 
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
+
+// min_i(|x_i - p_k| - r_i) for K points; lanes stride over the atoms of one class at a time so the
+// sqrt is taken once per (lane, class, point) instead of once per (atom, point).
 template <int K>
 __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double* px, const double* py,
                                                const double* pz, double* out) {
-  double m[K];
+  double v[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) m[k] = PWB_INF;
-  for (int i = A.lane; i < A.n; i += 32) {
-    double ax = A.x[i], ay = A.y[i], az = A.z[i], ar = A.r[i];
+  for (int k = 0; k < K; k++) v[k] = PWB_INF;
+  for (int c = 0; c < A.ncls; c++) {
+    const int cb = A.cls[c], ce = A.cls[c + 1];
+    if (cb == ce) continue;
+    double m[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
-      m[k] = fmin(m[k], sqrt(dx * dx + dy * dy + dz * dz) - ar);
+    for (int k = 0; k < K; k++) m[k] = PWB_INF;
+    for (int i = cb + A.lane; i < ce; i += 32) {
+      const double ax = A.x[i], ay = A.y[i], az = A.z[i];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
+        m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
+      }
     }
+    const double rc = A.r[cb];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
   }
 #pragma unroll
-  for (int k = 0; k < K; k++) out[k] = warp_min(m[k]);
+  for (int k = 0; k < K; k++) {
+    double a = v[k];
+    for (int s = 16; s; s >>= 1) a = dmin(a, shfl_xor_d(a, s));
+    out[k] = a;
+  }
 }
 
 // pore_diameter with first-occurrence argmin over ORIGINAL atom indices (utilities.py:375-388)

@@ -112,14 +112,25 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     pb = vi_min(pb, c);
   }
   pb = block_vi(pb, false, red, redi);
-  // ---- maximum dimension (utilities.py:355-372): upper triangle incl. diagonal, first arg-max
+  // ---- maximum dimension (utilities.py:355-372): upper triangle incl. diagonal, first arg-max.
+  // Row i is spread over the block (j = i + tid); the sqrt is only taken when the pair can beat the
+  // thread's running maximum: d + ri + rj > best  <=>  d^2 > (best - ri - rj)^2 (guarded by 1e-12).
   ValIdx mb; mb.v = -PWB_INF; mb.i = 0x7fffffff;
-  for (int p = tid; p < n * n; p += nt) {
-    int i = p / n, j = p - i * n;
-    if (j < i) continue;
-    double dx = sx[i] - sx[j], dy = sy[i] - sy[j], dz = sz[i] - sz[j];
-    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) + (sr[i] + sr[j]); c.i = p;
-    mb = vi_max(mb, c);
+  {
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    for (int i = wid; i < n; i += nw) {
+      const double xi = sx[i], yi = sy[i], zi = sz[i], ri = sr[i];
+      for (int j = i + lane; j < n; j += 32) {
+        double dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+        double d2 = dx * dx + dy * dy + dz * dz;
+        double rr = ri + sr[j];
+        double thr = (mb.v - rr) * (1.0 - 1e-12);
+        if (thr < 0 || d2 >= thr * thr) {
+          ValIdx c; c.v = sqrt(d2) + rr; c.i = i * n + j;
+          mb = vi_max(mb, c);
+        }
+      }
+    }
   }
   mb = block_vi(mb, true, red, redi);
   const double D = mb.v;
@@ -132,7 +143,10 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     idv[D_COM] = cx; idv[D_COM + 1] = cy; idv[D_COM + 2] = cz; idv[D_MAXD] = D;
   }
   if (!do_avg) return;
-  // ---- average diameter (utilities.py:1586-1650, :1556-1583): sphere radius = D (not D/2)
+  // ---- average diameter (utilities.py:1586-1650, :1556-1583): sphere radius = D (not D/2).
+  // Atom i counts for ray n iff r_i^2 - d_i^2 > 0 and |o+(t-h)n| < |o+(t+h)n| <=> t + o.n > 0; the exit
+  // point is o + s n with s = t + sqrt(r_i^2 - d_i^2) and |o + s n| grows with s, so the farthest exit
+  // is the largest s.  s <= t + r_i prunes the sqrt.
   __syncthreads();
   double ox = 0, oy = 0, oz = 0;
   for (int a = tid; a < n; a += nt) {
@@ -140,35 +154,75 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     ox += sx[a]; oy += sy[a]; oz += sz[a];
   }
   ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
-  for (int a = tid; a < n; a += nt) {
-    double lx = sx[a] - ox, ly = sy[a] - oy, lz = sz[a] - oz;
-    sx[a] = lx; sy[a] = ly; sz[a] = lz;
-    sw[a] = lx * lx + ly * ly + lz * lz;            // |L|^2
-    sr[a] = sr[a] * sr[a];                          // r^2
+  // atoms re-ordered by |L| + r descending (rank sort): the outermost atoms set the running maximum
+  // early, so the sqrt branch in the ray loop is almost never taken afterwards
+  constexpr int APT = 4;                        // atoms per thread held in registers while sorting
+  const bool sortable = n <= APT * nt;
+  double mx_[APT], my_[APT], mz_[APT], mr_[APT], mk_[APT];
+  int rank[APT];
+  {
+    int c2 = 0;
+    for (int a = tid; a < n; a += nt, c2++) {
+      double lx = sx[a] - ox, ly = sy[a] - oy, lz = sz[a] - oz, ra = sr[a];
+      if (sortable) {
+        mx_[c2] = lx; my_[c2] = ly; mz_[c2] = lz; mr_[c2] = ra;
+        mk_[c2] = sqrt(lx * lx + ly * ly + lz * lz) + ra;
+        sw[a] = mk_[c2];
+      } else { sx[a] = lx; sy[a] = ly; sz[a] = lz; sw[a] = ra * ra - (lx * lx + ly * ly + lz * lz); }
+    }
+  }
+  __syncthreads();
+  if (sortable) {
+    int c2 = 0;
+    for (int a = tid; a < n; a += nt, c2++) {
+      int rk = 0;
+      const double k = mk_[c2];
+      for (int j = 0; j < n; j++) { const double kj = sw[j]; rk += (kj > k) || (kj == k && j < a); }
+      rank[c2] = rk;
+    }
+  }
+  __syncthreads();
+  if (sortable) {
+    int c2 = 0;
+    for (int a = tid; a < n; a += nt, c2++) {
+      const int dst = rank[c2];
+      sx[dst] = mx_[c2]; sy[dst] = my_[c2]; sz[dst] = mz_[c2]; sr[dst] = mr_[c2];
+      sw[dst] = mr_[c2] * mr_[c2] - (mx_[c2] * mx_[c2] + my_[c2] * my_[c2] + mz_[c2] * mz_[c2]);   // r^2 - |L|^2
+    }
   }
   __syncthreads();
   const int P = n_sampling_points(D, b.adjust);
+  const double oo = ox * ox + oy * oy + oz * oz;
   double acc = 0, hits = 0;
-  for (int k = tid; k < P; k += nt) {
-    double px, py, pz;
-    spiral_point(k, P, D, px, py, pz);
-    double nr = sqrt(px * px + py * py + pz * pz);
-    double nx = px / nr, ny = py / nr, nz = pz / nr;
-    double far = -1.0;
+  constexpr int RPT = 4;
+  for (int k0 = tid * RPT; k0 < P; k0 += nt * RPT) {
+    double nx[RPT], ny[RPT], nz[RPT], on[RPT], sb[RPT];
+#pragma unroll
+    for (int u = 0; u < RPT; u++) {
+      double px, py, pz;
+      spiral_point(min(k0 + u, P - 1), P, D, px, py, pz);
+      double nr = sqrt(px * px + py * py + pz * pz);
+      nx[u] = px / nr; ny[u] = py / nr; nz[u] = pz / nr;
+      on[u] = -(ox * nx[u] + oy * ny[u] + oz * nz[u]);
+      sb[u] = -PWB_INF;
+    }
     for (int a = 0; a < n; a++) {
-      double t = sx[a] * nx + sy[a] * ny + sz[a] * nz;
-      double q = sw[a] - t * t;                     // d^2 (reference takes sqrt, NaN if < 0)
-      double under = sr[a] - q;
-      if (q >= 0 && under > 0) {
-        double h = sqrt(under);
-        double t0 = t - h, t1 = t + h;
-        double ax = ox + t0 * nx, ay = oy + t0 * ny, az = oz + t0 * nz;
-        double bx = ox + t1 * nx, by = oy + t1 * ny, bz = oz + t1 * nz;
-        double n0 = sqrt(ax * ax + ay * ay + az * az), n1 = sqrt(bx * bx + by * by + bz * bz);
-        if (n0 < n1) far = fmax(far, n1);
+      const double Lx = sx[a], Ly = sy[a], Lz = sz[a], W = sw[a], ra = sr[a];
+#pragma unroll
+      for (int u = 0; u < RPT; u++) {
+        double t = fma(Lx, nx[u], fma(Ly, ny[u], Lz * nz[u]));
+        double under = fma(t, t, W);
+        if (under > 0.0 && t > on[u] && t + ra > sb[u]) sb[u] = fmax(sb[u], t + sqrt(under));
       }
     }
-    if (far >= 0) { acc += far; hits += 1.0; }
+#pragma unroll
+    for (int u = 0; u < RPT; u++) {
+      if (k0 + u < P && sb[u] > -PWB_INF) {
+        double s = sb[u];
+        acc += sqrt(fma(s, s, fma(-2.0 * s, on[u], oo)));     // |o + s n|, o.n = -on
+        hits += 1.0;
+      }
+    }
   }
   acc = block_sum(acc, red); hits = block_sum(hits, red);
   if (tid == 0) rec[PWB_REC_AVGD] = 2.0 * (acc / hits);
@@ -180,8 +234,9 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 constexpr int OPT_WARPS = 4;
 
 struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-point differences
-  WarpAtoms A; const double* lo; const double* hi; const int* nbd;
+  WarpAtoms A; const double* lo; const double* hi; const int* nbd; int nfev;
   __device__ void fg(const double* x, double& f, double* g) {
+    nfev += 4;
     double px[4], py[4], pz[4], h[3], m[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
@@ -195,7 +250,7 @@ struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-p
   }
 };
 
-__global__ void __launch_bounds__(OPT_WARPS * 32)
+__global__ void __launch_bounds__(OPT_WARPS * 32, 8)
 k_opt_pore(pwb_batch b, Ws ws) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -213,10 +268,10 @@ k_opt_pore(pwb_batch b, Ws ws) {
     x[a] = q[0]; y[a] = q[1]; z[a] = q[2]; r[a] = q[3];
   }
   __syncwarp();
-  WarpAtoms A{x, y, z, r, n, lane};
+  WarpAtoms A{x, y, z, r, n, lane, iiv + I_CLS0, b.n_types};
   const int* orig = ws.atom_idx + off;
   double c[3] = {idv[D_COM], idv[D_COM + 1], idv[D_COM + 2]};
-  double fopt = 0; int nit = 0, st = 0;
+  double fopt = 0; int nit = 0, st = 0, nfev = 0;
   if (b.centre_override) {
     const double* o = b.centre_override + (size_t)item * 3;
     c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
@@ -231,15 +286,16 @@ k_opt_pore(pwb_batch b, Ws ws) {
     int nbd[3] = {2, 2, 2};
 #pragma unroll
     for (int i = 0; i < 3; i++) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
-    DevPoreObj3 obj{A, lo, hi, nbd};
+    DevPoreObj3 obj{A, lo, hi, nbd, 0};
     st = lbfgsb_minimize<3>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit);
+    nfev = obj.nfev;
   }
   ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
   if (lane == 0) {
     idv[D_CENTRE] = c[0]; idv[D_CENTRE + 1] = c[1]; idv[D_CENTRE + 2] = c[2];
     rec[PWB_REC_OPT_D] = 2.0 * pa.v; rec[PWB_REC_OPT_ATOM] = pa.i;
     rec[PWB_REC_OPT_C] = c[0]; rec[PWB_REC_OPT_C + 1] = c[1]; rec[PWB_REC_OPT_C + 2] = c[2];
-    rec[PWB_REC_OPT_NIT] = nit; rec[PWB_REC_OPT_STOP] = st;
+    rec[PWB_REC_OPT_NIT] = nit; rec[PWB_REC_OPT_STOP] = st; rec[PWB_REC_OPT_NFEV] = nfev;
   }
 }
 
@@ -247,7 +303,9 @@ k_opt_pore(pwb_batch b, Ws ws) {
 // k_rays
 // =================================================================================================
 constexpr int RAY_THREADS = 256;
-constexpr int RAY_TILE = 1024;   // rays per pass
+constexpr int RAY_TILE = 1024;   // rays per pass (4 per thread, register tiled)
+constexpr int RAY_RPT = RAY_TILE / RAY_THREADS;
+constexpr int RAY_ACAP = RAY_TILE;   // 2*min clearance of the survivors of one tile
 
 // Exclusive block scan of one int per thread; returns this thread's offset, `total` for all.
 __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
@@ -263,6 +321,12 @@ __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
   return base + inc - v;
 }
 
+// Direction n = p/|p| of ray k, its length |p| and the point p itself (utilities.py:1139, :1108)
+__device__ __forceinline__ void ray_dir(int k, int P, double R, double& px, double& py, double& pz, double& nr) {
+  spiral_point(k, P, R, px, py, pz);
+  nr = sqrt(px * px + py * py + pz * pz);
+}
+
 __global__ void __launch_bounds__(RAY_THREADS)
 k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   extern __shared__ double sm[];
@@ -273,13 +337,12 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   const int status0 = iiv[I_STATUS];
   if (status0 & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS)) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* ax = sm; double* ay = ax + NA; double* az = ay + NA;     // shifted, bucketed
-  double* lx = az + NA; double* ly = lx + NA; double* lz = ly + NA;  // relative to the centroid
-  double* l2 = lz + NA; double* r2 = l2 + NA;
-  double* red = r2 + NA;                    // 64
+  double* ax = sm; double* ay = ax + NA; double* az = ay + NA; double* aw = az + NA;   // shifted, bucketed, |x|^2
+  double* lx = aw + NA; double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
+  double* red = lw + NA;                    // 64
   double* cr = red + 64;                    // [PWB_MAX_TYPES]
-  double* sa2 = cr + PWB_MAX_TYPES;         // [RAY_TILE] 2*min clearance of survivors
-  int* cls = (int*)(sa2 + RAY_TILE);        // [PWB_MAX_TYPES+1]
+  double* sa = cr + PWB_MAX_TYPES;          // [RAY_ACAP] path clearances of the current sub-pass
+  int* cls = (int*)(sa + RAY_ACAP);         // [PWB_MAX_TYPES+1]
   int* wsum = cls + PWB_MAX_TYPES + 1;      // [32]
   int* surv = wsum + 32;                    // [RAY_TILE] ray index of survivors in this tile
   int* spos = surv + RAY_TILE;              // [RAY_TILE] arg-min path step (or -1)
@@ -298,18 +361,18 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   for (int a = tid; a < n; a += nt) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
     double x = q[0] - shx, y = q[1] - shy, z = q[2] - shz;
-    ax[a] = x; ay[a] = y; az[a] = z; r2[a] = q[3] * q[3];
+    ax[a] = x; ay[a] = y; az[a] = z; aw[a] = x * x + y * y + z * z;
+    lw[a] = q[3] * q[3];
     ox += x; oy += y; oz += z;
   }
   ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
   for (int a = tid; a < n; a += nt) {
     double x = ax[a] - ox, y = ay[a] - oy, z = az[a] - oz;
-    lx[a] = x; ly[a] = y; lz[a] = z; l2[a] = x * x + y * y + z * z;
+    lx[a] = x; ly[a] = y; lz[a] = z; lw[a] = lw[a] - (x * x + y * y + z * z);   // r^2 - |L|^2
   }
   const double R = idv[D_MAXD] / 2.0;     // max_dim is translation invariant: reuse (utilities.py:1398)
   const int P = n_sampling_points(R, b.adjust);
   __syncthreads();
-  Bucketed B{ax, ay, az, cls, cr, b.n_types};
   if (tid == 0) {
     idv[D_RADIUS] = R; idv[D_ICOM] = icx; idv[D_ICOM + 1] = icy; idv[D_ICOM + 2] = icz;
     idv[D_SHIFT] = shx; idv[D_SHIFT + 1] = shy; idv[D_SHIFT + 2] = shz;
@@ -326,65 +389,79 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   double* out_a2 = ws.clear_a2 + (size_t)item * b.ray_cap;
   int n_clear = 0, n_surv_total = 0;
   for (int base = 0; base < P; base += RAY_TILE) {
-    // ---- pre-test (utilities.py:1132-1161): 4 rays per thread, survivors compacted in ray order
-    int mine[RAY_TILE / RAY_THREADS];
-    int cntm = 0;
+    // ---- pre-test (utilities.py:1132-1161), RAY_RPT consecutive rays per thread, branch free:
+    // atom i counts iff r_i^2 - d_i^2 > 0 (d_i about the line through the centroid o) and
+    // |o+(t-h)n| < |o+(t+h)n|  <=>  t + o.n > 0   (both norms expand to |o|^2+2s(o.n)+s^2, h > 0)
+    double nx[RAY_RPT], ny[RAY_RPT], nz[RAY_RPT], on[RAY_RPT];
+    bool blk[RAY_RPT];
 #pragma unroll
-    for (int u = 0; u < RAY_TILE / RAY_THREADS; u++) {
-      int k = base + tid * (RAY_TILE / RAY_THREADS) + u;     // contiguous rays per thread keeps order
-      mine[u] = -1;
-      if (k < P) {
-        double px, py, pz;
-        spiral_point(k, P, R, px, py, pz);
-        double nr = sqrt(px * px + py * py + pz * pz);
-        double nx = px / nr, ny = py / nr, nz = pz / nr;
-        bool blocked = false;
-        for (int a = 0; a < n; a++) {
-          double t = lx[a] * nx + ly[a] * ny + lz[a] * nz;
-          double q = l2[a] - t * t;
-          double under = r2[a] - q;
-          if (q >= 0 && under > 0) {
-            double h = sqrt(under);
-            double t0 = t - h, t1 = t + h;
-            double x0 = ox + t0 * nx, y0 = oy + t0 * ny, z0 = oz + t0 * nz;
-            double x1 = ox + t1 * nx, y1 = oy + t1 * ny, z1 = oz + t1 * nz;
-            if (sqrt(x0 * x0 + y0 * y0 + z0 * z0) < sqrt(x1 * x1 + y1 * y1 + z1 * z1)) { blocked = true; break; }
-          }
-        }
-        if (!blocked) { mine[u] = k; cntm++; }
+    for (int u = 0; u < RAY_RPT; u++) {
+      int k = base + tid * RAY_RPT + u;
+      double px, py, pz, nr;
+      ray_dir(k < P ? k : 0, P, R, px, py, pz, nr);
+      nx[u] = px / nr; ny[u] = py / nr; nz[u] = pz / nr;
+      on[u] = -(ox * nx[u] + oy * ny[u] + oz * nz[u]);
+      blk[u] = k >= P;
+    }
+    for (int a = 0; a < n; a++) {
+      const double Lx = lx[a], Ly = ly[a], Lz = lz[a], W = lw[a];
+#pragma unroll
+      for (int u = 0; u < RAY_RPT; u++) {
+        double t = fma(Lx, nx[u], fma(Ly, ny[u], Lz * nz[u]));
+        double under = fma(t, t, W);
+        blk[u] = blk[u] || (under > 0.0 && t > on[u]);
       }
     }
+    int cntm = 0;
+#pragma unroll
+    for (int u = 0; u < RAY_RPT; u++) cntm += blk[u] ? 0 : 1;
     int nsurv;
     int o = block_excl_scan(cntm, wsum, nsurv);
 #pragma unroll
-    for (int u = 0; u < RAY_TILE / RAY_THREADS; u++) if (mine[u] >= 0) surv[o++] = mine[u];
+    for (int u = 0; u < RAY_RPT; u++) if (!blk[u]) surv[o++] = base + tid * RAY_RPT + u;
     __syncthreads();
     n_surv_total += nsurv;
-    // ---- stepped path clearance (utilities.py:1100-1129), one survivor per thread
+    // ---- stepped path clearance (utilities.py:1100-1129).  The reference evaluates
+    // a_j = min_i(|x_i - q_j| - r_i) at every step q_j = j*chunk and keeps min_j a_j, its first arg-min
+    // and "all a_j > 0".  For a fixed atom |x_i - q_j| is convex in j, so min_j is attained at one of the
+    // two steps bracketing the atom's projection: min_j min_i = min_i min_{j in {j0, j0+1}} -- 2 instead
+    // of chunks+1 evaluations per atom, same value, same arg-min (ties -> smaller j).
+    // |x - j*chunk|^2 = |x|^2 + j*(j*|chunk|^2 - 2 x.chunk).
     for (int s = tid; s < nsurv; s += nt) {
-      int k = surv[s];
-      double px, py, pz;
-      spiral_point(k, P, R, px, py, pz);
-      double nr = sqrt(px * px + py * py + pz * pz);
-      int chunks = (int)py_floordiv(nr, b.increment);
-      double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
-      double best = PWB_INF; int bestj = 0; bool clear = true;
-      for (int j = 0; j <= chunks; j++) {
-        double a = min_clearance(B, cxs * j, cys * j, czs * j);
-        if (!(a > 0)) { clear = false; break; }
-        if (a < best) { best = a; bestj = j; }
+      double px, py, pz, nr;
+      ray_dir(surv[s], P, R, px, py, pz, nr);
+      const int chunks = (int)py_floordiv(nr, b.increment);
+      const double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
+      const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
+      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
+      double bestv = PWB_INF, bestj = 0.0;
+      for (int c = 0; c < b.n_types; c++) {
+        const int cb = cls[c], ce = cls[c + 1];
+        if (cb == ce) continue;
+        double m = PWB_INF, mj = 0.0;
+        for (int a = cb; a < ce; a++) {
+          const double g = fma(ax[a], cxs, fma(ay[a], cys, az[a] * czs));
+          const double j0 = floor(fmin(fmax(g * icc, 0.0), jmax)), j1 = j0 + 1.0;
+          const double w = aw[a], g2 = -2.0 * g;
+          const double d0 = fma(j0, fma(j0, cc, g2), w), d1 = fma(j1, fma(j1, cc, g2), w);
+          if (d0 < m || (d0 == m && j0 < mj)) { m = d0; mj = j0; }
+          if (d1 < m || (d1 == m && j1 < mj)) { m = d1; mj = j1; }
+        }
+        const double v = sqrt(fmax(m, 0.0)) - cr[c];
+        if (v < bestv || (v == bestv && mj < bestj)) { bestv = v; bestj = mj; }
       }
-      spos[s] = clear ? bestj : -1;
-      sa2[s] = best * 2.0;
+      const bool clear = chunks > 0 && bestv > 0.0;
+      spos[s] = clear ? (int)bestj : -1;
+      sa[s] = bestv * 2.0;
     }
     __syncthreads();
     // ---- ordered compaction of the clear rays into the global lists
-    for (int s0 = 0; s0 < nsurv; s0 += nt) {
-      int s = s0 + tid;
+    for (int sb = 0; sb < nsurv; sb += nt) {
+      int s = sb + tid;
       int ok = (s < nsurv && spos[s] >= 0) ? 1 : 0;
       int tot;
       int oo = block_excl_scan(ok, wsum, tot);
-      if (ok) { out_k[n_clear + oo] = surv[s]; out_pos[n_clear + oo] = spos[s]; out_a2[n_clear + oo] = sa2[s]; }
+      if (ok) { out_k[n_clear + oo] = surv[s]; out_pos[n_clear + oo] = spos[s]; out_a2[n_clear + oo] = sa[s]; }
       n_clear += tot;
     }
     __syncthreads();
@@ -495,7 +572,7 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx) {
     int c = 0;
     for (int j = 0; j < S; j++) {
       double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
-      c += (dx * dx + dy * dy + dz * dz <= eps2);
+      c += (fma(dx, dx, fma(dy, dy, dz * dz)) <= eps2);
     }
     core[i] = c >= 5;
   }
@@ -590,7 +667,7 @@ __device__ __forceinline__ double angle_between(double x0, double x1, double x2,
   return acos(first);
 }
 
-__global__ void __launch_bounds__(WIN_WARPS * 32)
+__global__ void __launch_bounds__(WIN_WARPS * 32, 7)
 k_windows(pwb_batch b, Ws ws) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -603,19 +680,20 @@ k_windows(pwb_batch b, Ws ws) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   double* out = rec + PWB_REC_WIN0 + 4 * win;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* x = sm + (size_t)w * (NA * 4 + PWB_MAX_TYPES + 16);
-  double* y = x + NA; double* z = y + NA; double* r = z + NA;
-  double* cr = r + NA;                       // [PWB_MAX_TYPES]
+  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 16);
+  double* y = x + NA; double* z = y + NA; double* r = z + NA; double* w2 = r + NA;
+  double* cr = w2 + NA;                      // [PWB_MAX_TYPES]
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1] (fits in 8 doubles + slack)
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
     x[a] = q[0] - shx; y[a] = q[1] - shy; z[a] = q[2] - shz; r[a] = q[3];
+    w2[a] = x[a] * x[a] + y[a] * y[a] + z[a] * z[a];
   }
   if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
   if (lane < PWB_MAX_TYPES) cr[lane] = lane < b.n_types ? b.type_vdw[lane] : 0.0;
   __syncwarp();
-  Bucketed B{x, y, z, cls, cr, b.n_types};
+  Bucketed B{x, y, z, w2, cls, cr, b.n_types};
   const int P = iiv[I_P];
   const double R = idv[D_RADIUS];
   // ---- rescan of the arg-max ray with increment2 (utilities.py:1221-1227)
@@ -624,15 +702,23 @@ k_windows(pwb_batch b, Ws ws) {
   const double nr = sqrt(vx * vx + vy * vy + vz * vz);
   const int chunks = (int)py_floordiv(nr, b.increment2);
   const double cxs = vx / chunks, cys = vy / chunks, czs = vz / chunks;
+  // same bracketing argument as in k_rays: two candidate steps per atom, lanes stride over atoms
   ValIdx bj; bj.v = PWB_INF; bj.i = 0x7fffffff;
-  int bad = 0;
-  for (int j = lane; j <= chunks; j += 32) {
-    double a = min_clearance(B, cxs * j, cys * j, czs * j);
-    if (!(a > 0)) bad = 1;
-    ValIdx c; c.v = a; c.i = j;
-    bj = vi_min(bj, c);
+  {
+    const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
+    const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
+    for (int a = lane; a < n; a += 32) {
+      const double g = fma(x[a], cxs, fma(y[a], cys, z[a] * czs));
+      const double j0 = floor(fmin(fmax(g * icc, 0.0), jmax)), j1 = j0 + 1.0;
+      const double g2 = -2.0 * g, wv = w2[a];
+      const double d0 = fma(j0, fma(j0, cc, g2), wv), d1 = fma(j1, fma(j1, cc, g2), wv);
+      ValIdx c0; c0.v = sqrt(fmax(d0, 0.0)) - r[a]; c0.i = (int)j0;
+      ValIdx c1; c1.v = sqrt(fmax(d1, 0.0)) - r[a]; c1.i = (int)j1;
+      bj = vi_min(bj, vi_min(c0, c1));
+    }
   }
-  bad = __any_sync(0xffffffffu, bad);
+  bj = warp_vi_min(bj);
+  const int bad = !(chunks > 0 && bj.v > 0.0);
   if (bad) {
     if (lane == 0) {
       out[0] = nan(""); out[1] = out[2] = out[3] = nan("");
@@ -640,7 +726,6 @@ k_windows(pwb_batch b, Ws ws) {
     }
     return;
   }
-  bj = warp_vi_min(bj);
   const double qx = cxs * bj.i, qy = cys * bj.i, qz = czs * bj.i;
   const double new_z = sqrt(qx * qx + qy * qy + qz * qz);
   // ---- rotation angles, octant table (utilities.py:1235-1259)
@@ -664,9 +749,10 @@ k_windows(pwb_batch b, Ws ws) {
     double X1 = c1 * X0 + (-s1) * Y0, Y1 = s1 * X0 + c1 * Y0, Z1 = Z0;         // Rz(a1)
     double X2 = c2 * X1 + s2 * Z1, Y2 = Y1, Z2 = (-s2) * X1 + c2 * Z1;          // Ry(a2)
     x[a] = X2; y[a] = Y2; z[a] = Z2 - new_z;
+    w2[a] = x[a] * x[a] + y[a] * y[a] + z[a] * z[a];
   }
   __syncwarp();
-  WarpAtoms A{x, y, z, r, n, lane};
+  WarpAtoms A{x, y, z, r, n, lane, cls, b.n_types};
   double m0[1], zero = 0.0;
   warp_min_clear<1>(A, &zero, &zero, &zero, m0);
   const double d0 = m0[0] * 2.0;
@@ -679,11 +765,18 @@ k_windows(pwb_batch b, Ws ws) {
   const double glo = -d0 / 2, ghi = d0 / 2;
   const double gstep = (ghi - glo) / 19.0;
   ValIdx gb; gb.v = PWB_INF; gb.i = 0x7fffffff;
-  for (int g = lane; g < 400; g += 32) {
-    int ix = g / 20, iy = g - ix * 20;
-    double gxp = __dadd_rn(__dmul_rn((double)ix, gstep), glo), gyp = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
-    ValIdx c; c.v = -(min_clearance(B, gxp, gyp, wz) * 2.0); c.i = g;
+  for (int g = lane; g < 400; g += 64) {
+    double gxp[2], gyp[2], gzp[2] = {wz, wz}, gv[2];
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+      int gg = min(g + 32 * v, 399);
+      int ix = gg / 20, iy = gg - ix * 20;
+      gxp[v] = __dadd_rn(__dmul_rn((double)ix, gstep), glo); gyp[v] = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+    }
+    min_clearance_k<2>(B, gxp, gyp, gzp, gv);
+    ValIdx c; c.v = -(gv[0] * 2.0); c.i = g;
     gb = vi_min(gb, c);
+    if (g + 32 < 400) { c.v = -(gv[1] * 2.0); c.i = g + 32; gb = vi_min(gb, c); }
   }
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
@@ -864,7 +957,7 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   return 0;
 }
 static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_TILE) +
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_ACAP) +
               sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE);
   if (set_smem(k_rays, sm, c->max_smem)) return 1;
   k_rays<<<b->n_items, RAY_THREADS, sm, s>>>(*b, w, c->c);
@@ -886,7 +979,7 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + PWB_MAX_TYPES + 16) * WIN_WARPS + 64;
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 16) * WIN_WARPS + 64;
   if (set_smem(k_windows, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
   k_windows<<<(unsigned)((warps + WIN_WARPS - 1) / WIN_WARPS), WIN_WARPS * 32, sm, s>>>(*b, w);

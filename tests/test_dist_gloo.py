@@ -23,7 +23,7 @@ class _StubResult:
 
 class _StubEngine:
     win_cap = 16
-    rec_stride = 24 + 4 * 16
+    rec_stride = 28 + 4 * 16
 
     def analyse_frames(self, coords, elements, **kw):
         from pywindow_b200 import _lib as L
