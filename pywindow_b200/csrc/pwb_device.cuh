@@ -16,6 +16,7 @@ constexpr int ITEM_I = 32;   // ints of per-item scratch
 constexpr int D_COM = 0, D_MAXD = 3, D_CENTRE = 4, D_RADIUS = 7, D_EPS = 8, D_ICOM = 9, D_SHIFT = 12;
 // item_i slots
 constexpr int I_STATUS = 0, I_P = 1, I_NSURV = 2, I_NCLEAR = 3, I_NWIN = 4, I_N = 5, I_CLS0 = 6;  // cls_start[17]
+constexpr int I_DEFER = 24;   // cluster stage deferred to the large-shared-memory pass
 
 constexpr double PWB_INF = 1e300;
 constexpr double GOLDEN_ANGLE = 2.399963229728653;  // pi*(3-sqrt(5)), utilities.py:1412
@@ -66,26 +67,42 @@ __device__ __forceinline__ ValIdx vi_min(ValIdx a, ValIdx b) {   // smaller v, t
 __device__ __forceinline__ ValIdx vi_max(ValIdx a, ValIdx b) {   // larger v, then smaller i
   return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
-__device__ __forceinline__ ValIdx warp_vi_min(ValIdx a) {
-  for (int m = 16; m; m >>= 1) {
-    ValIdx b; b.v = shfl_xor_d(a.v, m); b.i = __shfl_xor_sync(0xffffffffu, a.i, m);
-    a = vi_min(a, b);
-  }
-  return a;
+// Warp-wide min / max of doubles with two 32-bit REDUX operations instead of five shuffle steps:
+// doubles are mapped to order-isomorphic unsigned 64-bit keys (sign flip), the high words are
+// reduced first, then the low words among the lanes that hold the winning high word.  Bit exact.
+__device__ __forceinline__ unsigned long long dkey(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-__device__ __forceinline__ ValIdx warp_vi_max(ValIdx a) {
-  for (int m = 16; m; m >>= 1) {
-    ValIdx b; b.v = shfl_xor_d(a.v, m); b.i = __shfl_xor_sync(0xffffffffu, a.i, m);
-    a = vi_max(a, b);
-  }
-  return a;
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ double warp_min(double v) {
+  const unsigned long long k = dkey(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return dunkey(((unsigned long long)mh << 32) | ml);
+}
+__device__ __forceinline__ double warp_max(double v) {
+  const unsigned long long k = dkey(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return dunkey(((unsigned long long)mh << 32) | ml);
+}
+__device__ __forceinline__ ValIdx warp_vi_min(ValIdx a) {        // smaller v, then smaller i
+  ValIdx r; r.v = warp_min(a.v);
+  r.i = (int)__reduce_min_sync(0xffffffffu, a.v == r.v ? (unsigned)a.i : 0xffffffffu);
+  return r;
+}
+__device__ __forceinline__ ValIdx warp_vi_max(ValIdx a) {        // larger v, then smaller i
+  ValIdx r; r.v = warp_max(a.v);
+  r.i = (int)__reduce_min_sync(0xffffffffu, a.v == r.v ? (unsigned)a.i : 0xffffffffu);
+  return r;
 }
 __device__ __forceinline__ double warp_sum(double a) {
   for (int m = 16; m; m >>= 1) a += shfl_xor_d(a, m);
-  return a;
-}
-__device__ __forceinline__ double warp_min(double a) {
-  for (int m = 16; m; m >>= 1) a = fmin(a, shfl_xor_d(a, m));
   return a;
 }
 
@@ -198,11 +215,7 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
     for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
   }
 #pragma unroll
-  for (int k = 0; k < K; k++) {
-    double a = v[k];
-    for (int s = 16; s; s >>= 1) a = dmin(a, shfl_xor_d(a, s));
-    out[k] = a;
-  }
+  for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);
 }
 
 // pore_diameter with first-occurrence argmin over ORIGINAL atom indices (utilities.py:375-388)

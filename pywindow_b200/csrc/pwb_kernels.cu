@@ -40,6 +40,14 @@ struct Ctx {
 // =================================================================================================
 constexpr int PREP_THREADS = 256;
 
+// Rarely taken paths kept out of line so the compiler does not if-convert a double-precision sqrt
+// (~40 instructions) into the hot loops.
+__device__ __noinline__ double rare_exit_param(double t, double under, double sb) { return fmax(sb, t + sqrt(under)); }
+__device__ __noinline__ ValIdx rare_pair_max(ValIdx mb, double d2, double rr, int idx) {
+  ValIdx c; c.v = sqrt(d2) + rr; c.i = idx;
+  return vi_max(mb, c);
+}
+
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(pwb_batch b, Ws ws, int do_avg) {
   extern __shared__ double sm[];
@@ -125,10 +133,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
         double d2 = dx * dx + dy * dy + dz * dz;
         double rr = ri + sr[j];
         double thr = (mb.v - rr) * (1.0 - 1e-12);
-        if (thr < 0 || d2 >= thr * thr) {
-          ValIdx c; c.v = sqrt(d2) + rr; c.i = i * n + j;
-          mb = vi_max(mb, c);
-        }
+        if (thr < 0 || d2 >= thr * thr) mb = rare_pair_max(mb, d2, rr, i * n + j);
       }
     }
   }
@@ -212,7 +217,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
       for (int u = 0; u < RPT; u++) {
         double t = fma(Lx, nx[u], fma(Ly, ny[u], Lz * nz[u]));
         double under = fma(t, t, W);
-        if (under > 0.0 && t > on[u] && t + ra > sb[u]) sb[u] = fmax(sb[u], t + sqrt(under));
+        if (under > 0.0 && t > on[u] && t + ra > sb[u]) sb[u] = rare_exit_param(t, under, sb[u]);
       }
     }
 #pragma unroll
@@ -393,7 +398,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     // atom i counts iff r_i^2 - d_i^2 > 0 (d_i about the line through the centroid o) and
     // |o+(t-h)n| < |o+(t+h)n|  <=>  t + o.n > 0   (both norms expand to |o|^2+2s(o.n)+s^2, h > 0)
     double nx[RAY_RPT], ny[RAY_RPT], nz[RAY_RPT], on[RAY_RPT];
-    bool blk[RAY_RPT];
+    int blk[RAY_RPT];
 #pragma unroll
     for (int u = 0; u < RAY_RPT; u++) {
       int k = base + tid * RAY_RPT + u;
@@ -403,13 +408,14 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       on[u] = -(ox * nx[u] + oy * ny[u] + oz * nz[u]);
       blk[u] = k >= P;
     }
+#pragma unroll 2
     for (int a = 0; a < n; a++) {
       const double Lx = lx[a], Ly = ly[a], Lz = lz[a], W = lw[a];
 #pragma unroll
       for (int u = 0; u < RAY_RPT; u++) {
         double t = fma(Lx, nx[u], fma(Ly, ny[u], Lz * nz[u]));
         double under = fma(t, t, W);
-        blk[u] = blk[u] || (under > 0.0 && t > on[u]);
+        blk[u] |= (int)(under > 0.0) & (int)(t > on[u]);
       }
     }
     int cntm = 0;
@@ -433,7 +439,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       const int chunks = (int)py_floordiv(nr, b.increment);
       const double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
       const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
-      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
+      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0), gmax = cc * (jmax + 0.5);
       double bestv = PWB_INF, bestj = 0.0;
       for (int c = 0; c < b.n_types; c++) {
         const int cb = cls[c], ce = cls[c + 1];
@@ -441,11 +447,13 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
         double m = PWB_INF, mj = 0.0;
         for (int a = cb; a < ce; a++) {
           const double g = fma(ax[a], cxs, fma(ay[a], cys, az[a] * czs));
-          const double j0 = floor(fmin(fmax(g * icc, 0.0), jmax)), j1 = j0 + 1.0;
+          const double gc = dmin(gmax, g > 0.0 ? g : 0.0);
+          const double j0 = floor(gc * icc), j1 = j0 + 1.0;
           const double w = aw[a], g2 = -2.0 * g;
           const double d0 = fma(j0, fma(j0, cc, g2), w), d1 = fma(j1, fma(j1, cc, g2), w);
-          if (d0 < m || (d0 == m && j0 < mj)) { m = d0; mj = j0; }
-          if (d1 < m || (d1 == m && j1 < mj)) { m = d1; mj = j1; }
+          const bool first = d0 <= d1;                       // ties -> smaller step
+          const double dm = first ? d0 : d1, jm = first ? j0 : j1;
+          if (dm < m) { m = dm; mj = jm; }
         }
         const double v = sqrt(fmax(m, 0.0)) - cr[c];
         if (v < bestv || (v == bestv && mj < bestj)) { bestv = v; bestj = mj; }
@@ -518,6 +526,7 @@ k_knn_fill(Ctx ctx) {
 // Then per cluster the first arg-max of column 1 (2*min clearance), utilities.py:1221.
 // =================================================================================================
 constexpr int CL_THREADS = 256;
+constexpr unsigned CL_SMALL_SMEM = 26 * 1024;   // pass-0 budget: S <= ~330 clear rays, 8 CTAs per SM
 
 __device__ __forceinline__ int uf_find(volatile int* parent, int i) {
   int p = parent[i];
@@ -534,8 +543,10 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {   // small
   }
 }
 
+// Two launches: pass 0 with a small shared-memory budget (high occupancy) handles every item whose
+// S clear rays fit, pass 1 with the full 200 KB handles the rest (large molecules / dense ray sets).
 __global__ void __launch_bounds__(CL_THREADS)
-k_cluster(pwb_batch b, Ws ws, Ctx ctx) {
+k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
   extern __shared__ double sm[];
   const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
@@ -543,50 +554,136 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   const int st = iiv[I_STATUS];
   if (st & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP)) { if (tid == 0) iiv[I_NWIN] = 0; return; }
+  if (pass == 1 && !iiv[I_DEFER]) return;
   const int S = iiv[I_NCLEAR], P = iiv[I_P];
   const double R = idv[D_RADIUS];
   const double m = R * ctx.knn_unit[P];
   const double eps = m + sqrt(m);
-  if (tid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; }
+  if (pass == 0 && tid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; iiv[I_DEFER] = 0; }
   if (S == 0) return;
   const int cap = b.ray_cap;
-  double* px = sm; double* py = px + cap; double* pz = py + cap;
-  unsigned long long* cbest = (unsigned long long*)(pz + cap);   // [win_cap] best a2 bits per cluster
-  int* parent = (int*)(cbest + b.win_cap);                       // [cap]
-  int* label = parent + cap;                                     // [cap]
-  int* cidx = label + cap;                                       // [win_cap] arg-max member per cluster
+  const int Wd = (S + 31) >> 5;
+  // shared memory carved by the ACTUAL number of clear rays
+  const size_t need_base = 32 * (size_t)S + 12 * (size_t)b.win_cap + 8 * (size_t)S + 4 * (32 + 128) + ((S + 7) & ~7) + 64;
+  const bool use_bits = need_base + 4 * (size_t)S * Wd <= budget;
+  if (pass == 0 ? !use_bits : need_base > budget) {
+    if (pass == 0) { if (tid == 0) iiv[I_DEFER] = 1; }
+    else if (tid == 0) { atomicOr(&iiv[I_STATUS], PWB_ST_RAY_CAP); }
+    return;
+  }
+  double* px = sm;                                               // [S][4] points
+  unsigned long long* cbest = (unsigned long long*)(px + 4 * (size_t)S);   // [win_cap] best a2 bits per cluster
+  int* parent = (int*)(cbest + b.win_cap);                       // [S]
+  int* label = parent + S;                                       // [S]
+  int* cidx = label + S;                                         // [win_cap] arg-max member per cluster
   int* wsum = cidx + b.win_cap;                                  // [32]
-  unsigned char* core = (unsigned char*)(wsum + 32);             // [cap]
+  unsigned* cm = (unsigned*)(wsum + 32);                         // [128] core mask words (S <= 4096)
+  unsigned char* core = (unsigned char*)(cm + 128);              // [S]
+  unsigned* adj = (unsigned*)(core + ((S + 7) & ~7));            // [S*Wd] adjacency bit rows (if use_bits)
   const int* ck = ws.clear_k + (size_t)item * cap;
   const double* ca2 = ws.clear_a2 + (size_t)item * cap;
+  // points as (x, y, z, |p|^2/2): |pi-pj|^2 <= eps^2  <=>  pi.pj - |pj|^2/2 >= (|pi|^2 - eps^2)/2
+  double4* pt = (double4*)px;                      // [cap] overlays px/py/pz (+ the slack behind them)
   for (int i = tid; i < S; i += nt) {
     double x, y, z;
     spiral_point(ck[i], P, R, x, y, z);
-    px[i] = x; py[i] = y; pz[i] = z;
+    pt[i] = make_double4(x, y, z, 0.5 * (x * x + y * y + z * z));
     parent[i] = i;
+    label[i] = 0;                                  // neighbour counter in pass 1
   }
   __syncthreads();
   const double eps2 = eps * eps;
-  for (int i = tid; i < S; i += nt) {
-    double x = px[i], y = py[i], z = pz[i];
+  // ---- adjacency as a bit matrix in shared memory (one FP64 test per ordered pair, once); core
+  // flags, components (min-label propagation with pointer jumping) and border labels are then pure
+  // integer work on the bit rows.  Falls back to recomputing distances if S is too large for the tile.
+  const int Q = max(1, (4 * nt + S - 1) / S), jl = (S + Q - 1) / Q;   // fallback path: (i, slice of j) items
+  if (use_bits) {
+    // item = (word w, point i) with i fastest: a warp shares the 32 partner points (broadcast loads)
+    // and the bit rows are stored transposed, adj[w*S + i], so row scans are conflict free
+    for (int it = tid; it < S * Wd; it += nt) {
+      const int w = it / S, i = it - w * S;
+      const double4 a = pt[i];
+      const double hi = a.w - 0.5 * eps2;
+      const int jb = w << 5, jn = min(32, S - jb);
+      unsigned bits = 0;
+      for (int t = 0; t < jn; t++) {
+        const double4 o = pt[jb + t];
+        bits |= (unsigned)(fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi) << t;
+      }
+      adj[it] = bits;
+    }
+    __syncthreads();
+    for (int i = tid; i < S; i += nt) {
+      int c = 0;
+      for (int w = 0; w < Wd; w++) c += __popc(adj[w * S + i]);
+      core[i] = c >= 5;
+      parent[i] = (c >= 5) ? i : 0x7fffffff;
+    }
+    __syncthreads();
+    for (int w = tid; w < Wd; w += nt) {
+      unsigned mbits = 0;
+      for (int t = 0; t < 32 && (w << 5) + t < S; t++) mbits |= (unsigned)core[(w << 5) + t] << t;
+      cm[w] = mbits;
+    }
+    __syncthreads();
+    int changed;
+    do {
+      changed = 0;
+      for (int i = tid; i < S; i += nt) {
+        if (!core[i]) continue;
+        int m0 = ((volatile int*)parent)[i], m = m0;
+        for (int w = 0; w < Wd; w++) {
+          unsigned bits = adj[w * S + i] & cm[w];
+          while (bits) {
+            const int j = (w << 5) + __ffs(bits) - 1;
+            bits &= bits - 1;
+            m = min(m, ((volatile int*)parent)[j]);
+          }
+        }
+        m = min(m, ((volatile int*)parent)[m]);
+        if (m < m0) { atomicMin(&parent[i], m); changed = 1; }
+      }
+      changed = __syncthreads_or(changed);
+    } while (changed);
+  } else {
+  for (int it = tid; it < S * Q; it += nt) {
+    const int i = it / Q, q = it - i * Q;
+    const double4 a = pt[i];
+    const double hi = a.w - 0.5 * eps2;
+    const int j1 = min(S, (q + 1) * jl);
     int c = 0;
-    for (int j = 0; j < S; j++) {
-      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
-      c += (fma(dx, dx, fma(dy, dy, dz * dz)) <= eps2);
+    for (int j = q * jl; j < j1; j++) {
+      const double4 o = pt[j];
+      c += (fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi);
     }
-    core[i] = c >= 5;
+    if (c) atomicAdd(&label[i], c);
   }
   __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    if (!core[i]) continue;
-    double x = px[i], y = py[i], z = pz[i];
-    for (int j = 0; j < i; j++) {
-      if (!core[j]) continue;
-      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
-      if (dx * dx + dy * dy + dz * dz <= eps2) uf_union(parent, i, j);
+  for (int i = tid; i < S; i += nt) core[i] = label[i] >= 5;
+  __syncthreads();
+  // union pass: warp-uniform trip counts and an explicit reconvergence point per step, otherwise the
+  // divergent union-find calls serialise the lanes for the rest of the loop
+  for (int it0 = 0; it0 < S * Q; it0 += nt) {
+    const int it = it0 + tid;
+    const bool valid = it < S * Q;
+    const int i = valid ? it / Q : 0, q = valid ? it - i * Q : 0;
+    const bool act = valid && core[i];
+    const double4 a = pt[i];
+    const double hi = a.w - 0.5 * eps2;
+    const int jb = q * jl, j1 = act ? min(i, (q + 1) * jl) : 0;
+    for (int s = 0; s < jl; s++) {
+      const int j = jb + s;
+      bool hit = false;
+      if (j < j1 && core[j]) {
+        const double4 o = pt[j];
+        hit = fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi;
+      }
+      if (hit) uf_union(parent, i, j);
+      __syncwarp();
     }
   }
   __syncthreads();
+  }
   // roots in ascending index order -> cluster numbers
   int nclus = 0;
   for (int s0 = 0; s0 < S; s0 += nt) {
@@ -601,19 +698,43 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx) {
   for (int i = tid; i < S; i += nt)
     if (core[i] && parent[i] != i) label[i] = label[uf_find(parent, i)];
   __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    if (core[i]) continue;
-    double x = px[i], y = py[i], z = pz[i];
-    int best = 0x7fffffff;
-    for (int j = 0; j < S; j++) {
-      if (!core[j]) continue;
-      double dx = x - px[j], dy = y - py[j], dz = z - pz[j];
-      if (dx * dx + dy * dy + dz * dz <= eps2) best = min(best, label[j]);
+  for (int i = tid; i < S; i += nt) if (!core[i]) parent[i] = 0x7fffffff;   // reuse parent[] as the border label
+  __syncthreads();
+  if (use_bits) {
+    for (int i = tid; i < S; i += nt) {
+      if (core[i]) continue;
+      int best = 0x7fffffff;
+      for (int w = 0; w < Wd; w++) {
+        unsigned bits = adj[w * S + i] & cm[w];
+        while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; best = min(best, label[j]); }
+      }
+      parent[i] = best;
     }
-    parent[i] = (best == 0x7fffffff) ? -1 : best;     // reuse parent[] as the border label
+    __syncthreads();
+  } else {
+  for (int it0 = 0; it0 < S * Q; it0 += nt) {
+    const int it = it0 + tid;
+    const bool valid = it < S * Q;
+    const int i = valid ? it / Q : 0, q = valid ? it - i * Q : 0;
+    const bool act = valid && !core[i];
+    if (__any_sync(0xffffffffu, act)) {                 // border / noise points are rare
+      const double4 a = pt[i];
+      const double hi = a.w - 0.5 * eps2;
+      const int jb = q * jl, j1 = act ? min(S, (q + 1) * jl) : 0;
+      int best = 0x7fffffff;
+      for (int s = 0; s < jl; s++) {
+        const int j = jb + s;
+        if (j < j1 && core[j]) {
+          const double4 o = pt[j];
+          if (fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi) best = min(best, label[j]);
+        }
+      }
+      if (best != 0x7fffffff) atomicMin(&parent[i], best);
+    }
   }
   __syncthreads();
-  for (int i = tid; i < S; i += nt) if (!core[i]) label[i] = parent[i];
+  }
+  for (int i = tid; i < S; i += nt) if (!core[i]) label[i] = (parent[i] == 0x7fffffff) ? -1 : parent[i];
   const int W = min(nclus, b.win_cap);
   for (int c = tid; c < b.win_cap; c += nt) { cbest[c] = 0ull; cidx[c] = 0x7fffffff; }
   __syncthreads();
@@ -970,11 +1091,12 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   if (set_smem(k_knn_fill, smk, c->max_smem)) return 1;
   k_knn_fill<<<c->c.table_cap - 2, KNN_THREADS, smk, s>>>(c->c);
   c->c.launches++;
-  size_t sm = sizeof(double) * (size_t)b->ray_cap * 3 + sizeof(unsigned long long) * b->win_cap +
-              sizeof(int) * ((size_t)b->ray_cap * 2 + b->win_cap + 32) + (size_t)b->ray_cap + 16;
-  if (set_smem(k_cluster, sm, c->max_smem)) return 1;
-  k_cluster<<<b->n_items, CL_THREADS, sm, s>>>(*b, w, c->c);
-  c->c.launches++;
+  // pass 0: small budget, high occupancy; pass 1: whatever the device allows, deferred items only
+  unsigned big = (unsigned)c->max_smem;
+  if (set_smem(k_cluster, big, c->max_smem)) return 1;
+  k_cluster<<<b->n_items, CL_THREADS, CL_SMALL_SMEM, s>>>(*b, w, c->c, 0, CL_SMALL_SMEM);
+  k_cluster<<<b->n_items, CL_THREADS, big, s>>>(*b, w, c->c, 1, big);
+  c->c.launches += 2;
   CK(cudaGetLastError());
   return 0;
 }
