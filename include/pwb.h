@@ -125,6 +125,8 @@ const char* pwb_last_error(void);
 
 int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap);
 int pwb_ctx_destroy(pwb_ctx* ctx);
+/* Cut batches into `chunks` (1..8) sub-batches pipelined over internal streams (default 1).      */
+int pwb_ctx_set_chunks(pwb_ctx* ctx, int chunks);
 
 /* bytes of workspace for a batch of n_items with total_atoms atoms */
 size_t pwb_workspace_bytes(int n_items, int total_atoms, int ray_cap, int win_cap);

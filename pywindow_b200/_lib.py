@@ -22,7 +22,7 @@ ST_OPT_BOUNDS, ST_NO_CLEAR_RAY, ST_RAY_CAP, ST_WIN_CAP, ST_WIN_DROPPED, ST_WIN_N
 STAGE_SCALARS, STAGE_AVGD, STAGE_OPT, STAGE_RAYS, STAGE_CLUSTER, STAGE_WINDOWS, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 
 EXPORTS = [
-    "pwb_abi_version", "pwb_last_error", "pwb_ctx_create", "pwb_ctx_destroy", "pwb_workspace_bytes",
+    "pwb_abi_version", "pwb_last_error", "pwb_ctx_create", "pwb_ctx_destroy", "pwb_ctx_set_chunks", "pwb_workspace_bytes",
     "pwb_workspace_layout", "pwb_ray_capacity", "pwb_frame_scalars", "pwb_average_diameter",
     "pwb_opt_pore", "pwb_ray_search", "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch",
     "pwb_full_analysis_host", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
@@ -71,6 +71,7 @@ def load():
     L.pwb_last_error.restype = ctypes.c_char_p
     L.pwb_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     L.pwb_ctx_destroy.argtypes = [vp]
+    L.pwb_ctx_set_chunks.argtypes = [vp, ci]
     L.pwb_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.pwb_workspace_bytes.restype = ctypes.c_size_t
     L.pwb_workspace_layout.argtypes = [ci, ci, ci, ci, ctypes.POINTER(WsLayout)]

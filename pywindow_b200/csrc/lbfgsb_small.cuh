@@ -41,6 +41,8 @@ enum LbStatus {
 PWB_HD double lb_fd_step(double x, int nbd, double lo, double hi) {
   double h = LB_FD_STEP;
   if (nbd == 0) return h;
+  // boxed variable with room for the step on one side: the general rule below reduces to a sign flip
+  if (nbd == 2 && hi - lo > 1e-6 && x >= lo && x <= hi) return (x + h > hi) ? -h : h;
   const double INF = 1.0 / 0.0;
   double lb = (nbd == 1 || nbd == 2) ? lo : -INF;
   double ub = (nbd == 2 || nbd == 3) ? hi : INF;

@@ -218,6 +218,109 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
   for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);
 }
 
+// ---- near lists: exact pruning for repeated evaluations around one point -------------------------
+// a(p) = min_i(|x_i - p| - r_i) is 1-Lipschitz, so for |p - c| <= rho:  a(p) <= a(c) + rho, while atom i
+// contributes at least |x_i - c| - rho - r_i.  Atoms with |x_i - c| - r_i > a(c) + 2 rho can therefore
+// never attain the minimum inside the ball and are dropped; the minimum over the kept atoms is
+// bit-identical to the minimum over all atoms.  The list holds atom indices, still grouped by class.
+struct NearList {
+  unsigned short* idx;   // [n] kept atom indices (shared memory)
+  int* cs;               // [ncls+1] class starts inside idx
+  double cx, cy, cz, rho2;
+};
+
+__device__ __forceinline__ void warp_build_near(const WarpAtoms& A, NearList& N, double cx, double cy, double cz,
+                                                double rho) {
+  double m[1];
+  warp_min_clear<1>(A, &cx, &cy, &cz, m);
+  const double thr = m[0] + 2.0 * rho + 1e-9;
+  int pos = 0;
+  for (int c = 0; c < A.ncls; c++) {
+    if (A.lane == 0) N.cs[c] = pos;
+    const int cb = A.cls[c], ce = A.cls[c + 1];
+    for (int base = cb; base < ce; base += 32) {
+      const int i = base + A.lane;
+      bool keep = false;
+      if (i < ce) {
+        const double dx = A.x[i] - cx, dy = A.y[i] - cy, dz = A.z[i] - cz;
+        keep = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i] <= thr;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) N.idx[pos + __popc(mask & ((1u << A.lane) - 1u))] = (unsigned short)i;
+      pos += __popc(mask);
+    }
+  }
+  if (A.lane == 0) N.cs[A.ncls] = pos;
+  N.cx = cx; N.cy = cy; N.cz = cz;
+  const double re = rho - 1e-6;
+  N.rho2 = re * re;
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool near_valid(const NearList& N, double x, double y, double z) {
+  const double dx = x - N.cx, dy = y - N.cy, dz = z - N.cz;
+  return dx * dx + dy * dy + dz * dz <= N.rho2;
+}
+
+// lanes stride over the kept atoms (optimiser objectives)
+template <int K>
+__device__ __forceinline__ void warp_min_clear_near(const WarpAtoms& A, const NearList& N, const double* px,
+                                                    const double* py, const double* pz, double* out) {
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = PWB_INF;
+  for (int c = 0; c < A.ncls; c++) {
+    const int cb = N.cs[c], ce = N.cs[c + 1];
+    if (cb == ce) continue;
+    double m[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) m[k] = PWB_INF;
+    for (int t = cb + A.lane; t < ce; t += 32) {
+      const int i = N.idx[t];
+      const double ax = A.x[i], ay = A.y[i], az = A.z[i];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
+        m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
+      }
+    }
+    const double rc = A.r[A.cls[c]];
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);
+}
+
+// every lane evaluates its own K points over the kept atoms (grid search)
+template <int K>
+__device__ __forceinline__ void min_clearance_k_near(const Bucketed& A, const NearList& N, const double* qx,
+                                                     const double* qy, const double* qz, double* out) {
+  double ax[K], ay[K], az[K], qq[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    qq[k] = qx[k] * qx[k] + qy[k] * qy[k] + qz[k] * qz[k];
+    ax[k] = -2.0 * qx[k]; ay[k] = -2.0 * qy[k]; az[k] = -2.0 * qz[k];
+    out[k] = PWB_INF;
+  }
+  for (int c = 0; c < A.ncls; c++) {
+    const int b = N.cs[c], e = N.cs[c + 1];
+    if (b == e) continue;
+    double m[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) m[k] = PWB_INF;
+    for (int t = b; t < e; t++) {
+      const int i = N.idx[t];
+      const double X = A.x[i], Y = A.y[i], Z = A.z[i], W = A.w[i];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = dmin(m[k], fma(ax[k], X, fma(ay[k], Y, fma(az[k], Z, W))));
+    }
+    const double rc = A.cr[c];
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = dmin(out[k], sqrt(fmax(m[k] + qq[k], 0.0)) - rc);
+  }
+}
+
 // pore_diameter with first-occurrence argmin over ORIGINAL atom indices (utilities.py:375-388)
 __device__ __forceinline__ ValIdx warp_pore_argmin(const WarpAtoms& A, const int* orig, double cx, double cy, double cz) {
   ValIdx b; b.v = PWB_INF; b.i = 0x7fffffff;

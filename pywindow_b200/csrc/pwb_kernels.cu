@@ -266,7 +266,8 @@ k_opt_pore(pwb_batch b, Ws ws) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* x = sm + (size_t)w * NA * 4;
+  const int NAp = (NA + 3) & ~3;
+  double* x = sm + (size_t)w * (NA * 4 + 16 + NAp / 4);
   double* y = x + NA; double* z = y + NA; double* r = z + NA;
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -774,10 +775,11 @@ struct DevZObj {   // optimise_z, utilities.py:1174-1188
   }
 };
 struct DevXYObj {  // optimise_xy, utilities.py:1164-1171
-  WarpAtoms A; double z;
+  WarpAtoms A; NearList N; double z;
   __device__ double f2(double x, double y) {
     double m[1];
-    warp_min_clear<1>(A, &x, &y, &z, m);
+    if (near_valid(N, x, y, z)) warp_min_clear_near<1>(A, N, &x, &y, &z, m);
+    else warp_min_clear<1>(A, &x, &y, &z, m);
     return -(m[0] * 2.0);
   }
 };
@@ -801,10 +803,13 @@ k_windows(pwb_batch b, Ws ws) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   double* out = rec + PWB_REC_WIN0 + 4 * win;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 16);
+  const int NAp = (NA + 3) & ~3;
+  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 32 + NAp / 4);
   double* y = x + NA; double* z = y + NA; double* r = z + NA; double* w2 = r + NA;
   double* cr = w2 + NA;                      // [PWB_MAX_TYPES]
-  int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1] (fits in 8 doubles + slack)
+  int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
+  int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
+  unsigned short* nidx = (unsigned short*)(cr + PWB_MAX_TYPES + 32);   // [NA] near-list atom indices
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -885,6 +890,9 @@ k_windows(pwb_batch b, Ws ws) {
   // ---- xy stage: 20x20 brute grid (first arg-min, row-major) + Nelder-Mead (utilities.py:1307-1316)
   const double glo = -d0 / 2, ghi = d0 / 2;
   const double gstep = (ghi - glo) / 19.0;
+  // only atoms that can touch a sphere centred within the grid square (+ slack for the simplex) matter
+  NearList NL; NL.idx = nidx; NL.cs = ncs;
+  warp_build_near(A, NL, 0.0, 0.0, wz, fabs(d0) * 0.7071067811865476 + 0.25);
   ValIdx gb; gb.v = PWB_INF; gb.i = 0x7fffffff;
   for (int g = lane; g < 400; g += 64) {
     double gxp[2], gyp[2], gzp[2] = {wz, wz}, gv[2];
@@ -894,7 +902,7 @@ k_windows(pwb_batch b, Ws ws) {
       int ix = gg / 20, iy = gg - ix * 20;
       gxp[v] = __dadd_rn(__dmul_rn((double)ix, gstep), glo); gyp[v] = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
     }
-    min_clearance_k<2>(B, gxp, gyp, gzp, gv);
+    min_clearance_k_near<2>(B, NL, gxp, gyp, gzp, gv);
     ValIdx c; c.v = -(gv[0] * 2.0); c.i = g;
     gb = vi_min(gb, c);
     if (g + 32 < 400) { c.v = -(gv[1] * 2.0); c.i = g + 32; gb = vi_min(gb, c); }
@@ -902,7 +910,7 @@ k_windows(pwb_batch b, Ws ws) {
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
   const double x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo), y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
-  DevXYObj xo{A, wz};
+  DevXYObj xo{A, NL, wz};
   double xy[2], fxy; int nfev;
   nelder_mead2(xo, x0, y0, 1e-4, 1e-4, 400, 400, xy, &fxy, &nfev);
   double mf[1];
@@ -973,7 +981,13 @@ __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
 // =================================================================================================
 using namespace pwb;
 
-struct pwb_ctx { Ctx c; int* d_tmp; int max_smem; };
+constexpr int PWB_MAX_CHUNKS = 8;
+struct pwb_ctx {
+  Ctx c; int* d_tmp; int max_smem;
+  int chunks;                                   // sub-batches pipelined over internal streams
+  cudaStream_t streams[PWB_MAX_CHUNKS];
+  cudaEvent_t fork, join[PWB_MAX_CHUNKS];
+};
 
 static thread_local char g_err[512] = "";
 static int fail(const char* what, cudaError_t e) {
@@ -1029,12 +1043,24 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
   CK(cudaMemset(c->c.knn_unit, 0, sizeof(double) * ray_table_cap));
   CK(cudaMemset(c->c.knn_need, 0, sizeof(int) * ray_table_cap));
   CK(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->chunks = 1;
+  for (int g = 0; g < PWB_MAX_CHUNKS; g++) {
+    CK(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->join[g], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
   *out = c;
+  return 0;
+}
+int pwb_ctx_set_chunks(pwb_ctx* c, int chunks) {
+  c->chunks = chunks < 1 ? 1 : (chunks > PWB_MAX_CHUNKS ? PWB_MAX_CHUNKS : chunks);
   return 0;
 }
 int pwb_ctx_destroy(pwb_ctx* c) {
   if (!c) return 0;
   cudaFree(c->c.knn_unit); cudaFree(c->c.knn_need); cudaFree(c->d_tmp);
+  for (int g = 0; g < PWB_MAX_CHUNKS; g++) { cudaStreamDestroy(c->streams[g]); cudaEventDestroy(c->join[g]); }
+  cudaEventDestroy(c->fork);
   delete c;
   return 0;
 }
@@ -1070,7 +1096,7 @@ static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * (size_t)b->max_atoms * 4 * OPT_WARPS;
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + 16 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4) * OPT_WARPS;
   if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
   k_opt_pore<<<(b->n_items + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, sm, s>>>(*b, w);
   c->c.launches++;
@@ -1101,7 +1127,7 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 16) * WIN_WARPS + 64;
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4) * WIN_WARPS + 64;
   if (set_smem(k_windows, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
   k_windows<<<(unsigned)((warps + WIN_WARPS - 1) / WIN_WARPS), WIN_WARPS * 32, sm, s>>>(*b, w);
@@ -1125,21 +1151,78 @@ int pwb_ray_capacity(pwb_ctx* c, const pwb_batch* b, void* stream, int* out_cap)
   return 0;
 }
 
-int pwb_full_analysis_batch(pwb_ctx* c, const pwb_batch* b, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (check(b)) return 1;
-  Ws w;
-  if (resolve(b, &w)) return 1;
+static int run_stages(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
   if (b->stages & (PWB_STAGE_SCALARS | PWB_STAGE_AVGD)) {
     CK(cudaMemsetAsync(b->records, 0, sizeof(double) * (size_t)b->n_items * b->rec_stride, s));
-  }
-  if (b->stages & (PWB_STAGE_SCALARS | PWB_STAGE_AVGD))
     if (run_prepare(c, b, w, s, (b->stages & PWB_STAGE_AVGD) ? 1 : 0)) return 1;
+  }
   if (b->stages & PWB_STAGE_OPT) if (run_opt(c, b, w, s)) return 1;
   if (b->stages & PWB_STAGE_RAYS) if (run_rays(c, b, w, s)) return 1;
   if (b->stages & PWB_STAGE_CLUSTER) if (run_cluster(c, b, w, s)) return 1;
   if (b->stages & PWB_STAGE_WINDOWS) if (run_windows(c, b, w, s)) return 1;
   return 0;
+}
+
+// Items are independent, so a large batch is cut into `chunks` contiguous sub-batches that run on
+// internal streams: the latency-bound optimiser kernels of one sub-batch overlap the FP-pipe-bound
+// ray / grid kernels of another, and the long tail of one kernel no longer idles the GPU.
+static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const double* h_coords, double* h_records) {
+  if (check(b)) return 1;
+  Ws w;
+  if (resolve(b, &w)) return 1;
+  const int G = (c->chunks > 1 && b->n_items >= 64 * c->chunks) ? c->chunks : 1;
+  // item_off lives on the device; the host variant needs atom offsets to cut the copies, which it
+  // can only do cheaply for equally sized items (trajectory of one molecule): total_atoms / n_items
+  const bool uniform = b->n_items > 0 && b->total_atoms % b->n_items == 0 && b->shared_types;
+  const size_t apf = uniform ? (size_t)(b->total_atoms / b->n_items) : 0;
+  const bool chunk_copies = h_coords && uniform;
+  if (h_coords && !chunk_copies)
+    CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, s));
+  if (G == 1) {
+    if (chunk_copies)
+      CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, s));
+    if (run_stages(c, b, w, s)) return 1;
+  } else {
+    CK(cudaEventRecord(c->fork, s));
+    const int per = (b->n_items + G - 1) / G;
+    for (int g = 0; g < G; g++) {
+      const int first = g * per, count = (first + per <= b->n_items) ? per : b->n_items - first;
+      if (count <= 0) break;
+      pwb_batch t = *b;
+      t.n_items = count;
+      t.item_off = b->item_off + first;
+      t.records = b->records + (size_t)first * b->rec_stride;
+      if (b->centre_override) t.centre_override = b->centre_override + (size_t)first * 3;
+      Ws u = w;
+      u.item_d += (size_t)first * ITEM_D; u.item_i += (size_t)first * ITEM_I;
+      u.clear_k += (size_t)first * b->ray_cap; u.clear_pos += (size_t)first * b->ray_cap;
+      u.clear_a2 += (size_t)first * b->ray_cap; u.labels += (size_t)first * b->ray_cap;
+      u.win_k += (size_t)first * b->win_cap;
+      cudaStream_t sg = c->streams[g];
+      CK(cudaStreamWaitEvent(sg, c->fork, 0));
+      if (chunk_copies)
+        CK(cudaMemcpyAsync((double*)b->coords + 3 * apf * first, h_coords + 3 * apf * first,
+                           sizeof(double) * 3 * apf * count, cudaMemcpyHostToDevice, sg));
+      if (run_stages(c, &t, u, sg)) return 1;
+      if (h_records)
+        CK(cudaMemcpyAsync(h_records + (size_t)first * b->rec_stride, t.records,
+                           sizeof(double) * (size_t)count * b->rec_stride, cudaMemcpyDeviceToHost, sg));
+      CK(cudaEventRecord(c->join[g], sg));
+      CK(cudaStreamWaitEvent(s, c->join[g], 0));
+    }
+    return 0;
+  }
+  if (h_records)
+    CK(cudaMemcpyAsync(h_records, b->records, sizeof(double) * (size_t)b->n_items * b->rec_stride, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// Items are independent, so a large batch is cut into `chunks` contiguous sub-batches that run on
+// internal streams: the latency-bound optimiser kernels of one sub-batch overlap the FP-pipe-bound
+// ray / grid kernels (and, in the host variant, the PCIe copies) of another, and the long tail of one
+// kernel no longer idles the GPU.
+int pwb_full_analysis_batch(pwb_ctx* c, const pwb_batch* b, void* stream) {
+  return batch_impl(c, b, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 static int run_stage(pwb_ctx* c, const pwb_batch* b, void* stream, int stages) {
@@ -1183,9 +1266,8 @@ int pwb_full_analysis_host(pwb_ctx* c, const pwb_batch* b, const double* h_coord
   pwb_batch t = *b;
   t.coords = d_coords;
   t.records = d_records;
-  CK(cudaMemcpyAsync(d_coords, h_coords, sizeof(double) * 3 * (size_t)total_atoms, cudaMemcpyHostToDevice, s));
-  if (pwb_full_analysis_batch(c, &t, stream)) return 1;
-  CK(cudaMemcpyAsync(h_records, d_records, sizeof(double) * (size_t)b->n_items * b->rec_stride, cudaMemcpyDeviceToHost, s));
+  t.total_atoms = total_atoms;
+  if (batch_impl(c, &t, s, h_coords, h_records)) return 1;
   CK(cudaStreamSynchronize(s));
   return 0;
 }

@@ -84,7 +84,7 @@ class BatchResult:
 
 
 class Engine:
-    def __init__(self, device=None, table_cap=4096, win_cap=DEFAULT_WIN_CAP):
+    def __init__(self, device=None, table_cap=4096, win_cap=DEFAULT_WIN_CAP, chunks=4):
         if not torch.cuda.is_available():
             raise PwbNoDeviceError("pywindow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -94,7 +94,13 @@ class Engine:
         self._ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pwb_ctx_create(ctypes.byref(self._ctx), self.device.index, table_cap))
+        self.set_chunks(chunks)
         self._pinned = {}
+
+    def set_chunks(self, chunks):
+        """Sub-batches pipelined over internal CUDA streams per call (1 = strictly sequential stages)."""
+        self.chunks = int(chunks)
+        self.lib.pwb_ctx_set_chunks(self._ctx, self.chunks)
 
     def close(self):
         if self._ctx:
