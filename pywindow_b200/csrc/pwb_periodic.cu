@@ -123,6 +123,13 @@ k_dm_bonds(DmArgs A, double max_dist) {
   unsigned list[DM_ADJ_CAP];
   int n = 0, overflow = 0;
   const bool images = A.rebuild != 0;
+  double taux = 0, tauy = 0, tauz = 0;
+  if (A.periodic) {
+    const double md = max_dist + 1e-6;     // slack for the 8-decimal rounding of the coordinates
+    taux = md * sqrt(fd[9] * fd[9] + fd[10] * fd[10] + fd[11] * fd[11]) * (1.0 + 1e-9);
+    tauy = md * sqrt(fd[12] * fd[12] + fd[13] * fd[13] + fd[14] * fd[14]) * (1.0 + 1e-9);
+    tauz = md * sqrt(fd[15] * fd[15] + fd[16] * fd[16] + fd[17] * fd[17]) * (1.0 + 1e-9);
+  }
   for (int t0 = 0; t0 < A.N; t0 += DM_TILE) {
     int b = t0 + threadIdx.x;
     __syncthreads();
@@ -145,12 +152,21 @@ k_dm_bonds(DmArgs A, double max_dist) {
         }
         continue;
       }
-      // minimum image offset, then the 27 offsets around it
-      const double m0x = rint(afx - sfx[j]), m0y = rint(afy - sfy[j]), m0z = rint(afz - sfz[j]);
-      // cheap reject: nearest image already farther than the cut-off in every candidate? (keep exact)
-      for (int ia = -1; ia <= 1; ia++)
-        for (int ib = -1; ib <= 1; ib++)
+      // minimum image offset m0, then the offsets around it that can be within the cut-off at all:
+      // |delta f_c| <= |delta x| * |row c of inv(lattice)|, so an image needs |df_c - m_c| <= tau_c on
+      // every axis; for ordinary cells that leaves at most the minimum image and rejects >99 % of the
+      // pairs after three subtractions.
+      const double dfx = afx - sfx[j], dfy = afy - sfy[j], dfz = afz - sfz[j];
+      const double m0x = rint(dfx), m0y = rint(dfy), m0z = rint(dfz);
+      const double ex = dfx - m0x, ey = dfy - m0y, ez = dfz - m0z;
+      if (fabs(ex) - 1.0 > taux || fabs(ey) - 1.0 > tauy || fabs(ez) - 1.0 > tauz) continue;
+      if (taux < 0.5 && tauy < 0.5 && tauz < 0.5 && (fabs(ex) > taux || fabs(ey) > tauy || fabs(ez) > tauz)) continue;
+      for (int ia = -1; ia <= 1; ia++) {
+        if (fabs(ex - ia) > taux) continue;
+        for (int ib = -1; ib <= 1; ib++) {
+          if (fabs(ey - ib) > tauy) continue;
           for (int ic = -1; ic <= 1; ic++) {
+            if (fabs(ez - ic) > tauz) continue;
             const double ma = m0x + ia, mb = m0y + ib, mc = m0z + ic;
             double X, Y, Z;
             if (ma == 0 && mb == 0 && mc == 0) { X = sx[j]; Y = sy[j]; Z = sz[j]; }
@@ -171,6 +187,8 @@ k_dm_bonds(DmArgs A, double max_dist) {
               if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
             }
           }
+        }
+      }
     }
   }
   if (a >= A.N) return;

@@ -116,6 +116,48 @@ def discrete_molecules_batch(coords, elements, lattice=None, rebuild=False, tol=
             return DiscreteBatch(n_mol.cpu().numpy(), mol_off, out_src, out_xyz, status, N)
 
 
+def analyse_cells(coords, elements, lattice=None, rebuild=False, tol=0.4, engine=None, **kw):
+    """Periodic pipeline kept on the device: ``discrete_molecules`` for every cell-frame, then
+    ``Molecule.full_analysis`` for every molecule found (MolecularSystem.make_modular + the per-molecule
+    loop of trajectory.py:512-522 for a whole batch of frames).
+
+    ``coords`` [F,N,3]; ``lattice`` None | [3,3] | [F,3,3].  Returns ``(records [M, stride] numpy,
+    keys [(frame_index, molecule_index)], sizes [M])`` in the reference's molecule order."""
+    eng = engine or default_engine()
+    dev = eng.device
+    res = discrete_molecules_batch(coords, elements, lattice=lattice, rebuild=rebuild, tol=tol, engine=eng)
+    F = int(coords.shape[0])
+    with torch.cuda.device(dev):
+        nm = torch.as_tensor(res.n_mol, device=dev, dtype=torch.int64)
+        mol_cap = res.mol_off.shape[1] - 1
+        out_cap = res.out_src.shape[1]
+        mmask = torch.arange(mol_cap, device=dev)[None, :] < nm[:, None]
+        starts = res.mol_off[:, :-1][mmask].to(torch.int64)
+        ends = res.mol_off[:, 1:][mmask].to(torch.int64)
+        sizes = ends - starts
+        if sizes.numel() == 0:
+            return np.zeros((0, eng.rec_stride)), [], np.zeros(0, dtype=np.int64)
+        tot = torch.gather(res.mol_off.to(torch.int64), 1, nm[:, None]).squeeze(1)
+        amask = torch.arange(out_cap, device=dev)[None, :] < tot[:, None]
+        dense_xyz = res.out_xyz[amask]
+        types, vdw, mass = _engine_types(elements)
+        dense_types = torch.as_tensor(types, device=dev)[res.out_src[amask].to(torch.int64)]
+        item_off = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=dev)
+        item_off[1:] = torch.cumsum(sizes, 0)
+        max_atoms = int(sizes.max().item())
+        out = eng.analyse(dense_xyz, item_off.to(torch.int32), dense_types, vdw, mass, shared_types=False,
+                          max_atoms=max_atoms, **kw)
+        frame_idx = torch.arange(F, device=dev)[:, None].expand(F, mol_cap)[mmask].cpu().numpy()
+        mol_idx = torch.arange(mol_cap, device=dev)[None, :].expand(F, mol_cap)[mmask].cpu().numpy()
+        keys = [(int(f), int(k)) for f, k in zip(frame_idx, mol_idx)]
+        return out.host_records(), keys, sizes.cpu().numpy()
+
+
+def _engine_types(elements):
+    from .engine import element_types
+    return element_types(elements)
+
+
 def discrete_molecules(system, rebuild=None, tol=0.4):
     """utilities.py:820-1085 for one system dict -> list of molecule dicts.  ``rebuild`` is the
     supercell dict of :func:`create_supercell` in the reference; only its presence matters here."""

@@ -181,17 +181,42 @@ class Trajectory:
         return np.concatenate(recs), [(f, "0") for f in frames]
 
     def _analyse_modular(self, frames, rebuild, swap_atoms, forcefield, gpu_kwargs):
+        """modular=True: every frame is decomposed into discrete molecules on the GPU (rebuilt across
+        the periodic boundary if asked) and every molecule analysed, whole batches of frames at once."""
+        from .periodic import analyse_cells
         eng = default_engine()
-        mols, keys = [], []
-        for f in frames:
-            ms = self._get_frame(self.trajectory_map[f], f, swap_atoms=swap_atoms, forcefield=forcefield)
-            ms.make_modular(rebuild=rebuild)
-            for k, m in ms.molecules.items():
-                mols.append((m.elements, m.coordinates))
-                keys.append((f, k))
-        if not mols:
+        if not frames:
             return np.zeros((0, eng.rec_stride)), []
-        return eng.analyse_molecules(mols, **gpu_kwargs).host_records(), keys
+        elements = self._elements_of(frames[0], swap_atoms, forcefield)
+        recs, keys = [], []
+        step = max(1, min(self.batch_frames, (1 << 21) // max(1, len(elements))))
+        for s in range(0, len(frames), step):
+            chunk = frames[s:s + step]
+            coords, lattice = self._decode_cells(chunk)
+            if rebuild and lattice is None:
+                raise _TrajectoryError("rebuild=True needs periodic frames (no lattice / CRYST1 record found)")
+            r, k, _ = analyse_cells(coords, elements, lattice=lattice, rebuild=rebuild, engine=eng, **gpu_kwargs)
+            recs.append(r)
+            keys += [(chunk[f], m) for f, m in k]
+        return np.concatenate(recs), keys
+
+    def _decode_cells(self, frames):
+        """([F,N,3] coordinates, [F,3,3] lattices | None) for the requested frames."""
+        coords, lats = None, []
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            for k, f in enumerate(frames):
+                start, end = self.trajectory_map[f]
+                fr = self._decode_frame(mm[start:end])
+                xyz = np.asarray(fr["coordinates"], dtype=np.float64)
+                if coords is None:
+                    coords = np.empty((len(frames),) + xyz.shape, dtype=np.float64)
+                if xyz.shape != coords.shape[1:]:
+                    raise _TrajectoryError(f"frame {f} has {xyz.shape[0]} atoms, expected {coords.shape[1]}")
+                coords[k] = xyz
+                if "lattice" in fr:
+                    lats.append(np.asarray(fr["lattice"], dtype=np.float64))
+        lattice = np.stack(lats) if len(lats) == len(frames) else None
+        return coords, lattice
 
     # ---- output (trajectory.py:251-347)
     def save_analysis(self, filepath=None, **kwargs):

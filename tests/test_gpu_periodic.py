@@ -65,3 +65,29 @@ def test_rebuild_system_and_modular_analysis():
     assert ms.no_of_discrete_molecules == 8
     p = ms.molecules[0].full_analysis()
     assert p["no_of_atoms"] == 168 and len(p["windows"]["diameters"]) == 4
+
+
+def test_periodic_trajectory_pipeline(tmp_path):
+    """Example-8 style flow: DLPOLY HISTORY with a lattice -> analysis(modular=True, rebuild=True);
+    the batched device pipeline must equal make_modular + full_analysis done molecule by molecule."""
+    import pywindow_b200 as pw
+    from pywindow_b200 import synthetic
+    from pywindow_b200.utilities import unit_cell_to_lattice_array
+    g = load_golden("per_pudxes_noise1")
+    g2 = load_golden("per_pudxes_noise2")
+    lat = unit_cell_to_lattice_array(g["unit_cell"])
+    X = np.stack([g["coords"], g2["coords"]])
+    path = tmp_path / "HISTORY"
+    synthetic.write_history(path, [e + "1" for e in g["elements"]], X, lattice=lat)
+    t = pw.DLPOLY(path)
+    t.analysis(modular=True, rebuild=True, forcefield="DLF")
+    assert sorted(t.analysis_output) == [0, 1]
+    for f, gg in ((0, g), (1, g2)):
+        assert sorted(t.analysis_output[f]) == list(range(8))
+        ms = t.get_frames(f, forcefield="DLF")[f]
+        ms.make_modular(rebuild=True)
+        for k in range(8):
+            np.testing.assert_allclose(ms.molecules[k].coordinates, gg["rebuild_coords"][168 * k:168 * (k + 1)], atol=2e-7)
+            p = ms.molecules[k].full_analysis()
+            assert pw.compare_properties_dict(p, t.analysis_output[f][k]) == (True, "none"), (f, k)
+            assert len(p["windows"]["diameters"]) == 4
