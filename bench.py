@@ -51,8 +51,8 @@ def synth(seeds, first, count):
 
 # ----------------------------------------------------------------------------- algorithmic work
 def flop_model(rec, n_atoms, increment=1.0, increment2=0.1):
-    """SURVEY.md 8(d) work formula evaluated with each frame's own P, S, C, W (mean FLOP per frame)
-    -> (total, rays_stage)."""
+    """SURVEY.md 8(d) work formula evaluated with each frame's own P, S, C, W: mean algorithmic FLOP
+    per frame, split by the stage (kernel) that does the work -> dict."""
     from pywindow_b200 import _lib as L
     N = n_atoms
     D = rec[:, L.REC_MAXD]
@@ -62,11 +62,17 @@ def flop_model(rec, n_atoms, increment=1.0, increment2=0.1):
     C2 = np.floor(R / increment2)
     Pa = np.floor(np.log10(4 * np.pi * D * D) * 250)
     c_p, c_d, c_r, E_p, E_z, E_xy = 12.0, 11.0, 10.0, 100.0, 30.0, 70.0
-    rays = c_r * N * Pw + c_d * N * S * (C + 1)
     nclear = rec[:, L.REC_NCLEAR]
-    tot = (c_p * N * N / 2 + c_d * N * (1 + E_p) + rays + 8 * nclear ** 2 +
-           W * c_d * N * (C2 + 1 + E_z + 400 + E_xy + 2) + c_r * N * Pa)
-    return float(tot.mean()), float(rays.mean())
+    parts = {
+        "prepare+avg_diameter": c_p * N * N / 2 + c_d * N + c_r * N * Pa,
+        "opt_pore": c_d * N * E_p + 0 * D,
+        "rays": c_r * N * Pw + c_d * N * S * (C + 1),
+        "cluster": 8 * nclear ** 2,
+        "windows": W * c_d * N * (C2 + 1 + E_z + 400 + E_xy + 2),
+    }
+    out = {k: float(np.mean(v)) for k, v in parts.items()}
+    out["total"] = float(sum(out.values()))
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -294,7 +300,8 @@ def run_ours(args):
 
     # ---- rank 0: roofline, CPU baseline, JSON line
     rec_h = rec.cpu().numpy()
-    flop_frame, flop_rays = flop_model(rec_h, N)
+    flops = flop_model(rec_h, N)
+    flop_frame = flops["total"]
     fp32 = ctypes.c_double(0)
     fp64 = ctypes.c_double(0)
     L.check(eng.lib.pwb_fma_peak(eng._ctx, 0, sp, ctypes.byref(fp32)))
@@ -304,13 +311,29 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    k_dom = int(np.argmax(stage_ms))
-    rays_idx = [n for n, _ in stage_list].index("rays")
-    rays_tflops = flop_rays * F / (stage_ms[rays_idx] * 1e-3) / 1e12
+    traffic = {}
+    tj = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tj):
+        traffic = json.load(open(tj))
+    names = [n for n, _ in stage_list]
+    kernel_of = {"prepare+avg_diameter": "k_prepare", "opt_pore": "k_opt_pore", "rays": "k_rays",
+                 "cluster": "k_cluster", "windows": "k_windows"}
+    stages = {}
+    for n, ms_ in zip(names, stage_ms):
+        tf = flops[n] * F / (ms_ * 1e-3) / 1e12
+        tr = traffic.get(kernel_of[n])
+        stages[n] = {"kernel": kernel_of[n], "ms": float(ms_), "share": float(ms_ / stage_ms.sum()),
+                     "flop_per_frame": flops[n], "achieved": tf, "frac": tf / fp32.value,
+                     "traffic": (tr["bytes_per_frame"] * F if tr else None)}
+    dom = names[int(np.argmax(stage_ms))]
     bytes_frame = N * 3 * 8 + eng.rec_stride * 8
     roofline = {
-        "bound": "fp32-fma", "kernel": "k_rays", "achieved": rays_tflops, "peak": fp32.value, "unit": "TFLOP/s",
-        "frac": rays_tflops / fp32.value, "traffic": None,
+        "bound": "fp32-fma (compute; neither hbm nor tensor: K=3 contractions, 4.7 KB/frame)",
+        "kernel": kernel_of[dom], "achieved": stages[dom]["achieved"], "peak": fp32.value, "unit": "TFLOP/s",
+        "frac": stages[dom]["frac"], "traffic": stages[dom]["traffic"],
+        "definition": "dominant kernel by time; achieved = SURVEY 8(d) algorithmic FLOP of that stage x frames / its "
+                      "CUDA-event duration; opt_pore / windows are serial optimisers (latency bound), rays / prepare "
+                      "are FP-pipe bound",
         "peak_source": "pwb_fma_peak FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure); "
                        "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
         "fp64_peak_measured": fp64.value,
@@ -319,10 +342,9 @@ def run_ours(args):
         "hbm": {"achieved": value / world * bytes_frame / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": value / world * bytes_frame / 1e9 / hbm_peak,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"},
-        "stage_ms": {n: float(v) for (n, _), v in zip(stage_list, stage_ms)},
+        "stages": stages,
         "stage_ms_note": "stage-by-stage re-run of the same steps on one stream (chunks=1); the timed region "
                          "pipelines %d sub-batches over internal streams, so its step time is below the sum" % args.chunks,
-        "dominant_stage": stage_list[k_dom][0],
         "arithmetic": "f64 kernels; FLOP counted by the SURVEY 8(d) per-frame work formula",
     }
     cores = os.cpu_count() or 1

@@ -117,6 +117,8 @@ typedef struct pwb_ws_layout {
   size_t clear_a2;   /* double[F][ray_cap]: 2*min clearance along the ray (column 1 of the record)*/
   size_t labels;     /* int32[F][ray_cap]: DBSCAN label of each clear ray                         */
   size_t win_k;      /* int32[F][win_cap]: arg-max ray of each cluster                            */
+  size_t big_pts;    /* double[F][ray_cap][4]: unit ray points, only if ray_cap > 4096 (config 5) */
+  size_t big_i;      /* int32[F][2][ray_cap]: union-find scratch of the large-ray-count path      */
   size_t total;
 } pwb_ws_layout;
 

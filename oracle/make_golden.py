@@ -31,7 +31,7 @@ def versions():
                      f"sklearn {sklearn.__version__}"])
 
 
-def analyse(pw, util, elements, coords, name, windows=True, scalars=True, avg=True):
+def analyse(pw, util, elements, coords, name, windows=True, scalars=True, avg=True, adjust=1):
     elements = np.asarray(elements)
     coords = np.asarray(coords, dtype=np.float64)
     out = {"elements": elements.astype("U4"), "coords": coords, "versions": versions()}
@@ -47,10 +47,11 @@ def analyse(pw, util, elements, coords, name, windows=True, scalars=True, avg=Tr
         except ValueError as e:  # bounds inverted when pore_diameter(COM) < 0
             out["opt_error"] = np.array([str(e)])
     if avg:
-        out["avg_diameter"] = np.array(util.find_average_diameter(elements, coords))
+        out["avg_diameter"] = np.array(util.find_average_diameter(elements, coords, adjust=adjust))
+        out["adjust"] = np.array(float(adjust))
     if windows and "opt_error" not in out:
         with Recorder(util) as rec:
-            res = util.find_windows(elements, coords)
+            res = util.find_windows(elements, coords, adjust=adjust)
         P = len(rec.rays)
         out["fw_centre"] = np.asarray(rec.opt[0][2], dtype=np.float64)
         out["fw_shifted"] = rec.shifted
@@ -162,6 +163,12 @@ def main():
             ms = pw.MolecularSystem.load_file(os.path.join(inp, fn))
             analyse(pw, util, ms.system["elements"], ms.system["coordinates"], "ex_" + nm)
         jobs.append(("ex_" + nm, ex))
+
+    for nm, fn, adj in (("mibqar_adj8", "MIBQAR.pdb", 8), ("saygor_adj113", "SAYGOR.pdb", 113)):
+        def big(nm=nm, fn=fn, adj=adj):
+            ms = pw.MolecularSystem.load_file(os.path.join(inp, fn))
+            analyse(pw, util, ms.system["elements"], ms.system["coordinates"], "big_" + nm, adjust=adj)
+        jobs.append(("big_" + nm, big))
 
     for nm, fn in (("pudxes_cell", "PUDXES_no_solvent.pdb"), ("epirur_cell", "EPIRUR_no_solvent.pdb"),
                    ("tatver_cell", "TATVER_no_solvent.pdb")):

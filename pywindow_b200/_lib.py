@@ -46,7 +46,7 @@ class Batch(ctypes.Structure):
 class WsLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
                 ("atoms", "atom_idx", "item_d", "item_i", "clear_k", "clear_pos", "clear_a2", "labels",
-                 "win_k", "total")]
+                 "win_k", "big_pts", "big_i", "total")]
 
 
 class PwbLibraryError(RuntimeError):

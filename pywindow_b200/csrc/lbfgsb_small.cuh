@@ -175,9 +175,12 @@ struct LbLineSearch {
   }
 };
 
+// The (s, y) ring lives in caller-provided storage (2*LB_M*N doubles): shared memory on the device, so
+// the 32 lanes that run the optimiser redundantly share ONE copy instead of 32 local-memory copies.
 template <int N>
 struct LbHistory {
-  double S[LB_M][N], Y[LB_M][N];
+  double (*S)[N];
+  double (*Y)[N];
   int col, head;   // head = slot of the oldest pair
 };
 
@@ -392,7 +395,8 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
 // lane runs this routine redundantly with identical data, so control flow is warp-uniform.)
 template <int N, class Obj>
 PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd,
-                            double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out) {
+                            double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out,
+                            double* hist_storage) {
   double g[N], f;
   int iwhere[N];
   bool cnstnd = false, boxed = true;
@@ -411,6 +415,8 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
   double sbgnrm = lb_projgr<N>(x, g, lo, hi, nbd);
   int iter = 0, status = LB_MAXITER;
   LbHistory<N> H;
+  H.S = reinterpret_cast<double (*)[N]>(hist_storage);
+  H.Y = reinterpret_cast<double (*)[N]>(hist_storage + LB_M * N);
   H.col = 0; H.head = 0;
   double theta = 1.0;
   if (sbgnrm <= pgtol) { *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }

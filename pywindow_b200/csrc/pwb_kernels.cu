@@ -25,7 +25,12 @@ struct Ws {   // resolved workspace pointers
   double* clear_a2;
   int* labels;
   int* win_k;      // [F][win_cap]
+  double* big_pts; // [F][ray_cap][4] unit-sphere ray points (only if ray_cap > KNN_SMEM_CAP)
+  int* big_i;      // [F][2][ray_cap] union-find / flag scratch of the large-ray-count path
 };
+
+constexpr int KNN_SMEM_CAP = 4096;   // ray counts served by the shared-memory eps table / DBSCAN paths
+constexpr int BIG_SLICES = 64;      // CTAs per item in the large-ray-count k-NN kernel
 
 struct Ctx {
   int device;
@@ -266,9 +271,9 @@ k_opt_pore(pwb_batch b, Ws ws) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  const int NAp = (NA + 3) & ~3;
-  double* x = sm + (size_t)w * (NA * 4 + 16 + NAp / 4);
+  double* x = sm + (size_t)w * (NA * 4 + 2 * LB_M * 3);
   double* y = x + NA; double* z = y + NA; double* r = z + NA;
+  double* hist = r + NA;                                      // [2*LB_M*3] L-BFGS (s, y) ring, one copy per warp
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
     x[a] = q[0]; y[a] = q[1]; z[a] = q[2]; r[a] = q[3];
@@ -293,7 +298,7 @@ k_opt_pore(pwb_batch b, Ws ws) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
     DevPoreObj3 obj{A, lo, hi, nbd, 0};
-    st = lbfgsb_minimize<3>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit);
+    st = lbfgsb_minimize<3>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
     nfev = obj.nfev;
   }
   ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
@@ -384,9 +389,9 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     idv[D_SHIFT] = shx; idv[D_SHIFT + 1] = shy; idv[D_SHIFT + 2] = shz;
     iiv[I_P] = P;
     rec[PWB_REC_NRAYS] = P; rec[PWB_REC_RADIUS] = R;
-    if (P >= 2 && P < ctx.table_cap) ctx.knn_need[P] = 1;
+    if (P >= 2 && P < ctx.table_cap && P <= KNN_SMEM_CAP) ctx.knn_need[P] = 1;
   }
-  if (P > b.ray_cap || P >= ctx.table_cap || P < 2) {
+  if (P > b.ray_cap || (P <= KNN_SMEM_CAP && P >= ctx.table_cap) || P < 2) {
     if (tid == 0) { iiv[I_STATUS] |= PWB_ST_RAY_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; iiv[I_NCLEAR] = 0; iiv[I_NSURV] = 0; }
     return;
   }
@@ -488,12 +493,12 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
 // =================================================================================================
 constexpr int KNN_THREADS = 256;
 __global__ void __launch_bounds__(KNN_THREADS)
-k_knn_fill(Ctx ctx) {
+k_knn_fill(Ctx ctx, int kcap) {
   extern __shared__ double sm[];
   const int P = blockIdx.x + 2;
-  if (P >= ctx.table_cap) return;
+  if (P >= kcap) return;
   if (!ctx.knn_need[P] || ctx.knn_unit[P] != 0.0) return;
-  double* ux = sm; double* uy = ux + ctx.table_cap; double* uz = uy + ctx.table_cap;
+  double* ux = sm; double* uy = ux + kcap; double* uz = uy + kcap;
   __shared__ double red[64];
   for (int i = threadIdx.x; i < P; i += blockDim.x) spiral_point(i, P, 1.0, ux[i], uy[i], uz[i]);
   __syncthreads();
@@ -555,8 +560,12 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   const int st = iiv[I_STATUS];
   if (st & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP)) { if (tid == 0) iiv[I_NWIN] = 0; return; }
-  if (pass == 1 && !iiv[I_DEFER]) return;
+  if (pass == 1 && iiv[I_DEFER] != 1) return;
   const int S = iiv[I_NCLEAR], P = iiv[I_P];
+  if (P > KNN_SMEM_CAP) {                        // eps table not available: large-ray-count path
+    if (pass == 0 && tid == 0) { iiv[I_DEFER] = 2; iiv[I_NWIN] = 0; rec[PWB_REC_NWIN] = 0; }
+    return;
+  }
   const double R = idv[D_RADIUS];
   const double m = R * ctx.knn_unit[P];
   const double eps = m + sqrt(m);
@@ -568,8 +577,7 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
   const size_t need_base = 32 * (size_t)S + 12 * (size_t)b.win_cap + 8 * (size_t)S + 4 * (32 + 128) + ((S + 7) & ~7) + 64;
   const bool use_bits = need_base + 4 * (size_t)S * Wd <= budget;
   if (pass == 0 ? !use_bits : need_base > budget) {
-    if (pass == 0) { if (tid == 0) iiv[I_DEFER] = 1; }
-    else if (tid == 0) { atomicOr(&iiv[I_STATUS], PWB_ST_RAY_CAP); }
+    if (tid == 0) iiv[I_DEFER] = (pass == 0) ? 1 : 2;   // 2: does not fit any shared-memory path
     return;
   }
   double* px = sm;                                               // [S][4] points
@@ -760,6 +768,201 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
 }
 
 // =================================================================================================
+// Large ray counts (adjust >> 1, P up to ~1e6; BASELINE config 5).  The golden spiral is monotone in z
+// (z_k falls by 2/P per point), so two points closer than d differ by at most d*P/2 in index: both the
+// 10-NN mean (eps) and the DBSCAN neighbourhoods only need an index window instead of all pairs.
+//   k_big_points  unit-sphere points of the item's ray set -> big_pts
+//   k_knn_big     BIG_SLICES CTAs per item: partial sums of the 10 smallest distances (stored in .w)
+//   k_cluster_big one CTA per item: windowed DBSCAN with union-find in global memory
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_big_points(pwb_batch b, Ws ws) {
+  const int item = blockIdx.y;
+  const int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  if (iiv[I_DEFER] != 2 || (iiv[I_STATUS] & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP))) return;
+  const int P = iiv[I_P];
+  double4* U = (double4*)(ws.big_pts + (size_t)item * b.ray_cap * 4);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P; k += gridDim.x * blockDim.x) {
+    double x, y, z;
+    spiral_point(k, P, 1.0, x, y, z);
+    U[k] = make_double4(x, y, z, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_knn_big(pwb_batch b, Ws ws) {
+  const int item = blockIdx.y, slice = blockIdx.x;
+  const int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  if (iiv[I_DEFER] != 2 || (iiv[I_STATUS] & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP))) return;
+  const int P = iiv[I_P];
+  double4* U = (double4*)(ws.big_pts + (size_t)item * b.ray_cap * 4);
+  __shared__ double red[64];
+  // a disc holding 10 of P uniformly spread points has radius sqrt(40/P); 1.5x that bounds the 10th
+  // neighbour everywhere on the spiral (checked per point, full scan otherwise)
+  const double dmax = 1.5 * sqrt(40.0 / (double)P), dmax2 = dmax * dmax;
+  const int Wk = (int)ceil(dmax * P * 0.5) + 2;
+  const int per = (P + BIG_SLICES - 1) / BIG_SLICES;
+  const int i0 = slice * per, i1 = min(P, i0 + per);
+  double acc = 0;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const double4 a = U[i];
+    double best[10];
+    int lo = max(0, i - Wk), hi = min(P, i + Wk + 1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+#pragma unroll
+      for (int q = 0; q < 10; q++) best[q] = PWB_INF;
+      for (int j = lo; j < hi; j++) {
+        const double4 o = U[j];
+        const double dx = a.x - o.x, dy = a.y - o.y, dz = a.z - o.z;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best[9]) {
+          best[9] = d2;
+#pragma unroll
+          for (int q = 9; q > 0; q--)
+            if (best[q] < best[q - 1]) { double t = best[q]; best[q] = best[q - 1]; best[q - 1] = t; }
+        }
+      }
+      if (best[9] <= dmax2 || (lo == 0 && hi == P)) break;   // window provably contained the 10 nearest
+      lo = 0; hi = P;
+    }
+#pragma unroll
+    for (int q = 0; q < 10; q++) acc += sqrt(best[q]);
+  }
+  acc = block_sum(acc, red);
+  __syncthreads();
+  if (threadIdx.x == 0) ((double*)&U[slice])[3] = acc;      // partial sum parked in the unused .w
+}
+
+__device__ __forceinline__ int uf_find_halving(int* parent, int i) {
+  while (true) {
+    int p = ((volatile int*)parent)[i];
+    if (p == i) return i;
+    int gp = ((volatile int*)parent)[p];
+    if (gp != p) parent[i] = gp;           // path halving (benign race: gp is still an ancestor)
+    i = p;
+  }
+}
+__device__ __forceinline__ void uf_union_g(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find_halving(parent, a); b = uf_find_halving(parent, b);
+    if (a == b) return;
+    if (a > b) { int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[b], b, a) == b) return;
+  }
+}
+
+constexpr int CLB_THREADS = 512;
+__global__ void __launch_bounds__(CLB_THREADS)
+k_cluster_big(pwb_batch b, Ws ws) {
+  const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  int* iiv = ws.item_i + (size_t)item * ITEM_I;
+  if (iiv[I_DEFER] != 2 || (iiv[I_STATUS] & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP))) return;
+  double* idv = ws.item_d + (size_t)item * ITEM_D;
+  double* rec = b.records + (size_t)item * b.rec_stride;
+  const int S = iiv[I_NCLEAR], P = iiv[I_P], cap = b.ray_cap;
+  const double R = idv[D_RADIUS];
+  const double4* U = (const double4*)(ws.big_pts + (size_t)item * cap * 4);
+  __shared__ int wsum[32];
+  __shared__ unsigned long long cbest[64];
+  __shared__ int cidx[64];
+  double munit;
+  if (P > KNN_SMEM_CAP) {
+    double t = 0;
+    for (int sl = 0; sl < BIG_SLICES; sl++) t += U[sl].w;   // fixed order: deterministic
+    munit = t / (10.0 * (double)P);
+  } else munit = 0.0;   // (items deferred only for their size have P <= KNN_SMEM_CAP: not routed here)
+  const double m = R * munit;
+  const double eps = m + sqrt(m), eps2 = eps * eps;
+  if (tid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; }
+  if (S == 0) return;
+  const int Wk = (int)ceil((eps / R) * P * 0.5) + 2;
+  const int* ck = ws.clear_k + (size_t)item * cap;
+  const double* ca2 = ws.clear_a2 + (size_t)item * cap;
+  int* parent = ws.big_i + (size_t)item * 2 * cap;
+  int* aux = parent + cap;                    // core flag, later the border label
+  int* label = ws.labels + (size_t)item * cap;
+  const double hR2 = 0.5 * R * R;             // |p|^2/2 for p = R u, |u| = 1 (to rounding)
+  // window [jlo, jhi) of clear rays whose ray index is within Wk of ray i's (ck is ascending)
+  auto window = [&](int i, int& jlo, int& jhi) {
+    const int klo = ck[i] - Wk, khi = ck[i] + Wk;
+    int a = 0, c = i;
+    while (a < c) { int mid = (a + c) >> 1; if (ck[mid] < klo) a = mid + 1; else c = mid; }
+    jlo = a;
+    a = i; c = S;
+    while (a < c) { int mid = (a + c) >> 1; if (ck[mid] <= khi) a = mid + 1; else c = mid; }
+    jhi = a;
+  };
+  auto adjacent = [&](const double4& ui, int j) {
+    const double4 uj = U[ck[j]];
+    const double dx = R * ui.x - R * uj.x, dy = R * ui.y - R * uj.y, dz = R * ui.z - R * uj.z;
+    return dx * dx + dy * dy + dz * dz <= eps2;
+  };
+  (void)hR2;
+  for (int i = tid; i < S; i += nt) {
+    int jlo, jhi, c = 0;
+    window(i, jlo, jhi);
+    const double4 ui = U[ck[i]];
+    for (int j = jlo; j < jhi; j++) c += adjacent(ui, j);
+    aux[i] = c >= 5;
+    parent[i] = i;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    if (!aux[i]) continue;
+    int jlo, jhi;
+    window(i, jlo, jhi);
+    const double4 ui = U[ck[i]];
+    for (int j = jlo; j < i; j++)
+      if (aux[j] && adjacent(ui, j)) uf_union_g(parent, i, j);
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) if (aux[i]) parent[i] = uf_find_halving(parent, i);
+  __syncthreads();
+  int nclus = 0;
+  for (int s0 = 0; s0 < S; s0 += nt) {
+    const int i = s0 + tid;
+    const int isroot = (i < S && aux[i] && parent[i] == i) ? 1 : 0;
+    int tot;
+    const int o = block_excl_scan(isroot, wsum, tot);
+    if (isroot) label[i] = nclus + o;
+    nclus += tot;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) if (aux[i] && parent[i] != i) label[i] = label[parent[i]];
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    if (aux[i]) continue;
+    int jlo, jhi, best = 0x7fffffff;
+    window(i, jlo, jhi);
+    const double4 ui = U[ck[i]];
+    for (int j = jlo; j < jhi; j++)
+      if (aux[j] && adjacent(ui, j)) best = min(best, label[j]);
+    parent[i] = best;
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) if (!aux[i]) label[i] = (parent[i] == 0x7fffffff) ? -1 : parent[i];
+  const int W = min(nclus, min(b.win_cap, 64));
+  for (int c = tid; c < 64; c += nt) { cbest[c] = 0ull; cidx[c] = 0x7fffffff; }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    const int l = label[i];
+    if (l >= 0 && l < W) atomicMax(&cbest[l], (unsigned long long)__double_as_longlong(ca2[i]));
+  }
+  __syncthreads();
+  for (int i = tid; i < S; i += nt) {
+    const int l = label[i];
+    if (l >= 0 && l < W && (unsigned long long)__double_as_longlong(ca2[i]) == cbest[l]) atomicMin(&cidx[l], i);
+  }
+  __syncthreads();
+  int* wk = ws.win_k + (size_t)item * b.win_cap;
+  for (int c = tid; c < W; c += nt) wk[c] = ck[cidx[c]];
+  if (tid == 0) {
+    iiv[I_NWIN] = W; rec[PWB_REC_NWIN] = W;
+    if (nclus > W) { iiv[I_STATUS] |= PWB_ST_WIN_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+  }
+}
+
+// =================================================================================================
 // k_windows: window_analysis (utilities.py:1191-1361), one warp per (item, window)
 // =================================================================================================
 constexpr int WIN_WARPS = 4;
@@ -804,12 +1007,13 @@ k_windows(pwb_batch b, Ws ws) {
   double* out = rec + PWB_REC_WIN0 + 4 * win;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
   const int NAp = (NA + 3) & ~3;
-  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 32 + NAp / 4);
+  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 32 + NAp / 4 + 2 * LB_M);
   double* y = x + NA; double* z = y + NA; double* r = z + NA; double* w2 = r + NA;
   double* cr = w2 + NA;                      // [PWB_MAX_TYPES]
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
   int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
   unsigned short* nidx = (unsigned short*)(cr + PWB_MAX_TYPES + 32);   // [NA] near-list atom indices
+  double* hist = cr + PWB_MAX_TYPES + 32 + NAp / 4;                     // [2*LB_M] z-stage L-BFGS ring
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -885,7 +1089,7 @@ k_windows(pwb_batch b, Ws ws) {
   // ---- z stage: L-BFGS-B from 0 with lower bound -new_z (utilities.py:1296-1305)
   double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nbd1[1] = {1}, nitz;
   DevZObj zo{A, -new_z};
-  lbfgsb_minimize<1>(zo, zc, zlo, zhi, nbd1, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz);
+  lbfgsb_minimize<1>(zo, zc, zlo, zhi, nbd1, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
   const double wz = zc[0];
   // ---- xy stage: 20x20 brute grid (first arg-min, row-major) + Nelder-Mead (utilities.py:1307-1316)
   const double glo = -d0 / 2, ghi = d0 / 2;
@@ -1022,6 +1226,9 @@ int pwb_workspace_layout(int F, int total_atoms, int ray_cap, int win_cap, pwb_w
   L->clear_a2 = o; o = align_up(o + (size_t)F * ray_cap * sizeof(double));
   L->labels = o; o = align_up(o + (size_t)F * ray_cap * sizeof(int));
   L->win_k = o; o = align_up(o + (size_t)F * win_cap * sizeof(int));
+  const size_t big = ray_cap > KNN_SMEM_CAP ? (size_t)F * ray_cap : 0;   // large-ray-count scratch
+  L->big_pts = o; o = align_up(o + big * 4 * sizeof(double));
+  L->big_i = o; o = align_up(o + big * 2 * sizeof(int));
   L->total = o;
   return 0;
 }
@@ -1076,6 +1283,7 @@ static int resolve(const pwb_batch* b, Ws* w) {
   w->item_d = (double*)(p + L.item_d); w->item_i = (int*)(p + L.item_i);
   w->clear_k = (int*)(p + L.clear_k); w->clear_pos = (int*)(p + L.clear_pos);
   w->clear_a2 = (double*)(p + L.clear_a2); w->labels = (int*)(p + L.labels); w->win_k = (int*)(p + L.win_k);
+  w->big_pts = (double*)(p + L.big_pts); w->big_i = (int*)(p + L.big_i);
   return 0;
 }
 
@@ -1083,7 +1291,7 @@ static int check(const pwb_batch* b) {
   if (b->n_items <= 0) { snprintf(g_err, sizeof g_err, "n_items must be positive"); return 1; }
   if (b->n_types < 1 || b->n_types > PWB_MAX_TYPES) { snprintf(g_err, sizeof g_err, "n_types out of range"); return 1; }
   if (b->rec_stride < PWB_REC_WIN0 + 4 * b->win_cap) { snprintf(g_err, sizeof g_err, "rec_stride too small"); return 1; }
-  if (b->ray_cap > 4096) { snprintf(g_err, sizeof g_err, "ray_cap > 4096 not supported by this revision"); return 1; }
+  if (b->ray_cap > (1 << 22)) { snprintf(g_err, sizeof g_err, "ray_cap > 4M rays not supported"); return 1; }
   return 0;
 }
 
@@ -1096,7 +1304,7 @@ static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + 16 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4) * OPT_WARPS;
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + 2 * LB_M * 3) * OPT_WARPS;
   if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
   k_opt_pore<<<(b->n_items + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, sm, s>>>(*b, w);
   c->c.launches++;
@@ -1113,9 +1321,10 @@ static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s)
   return 0;
 }
 static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t smk = sizeof(double) * 3 * (size_t)c->c.table_cap;
+  const int kcap = c->c.table_cap < KNN_SMEM_CAP + 1 ? c->c.table_cap : KNN_SMEM_CAP + 1;
+  size_t smk = sizeof(double) * 3 * (size_t)kcap;
   if (set_smem(k_knn_fill, smk, c->max_smem)) return 1;
-  k_knn_fill<<<c->c.table_cap - 2, KNN_THREADS, smk, s>>>(c->c);
+  k_knn_fill<<<kcap - 2, KNN_THREADS, smk, s>>>(c->c, kcap);
   c->c.launches++;
   // pass 0: small budget, high occupancy; pass 1: whatever the device allows, deferred items only
   unsigned big = (unsigned)c->max_smem;
@@ -1123,11 +1332,17 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   k_cluster<<<b->n_items, CL_THREADS, CL_SMALL_SMEM, s>>>(*b, w, c->c, 0, CL_SMALL_SMEM);
   k_cluster<<<b->n_items, CL_THREADS, big, s>>>(*b, w, c->c, 1, big);
   c->c.launches += 2;
+  if (b->ray_cap > KNN_SMEM_CAP) {                 // items whose ray count exceeds the shared-memory paths
+    k_big_points<<<dim3(64, b->n_items), 256, 0, s>>>(*b, w);
+    k_knn_big<<<dim3(BIG_SLICES, b->n_items), 256, 0, s>>>(*b, w);
+    k_cluster_big<<<b->n_items, CLB_THREADS, 0, s>>>(*b, w);
+    c->c.launches += 3;
+  }
   CK(cudaGetLastError());
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4) * WIN_WARPS + 64;
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4 + 2 * LB_M) * WIN_WARPS + 64;
   if (set_smem(k_windows, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
   k_windows<<<(unsigned)((warps + WIN_WARPS - 1) / WIN_WARPS), WIN_WARPS * 32, sm, s>>>(*b, w);
@@ -1198,6 +1413,7 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       u.clear_k += (size_t)first * b->ray_cap; u.clear_pos += (size_t)first * b->ray_cap;
       u.clear_a2 += (size_t)first * b->ray_cap; u.labels += (size_t)first * b->ray_cap;
       u.win_k += (size_t)first * b->win_cap;
+      if (b->ray_cap > KNN_SMEM_CAP) { u.big_pts += (size_t)first * b->ray_cap * 4; u.big_i += (size_t)first * b->ray_cap * 2; }
       cudaStream_t sg = c->streams[g];
       CK(cudaStreamWaitEvent(sg, c->fork, 0));
       if (chunk_copies)

@@ -84,7 +84,7 @@ class BatchResult:
 
 
 class Engine:
-    def __init__(self, device=None, table_cap=4096, win_cap=DEFAULT_WIN_CAP, chunks=4):
+    def __init__(self, device=None, table_cap=4100, win_cap=DEFAULT_WIN_CAP, chunks=4):
         if not torch.cuda.is_available():
             raise PwbNoDeviceError("pywindow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = _lib.load()
@@ -146,8 +146,6 @@ class Engine:
             b.ray_cap = 0
             _lib.check(self.lib.pwb_ray_capacity(self._ctx, ctypes.byref(b), stream, ctypes.byref(cap)))
             ray_cap = max(64, (cap.value + 63) // 64 * 64)
-        if ray_cap > self.table_cap - 1:
-            raise ValueError(f"ray capacity {ray_cap} exceeds the engine's table_cap {self.table_cap}")
         b.ray_cap = int(ray_cap)
         return b, stream, F, total
 

@@ -175,3 +175,33 @@ def test_batch_vs_single_and_shared_types(eng, goldens):
         np.testing.assert_array_equal(a[i], b)
     c = eng.analyse_molecules([(el, x) for x in X]).host_records()
     np.testing.assert_array_equal(a, c)
+
+
+BIG = golden_names(("big_",))
+
+
+@pytest.mark.parametrize("name", BIG)
+def test_dense_ray_sampling(eng, name):
+    """BASELINE config 5: find_windows / find_average_diameter with adjust >> 1 (7e3 and 1e5 rays),
+    teacher-forced with the reference's pore centre: ray count, clear-ray mask, eps, DBSCAN labels,
+    window count exact; diameters 1e-3 A."""
+    from pywindow_b200 import _lib as L
+    from pywindow_b200.engine import record_windows
+    g = load_golden(name)
+    adj = float(g["adjust"])
+    res = eng.analyse_molecules([(g["elements"], g["coords"])], centre_override=g["fw_centre"][None], adjust=adj)
+    rec = res.host_records()[0]
+    P = g["ray_clear"].shape[0]
+    assert int(rec[L.REC_NRAYS]) == P
+    S = int(rec[L.REC_NCLEAR])
+    want = np.nonzero(g["ray_clear"])[0]
+    assert S == len(want)
+    assert (res.clear_k.cpu().numpy()[0, :S] == want).all()
+    np.testing.assert_allclose(res.clear_a2.cpu().numpy()[0, :S], g["ray_records"][:, 1], atol=1e-9)
+    assert abs(rec[L.REC_EPS] - float(g["eps"])) < 1e-9
+    assert (res.labels.cpu().numpy()[0, :S] == g["labels"]).all()
+    assert abs(rec[L.REC_AVGD] - float(g["avg_diameter"])) < 1e-9
+    w = record_windows(rec, warn=False)
+    assert w is not None and w[0].shape == g["windows_diam"].shape
+    np.testing.assert_allclose(w[0], g["windows_diam"], atol=1e-3)
+    np.testing.assert_allclose(w[1], g["windows_com"], atol=5e-3)
