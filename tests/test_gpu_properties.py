@@ -1,0 +1,74 @@
+"""Size-independent properties at the benchmark's full size (10 000 synthetic CC3 MD frames):
+the answers must not depend on how frames are batched, ordered, pipelined or translated."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+F = 10000
+
+
+@pytest.fixture(scope="module")
+def data():
+    from pywindow_b200 import synthetic
+    from pywindow_b200.engine import Engine
+    seeds = np.stack([load_golden(f"md_frame{i:02d}")["coords"] for i in range(20)])
+    el = load_golden("md_frame00")["elements"]
+    X = synthetic.noisy_frames(seeds, 0, F)
+    eng = Engine(0)
+    base = eng.analyse_frames(X, el).host_records()
+    return eng, el, X, base
+
+
+def test_every_frame_has_four_windows(data):
+    from pywindow_b200 import _lib as L
+    _, _, _, base = data
+    assert (base[:, L.REC_STATUS] == 0).all()
+    assert (base[:, L.REC_NWIN] == 4).all()                       # north_star: identical window counts
+    w = base[:, L.REC_WIN0:L.REC_WIN0 + 16].reshape(-1, 4, 4)[:, :, 0]
+    assert np.isfinite(w).all() and (w > 2.0).all() and (w < 5.5).all()
+    assert (base[:, L.REC_OPT_D] >= base[:, L.REC_PORE_D] - 1e-9).all()   # optimising never shrinks the pore
+    assert (base[:, L.REC_AVGD] < base[:, L.REC_MAXD]).all()
+
+
+def test_independent_of_batching_order_and_pipelining(data):
+    eng, el, X, base = data
+    perm = np.random.default_rng(0).permutation(F)
+    shuffled = eng.analyse_frames(X[perm], el).host_records()
+    np.testing.assert_array_equal(shuffled, base[perm])            # bit exact
+    eng.set_chunks(1)
+    try:
+        seq = eng.analyse_frames(X, el).host_records()
+    finally:
+        eng.set_chunks(4)
+    np.testing.assert_array_equal(seq, base)
+    parts = np.concatenate([eng.analyse_frames(X[s:s + 1237], el).host_records() for s in range(0, F, 1237)])
+    np.testing.assert_array_equal(parts, base)
+
+
+def test_host_entry_point_equals_device_path_at_full_size(data):
+    eng, el, X, base = data
+    h = eng.analyse_frames_host(X, el, ray_cap=1152).numpy()
+    np.testing.assert_array_equal(h, base)
+
+
+def test_translation_covariance_with_forced_centres(data):
+    """Shift every frame by a constant vector, force the (shifted) pore centres: diameters unchanged,
+    centres shifted; window count exact."""
+    from pywindow_b200 import _lib as L
+    eng, el, X, base = data
+    n = 2000
+    t = np.array([3.25, -1.5, 7.125])
+    c0 = base[:n, L.REC_OPT_C:L.REC_OPT_C + 3]
+    a = eng.analyse_frames(X[:n], el, centre_override=c0).host_records()
+    b = eng.analyse_frames(X[:n] + t, el, centre_override=c0 + t).host_records()
+    assert (a[:, L.REC_NWIN] == b[:, L.REC_NWIN]).all()
+    np.testing.assert_allclose(b[:, L.REC_COM:L.REC_COM + 3], a[:, L.REC_COM:L.REC_COM + 3] + t, atol=1e-9)
+    for col in (L.REC_MAXD, L.REC_PORE_D, L.REC_OPT_D, L.REC_AVGD):
+        np.testing.assert_allclose(b[:, col], a[:, col], atol=1e-8)
+    wa = a[:, L.REC_WIN0:L.REC_WIN0 + 16].reshape(-1, 4, 4)
+    wb = b[:, L.REC_WIN0:L.REC_WIN0 + 16].reshape(-1, 4, 4)
+    d = np.abs(wa[:, :, 0] - wb[:, :, 0])
+    assert np.quantile(d, 0.999) < 1e-3 and (d < 5e-2).all()       # window stage is well conditioned
+    assert (np.abs(wb[:, :, 1:] - wa[:, :, 1:] - t) < 0.2).all()
