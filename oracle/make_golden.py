@@ -88,6 +88,10 @@ def analyse(pw, util, elements, coords, name, windows=True, scalars=True, avg=Tr
             out["has_windows"] = np.array(True)
             out["windows_diam"] = np.asarray(res[0], dtype=np.float64)
             out["windows_com"] = np.asarray(res[1], dtype=np.float64).reshape(-1, 3)
+    if adjust != 1 and "ray_records" in out:          # dense ray sets: keep the fixtures small
+        out["ray_a2"] = out["ray_records"][:, 1].copy()
+        for k in ("ray_records", "ray_points", "fw_shifted", "win_rescan_vector"):
+            out.pop(k, None)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     nw = out.get("windows_diam", np.zeros(0)).shape[0]
     print(f"{name}: N={len(elements)} windows={nw}", flush=True)

@@ -197,7 +197,7 @@ def test_dense_ray_sampling(eng, name):
     want = np.nonzero(g["ray_clear"])[0]
     assert S == len(want)
     assert (res.clear_k.cpu().numpy()[0, :S] == want).all()
-    np.testing.assert_allclose(res.clear_a2.cpu().numpy()[0, :S], g["ray_records"][:, 1], atol=1e-9)
+    np.testing.assert_allclose(res.clear_a2.cpu().numpy()[0, :S], g["ray_a2"], atol=1e-9)
     assert abs(rec[L.REC_EPS] - float(g["eps"])) < 1e-9
     assert (res.labels.cpu().numpy()[0, :S] == g["labels"]).all()
     assert abs(rec[L.REC_AVGD] - float(g["avg_diameter"])) < 1e-9
