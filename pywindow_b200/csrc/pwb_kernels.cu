@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(OPT_WARPS * 32, 8)
 k_opt_pore(pwb_batch b, Ws ws) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int item = blockIdx.x * OPT_WARPS + w;
+  const int item = blockIdx.x * (blockDim.x >> 5) + w;      // warps per CTA chosen at launch (<= OPT_WARPS)
   if (item >= b.n_items) return;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(WIN_WARPS * 32, 7)
 k_windows(pwb_batch b, Ws ws) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int gw = blockIdx.x * WIN_WARPS + w;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + w;        // warps per CTA chosen at launch (<= WIN_WARPS)
   const int item = gw / b.win_cap, win = gw - item * b.win_cap;
   if (item >= b.n_items) return;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
@@ -1304,9 +1304,13 @@ static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 4 + 2 * LB_M * 3) * OPT_WARPS;
+  // fewer warps per CTA for very large molecules so the per-warp atom tiles still fit shared memory
+  const size_t per_warp = sizeof(double) * ((size_t)b->max_atoms * 4 + 2 * LB_M * 3);
+  int wpb = OPT_WARPS;
+  while (wpb > 1 && per_warp * wpb > (size_t)c->max_smem) wpb >>= 1;
+  size_t sm = per_warp * wpb;
   if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
-  k_opt_pore<<<(b->n_items + OPT_WARPS - 1) / OPT_WARPS, OPT_WARPS * 32, sm, s>>>(*b, w);
+  k_opt_pore<<<(b->n_items + wpb - 1) / wpb, wpb * 32, sm, s>>>(*b, w);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1342,10 +1346,13 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4 + 2 * LB_M) * WIN_WARPS + 64;
+  const size_t per_warp = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4 + 2 * LB_M);
+  int wpb = WIN_WARPS;
+  while (wpb > 1 && per_warp * wpb + 64 > (size_t)c->max_smem) wpb >>= 1;
+  size_t sm = per_warp * wpb + 64;
   if (set_smem(k_windows, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
-  k_windows<<<(unsigned)((warps + WIN_WARPS - 1) / WIN_WARPS), WIN_WARPS * 32, sm, s>>>(*b, w);
+  k_windows<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, sm, s>>>(*b, w);
   k_finish<<<(b->n_items + 255) / 256, 256, 0, s>>>(*b, w);
   c->c.launches += 2;
   CK(cudaGetLastError());

@@ -153,6 +153,10 @@ class Engine:
                 centre_override=None, stages=_lib.STAGE_ALL, adjust=1.0, increment=1.0, increment2=0.1,
                 pore_opt=True, ray_cap=None):
         """Run the stages on a batch whose inputs are (or are moved to) device tensors."""
+        if int(item_off.shape[0] if hasattr(item_off, "shape") else len(item_off)) <= 1:      # empty batch
+            empty = torch.zeros((0, self.rec_stride), dtype=torch.float64, device=self.device)
+            return BatchResult(empty, torch.zeros(0, dtype=torch.uint8, device=self.device), _lib.WsLayout(), 0, 0,
+                               int(ray_cap or 64), self.win_cap)
         with torch.cuda.device(self.device):
             coords = self._dev(coords, torch.float64).view(-1, 3)
             item_off = self._dev(item_off, torch.int32)

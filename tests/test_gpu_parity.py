@@ -205,3 +205,31 @@ def test_dense_ray_sampling(eng, name):
     assert w is not None and w[0].shape == g["windows_diam"].shape
     np.testing.assert_allclose(w[0], g["windows_diam"], atol=1e-3)
     np.testing.assert_allclose(w[1], g["windows_com"], atol=5e-3)
+
+
+def test_edge_cases(eng):
+    """Empty batch, a large synthetic shell (1 800 atoms: reduced warps per CTA), tiny molecules."""
+    from pywindow_b200 import _lib as L
+    import pw_oracle as O
+    g = load_golden("md_frame00")
+    assert eng.analyse_frames(np.zeros((0, 168, 3)), g["elements"]).host_records().shape[0] == 0
+    rng = np.random.default_rng(5)
+    n = 1800
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    X = u * rng.uniform(14.0, 16.0, size=(n, 1))
+    keep = (np.abs(u[:, 2]) < 0.93)                       # two polar openings
+    X = X[keep]
+    el = np.array(["C", "H", "N", "O"])[rng.integers(0, 4, size=X.shape[0])]
+    rec = eng.analyse_molecules([(el, X)]).host_records()[0]
+    r, m = O.vdw_of(el), O.masses_of(el)
+    assert abs(rec[L.REC_MAXD] - O.max_dim(r, X)[2]) < 1e-9
+    assert abs(rec[L.REC_AVGD] - O.find_average_diameter(r, m, X)) < 1e-9
+    w = O.find_windows(r, m, X, centre=rec[L.REC_OPT_C:L.REC_OPT_C + 3])
+    nw = 0 if w is None else len(w[0])
+    assert int(rec[L.REC_NWIN]) == nw and nw >= 2
+    got = np.sort(rec[L.REC_WIN0:L.REC_WIN0 + 4 * nw].reshape(nw, 4)[:, 0])
+    np.testing.assert_allclose(got, np.sort(w[0]), atol=1e-3)
+    # water-sized molecule: no cavity, COM inside an atom -> inverted optimiser bounds flag, no crash
+    tiny = eng.analyse_molecules([(np.array(["O", "H", "H"]), np.array([[0, 0, 0.0], [0.96, 0, 0], [-0.24, 0.93, 0]]))])
+    assert int(tiny.host_records()[0][L.REC_STATUS]) & L.ST_OPT_BOUNDS
