@@ -178,6 +178,13 @@ int pwb_discrete_molecules(int n_frames, int n_atoms, int rebuild, double tol, d
                            int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 void pwb_set_error(const char* msg);
 
+/* ---- host side: DL_POLY HISTORY text -> [F][N][3] float64 (replaces the per-frame Python decode of
+ * trajectory.py:217-249, :647-689, :712-766).  HOST pointers; multi-threaded; numbers are converted
+ * exactly like Python's float().                                                                    */
+int64_t pwb_history_index(const char* buf, int64_t len, int64_t* starts, int64_t cap);
+int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
+                           int natoms, int keytrj, int imcon, double* xyz, double* lattice, int threads);
+
 /* Measurement utility: sustained FMA throughput of the FP32 (fp64 = 0) or FP64 (fp64 = 1) pipe in
  * TFLOP/s, timed with CUDA events (the roofline denominator of this compute-bound path).          */
 int pwb_fma_peak(pwb_ctx*, int fp64, void* stream, double* tflops);

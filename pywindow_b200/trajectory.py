@@ -58,6 +58,65 @@ def make_supercell(system, matrix, supercell=(1, 1, 1)):
     return MolecularSystem.load_system(out)
 
 
+class LazyFrame(dict):
+    """``{molecule_key: properties}`` of one analysed frame, built from the GPU result records on first
+    access.  ``analysis_output`` stays a plain ``dict`` of these, so a 100 000-frame analysis does not
+    pay for 100 000 Python property dictionaries nobody looks at (trajectory.py:483, :516-522 build
+    them eagerly)."""
+
+    __slots__ = ("_pending",)
+
+    def __init__(self, pending=()):
+        super().__init__()
+        self._pending = list(pending)
+
+    def _add(self, mol_key, rec):
+        self._pending.append((mol_key, rec))
+
+    def _load(self):
+        if self._pending:
+            pend, self._pending = self._pending, []
+            for k, rec in pend:
+                super().__setitem__(k, record_to_properties(rec))
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._load(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._load())
+
+    def __len__(self):
+        return dict.__len__(self) + len(self._pending)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or any(p[0] == k for p in self._pending)
+
+    def __eq__(self, other):
+        return dict.__eq__(self._load(), other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __repr__(self):
+        return dict.__repr__(self._load())
+
+    def keys(self):
+        return dict.keys(self._load())
+
+    def values(self):
+        return dict.values(self._load())
+
+    def items(self):
+        return dict.items(self._load())
+
+    def get(self, k, default=None):
+        return dict.get(self._load(), k, default)
+
+    def copy(self):
+        return dict(self._load())
+
+
 class Trajectory:
     """Shared machinery: frame selection, batched GPU analysis, result storage."""
 
@@ -141,8 +200,12 @@ class Trajectory:
             records, keys = self._analyse_single(mine, swap_atoms, forcefield, gpu_kwargs)
         if size > 1:
             records, keys = gather_records(records, keys)
+        out = self.analysis_output
         for (frame, mol_key), rec in zip(keys, records):
-            self.analysis_output.setdefault(frame, {})[mol_key] = record_to_properties(rec)
+            fr = out.get(frame)
+            if not isinstance(fr, LazyFrame):
+                fr = out[frame] = LazyFrame()
+            fr._add(mol_key, rec)
 
     def _elements_of(self, frame, swap_atoms, forcefield):
         ms = self._get_frame(self.trajectory_map[frame], frame, swap_atoms=swap_atoms, forcefield=forcefield)
@@ -225,7 +288,7 @@ class Trajectory:
         filepath = pathlib.Path(filepath)
         if filepath.suffix != ".json":
             filepath = pathlib.Path(str(filepath) + ".json")
-        out = {str(f): {str(k): v for k, v in mols.items()} for f, mols in self.analysis_output.items()}
+        out = {str(f): {str(k): v for k, v in dict(mols.items()).items()} for f, mols in self.analysis_output.items()}
         with filepath.open("w") as fh:
             json.dump(out, fh, default=U.to_list, **kwargs)
 
@@ -253,22 +316,60 @@ class DLPOLY(Trajectory):
         self._map_history()
 
     def _map_history(self):
+        lib = _lib.load()
         with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            starts = [m.start() for m in re.finditer(rb"^timestep", mm, flags=re.MULTILINE)]
             size = len(mm)
+            buf = np.frombuffer(mm, dtype=np.uint8)
+            cap = max(1024, size // 2048)
+            while True:
+                starts = np.empty(cap, dtype=np.int64)
+                n = int(lib.pwb_history_index(buf.ctypes.data, size, starts.ctypes.data, cap))
+                if n <= cap:
+                    break
+                cap = n
+            starts = starts[:n].tolist()
             if not starts:
                 raise _TrajectoryError("no 'timestep' record found: not a DL_POLY HISTORY file")
-            head = mm[:starts[0]].decode("utf-8").split("\n")
+            head = bytes(mm[:starts[0]]).decode("utf-8").split("\n")
+            first = bytes(mm[starts[0]:mm.find(b"\n", starts[0])]).split()
+            del buf
         header = [int(i) for i in head[1].split()]
         self.trajectory_map = {"header": header}
         self.content_type = self._keytrj[header[0]]
         self.periodic_boundary = self._imcon[header[1]]
         self.no_of_atoms = header[2]
+        self._frame_keytrj, self._frame_imcon = int(first[3]), int(first[4])
         bounds = starts + [size]
         for k in range(len(starts)):
             self.trajectory_map[k] = [bounds[k], bounds[k + 1]]
         self.no_of_frames = len(starts)
         self.check_log = ""
+
+    def _native_decode(self, frames, want_lattice):
+        """[F,N,3] (and [F,3,3] lattices) through the multi-threaded C++ decoder (pwb_history_decode)."""
+        lib = _lib.load()
+        n, N = len(frames), self.no_of_atoms
+        starts = np.array([self.trajectory_map[f][0] for f in frames], dtype=np.int64)
+        ends = np.array([self.trajectory_map[f][1] for f in frames], dtype=np.int64)
+        xyz = np.empty((n, N, 3), dtype=np.float64)
+        periodic = self._frame_imcon in (1, 2, 3)
+        lat = np.empty((n, 3, 3), dtype=np.float64) if (want_lattice and periodic) else None
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            buf = np.frombuffer(mm, dtype=np.uint8)
+            bad = int(lib.pwb_history_decode(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, N,
+                                             self._frame_keytrj, self._frame_imcon, xyz.ctypes.data,
+                                             lat.ctypes.data if lat is not None else None, 0))
+            del buf
+        if bad:
+            raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {N} atoms, keytrj "
+                                   f"{self._frame_keytrj}, imcon {self._frame_imcon})")
+        return xyz, lat
+
+    def _decode_coordinates(self, frames):
+        return self._native_decode(frames, False)[0]
+
+    def _decode_cells(self, frames):
+        return self._native_decode(frames, True)
 
     def _layout(self, lines):
         info = lines[0].split()

@@ -124,3 +124,34 @@ def test_atom_key_deciphering_and_comparator():
     assert U.compare_properties_dict(a, b) == (False, "pore_diameter.atom")
     lat = U.unit_cell_to_lattice_array([10, 11, 12, 80, 95, 100])
     np.testing.assert_allclose(U.lattice_array_to_unit_cell(lat), [10, 11, 12, 80, 95, 100])
+
+
+def test_native_history_decoder_is_bit_exact(tmp_path):
+    """pwb_history_decode (C++, threaded) against the Python per-frame decoder on awkward number
+    formats, velocities/forces records (keytrj 2) and a lattice block (imcon 3)."""
+    from pywindow_b200.trajectory import DLPOLY
+    rng = np.random.default_rng(3)
+    n, F = 37, 11
+    fmts = ["%.17E", "%12.4E", "%20.10f", "%.3f", "%.17g", "%25.16e"]
+    path = tmp_path / "HISTORY"
+    X = rng.normal(0, 30, size=(F, n, 3)) * 10.0 ** rng.integers(-12, 6, size=(F, n, 1))
+    lat = rng.normal(0, 20, size=(F, 3, 3))
+    with open(path, "w") as fh:
+        fh.write("title\n         2         3        %d\n" % n)
+        for f in range(F):
+            fh.write("timestep %d %d 2 3 0.001\n" % (f + 1, n))
+            for r in range(3):
+                fh.write(" ".join(fmts[(f + r) % len(fmts)] % v for v in lat[f, r]) + "\n")
+            for a in range(n):
+                fh.write("C%d   %d  12.011  0.1\n" % (a % 7, a + 1))
+                fh.write("  ".join(fmts[(f + a) % len(fmts)] % v for v in X[f, a]) + "\n")
+                fh.write("1.0 2.0 3.0\n4.0 5.0 6.0\n")
+    t = DLPOLY(path)
+    assert t.no_of_frames == F and t._frame_keytrj == 2 and t._frame_imcon == 3
+    xyz, lattice = t._decode_cells(list(range(F)))
+    for f in range(F):
+        fr = t._decode_frame(t._frame_bytes(f))                 # Python reference decode (float())
+        np.testing.assert_array_equal(xyz[f], fr["coordinates"])
+        np.testing.assert_array_equal(lattice[f], fr["lattice"])
+        assert fr["velocities"].shape == (n, 3) and fr["forces"].shape == (n, 3)
+    np.testing.assert_array_equal(t._decode_coordinates([3, 0]), xyz[[3, 0]])
