@@ -218,6 +218,77 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
   for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);
 }
 
+// ---- direction grid: which atoms can a ray from the centroid hit at all? ---------------------------
+// The pre-test of find_windows and the average-diameter sampling both ask, for ~1e3 rays from the
+// centroid o, which of the N vdW spheres the ray's LINE intersects.  Sphere i subtends a cap of angular
+// radius asin(r_i/|L_i|) around +-L_i/|L_i| (L_i = x_i - o); caps are rasterised (conservatively: bounding
+// box in z = cos(theta) and phi, plus 1e-7 rad) into a 16 x 32 grid of direction bins, so a ray only
+// tests the handful of atoms listed in its bin.  The tests themselves are unchanged (exact, FP64).
+constexpr int DG_NZ = 16, DG_NPHI = 32, DG_BINS = DG_NZ * DG_NPHI, DG_CAP = 24;
+constexpr double DG_PI = 3.141592653589793;
+
+struct DirGrid { unsigned short* list; int* cnt; int* overflow; };   // list[DG_BINS][DG_CAP], cnt[DG_BINS]
+
+__device__ __forceinline__ int dg_bin(double nx, double ny, double nz) {
+  int iz = (int)floor((nz + 1.0) * (DG_NZ * 0.5));
+  iz = iz < 0 ? 0 : (iz >= DG_NZ ? DG_NZ - 1 : iz);
+  int ip = (int)floor((atan2(ny, nx) + DG_PI) * (DG_NPHI / (2.0 * DG_PI)));
+  ip = ip < 0 ? 0 : (ip >= DG_NPHI ? DG_NPHI - 1 : ip);
+  return iz * DG_NPHI + ip;
+}
+
+__device__ __forceinline__ void dg_push(const DirGrid& G, int bin, int a) {
+  const int pos = atomicAdd(&G.cnt[bin], 1);
+  if (pos < DG_CAP) G.list[bin * DG_CAP + pos] = (unsigned short)a; else *G.overflow = 1;
+}
+
+__device__ __forceinline__ void dg_insert_cap(const DirGrid& G, int a, double ux, double uy, double uz, double alpha) {
+  const double tc = acos(fmin(1.0, fmax(-1.0, uz)));
+  const double tlo = tc - alpha, thi = tc + alpha;
+  const double zhi = tlo <= 0.0 ? 1.0 : cos(tlo), zlo = thi >= DG_PI ? -1.0 : cos(thi);
+  int iz0 = (int)floor((zlo + 1.0) * (DG_NZ * 0.5) - 1e-9), iz1 = (int)floor((zhi + 1.0) * (DG_NZ * 0.5) + 1e-9);
+  iz0 = iz0 < 0 ? 0 : iz0; iz1 = iz1 >= DG_NZ ? DG_NZ - 1 : iz1;
+  bool full = tlo <= 0.0 || thi >= DG_PI;
+  int ip0 = 0, ip1 = DG_NPHI - 1;
+  if (!full) {
+    const double sr = sin(alpha) / sin(tc);
+    if (sr >= 1.0) full = true;
+    else {
+      const double dphi = asin(sr) + 1e-7, pc = atan2(uy, ux) + DG_PI;
+      ip0 = (int)floor((pc - dphi) * (DG_NPHI / (2.0 * DG_PI)));
+      ip1 = (int)floor((pc + dphi) * (DG_NPHI / (2.0 * DG_PI)));
+      if (ip1 - ip0 + 1 >= DG_NPHI) full = true;
+    }
+  }
+  if (full) { ip0 = 0; ip1 = DG_NPHI - 1; }
+  for (int iz = iz0; iz <= iz1; iz++)
+    for (int ip = ip0; ip <= ip1; ip++) dg_push(G, iz * DG_NPHI + ((ip % DG_NPHI) + DG_NPHI) % DG_NPHI, a);
+}
+
+// block-wide build from centroid-relative positions L and radii r (one thread per atom); `onorm` = |o|,
+// the distance of the centroid from the origin the forward test (x.n > 0) refers to
+__device__ __forceinline__ void dg_build(const DirGrid& G, const double* Lx, const double* Ly, const double* Lz,
+                                         const double* r, int n, double onorm) {
+  for (int c = threadIdx.x; c < DG_BINS; c += blockDim.x) G.cnt[c] = 0;
+  if (threadIdx.x == 0) *G.overflow = (n > 65535) ? 1 : 0;
+  __syncthreads();
+  for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    const double x = Lx[a], y = Ly[a], z = Lz[a], ra = r[a];
+    const double L = sqrt(x * x + y * y + z * z);
+    if (L <= ra * (1.0 + 1e-9) + 1e-12) {               // the centroid lies inside this sphere: every ray hits it
+      for (int c = 0; c < DG_BINS; c++) dg_push(G, c, a);
+      continue;
+    }
+    const double alpha = asin(fmin(1.0, ra / L)) + 1e-7;
+    const double il = 1.0 / L;
+    dg_insert_cap(G, a, x * il, y * il, z * il, alpha);
+    // the line also meets the sphere on the far side of o; that only counts if x.n > 0 can still hold,
+    // i.e. for atoms closer to the centroid than the centroid is to the origin
+    if (L - ra <= onorm + 1e-9) dg_insert_cap(G, a, -x * il, -y * il, -z * il, alpha);
+  }
+  __syncthreads();
+}
+
 // ---- near lists: exact pruning for repeated evaluations around one point -------------------------
 // a(p) = min_i(|x_i - p| - r_i) is 1-Lipschitz, so for |p - c| <= rho:  a(p) <= a(c) + rho, while atom i
 // contributes at least |x_i - c| - rho - r_i.  Atoms with |x_i - c| - r_i > a(c) + 2 rho can therefore

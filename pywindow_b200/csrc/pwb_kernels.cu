@@ -72,6 +72,10 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   int* redi = (int*)(red + 64);     // 64 ints
   int* stype = redi + 64;           // [NA]
   int* cnt = stype + NA;            // [PWB_MAX_TYPES + 1]
+  DirGrid DG;
+  DG.cnt = cnt + PWB_MAX_TYPES + 1;                      // [DG_BINS]
+  DG.overflow = DG.cnt + DG_BINS;                        // [1] (+1 pad)
+  DG.list = (unsigned short*)(DG.overflow + 2);          // [DG_BINS][DG_CAP]
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
   for (int c = tid; c <= PWB_MAX_TYPES; c += nt) cnt[c] = 0;
@@ -203,7 +207,28 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   __syncthreads();
   const int P = n_sampling_points(D, b.adjust);
   const double oo = ox * ox + oy * oy + oz * oz;
+  dg_build(DG, sx, sy, sz, sr, n, sqrt(oo));
+  const bool use_grid = *DG.overflow == 0;
   double acc = 0, hits = 0;
+  if (use_grid) {
+    for (int k = tid; k < P; k += nt) {
+      double px, py, pz;
+      spiral_point(k, P, D, px, py, pz);
+      const double nr = sqrt(px * px + py * py + pz * pz);
+      const double nx = px / nr, ny = py / nr, nz = pz / nr;
+      const double on = -(ox * nx + oy * ny + oz * nz);
+      const int bin = dg_bin(nx, ny, nz), m = DG.cnt[bin];
+      const unsigned short* lst = DG.list + bin * DG_CAP;
+      double sb = -PWB_INF;
+      for (int e = 0; e < m; e++) {
+        const int a = lst[e];
+        const double t = fma(sx[a], nx, fma(sy[a], ny, sz[a] * nz));
+        const double under = fma(t, t, sw[a]);
+        if (under > 0.0 && t > on && t + sr[a] > sb) sb = rare_exit_param(t, under, sb);
+      }
+      if (sb > -PWB_INF) { acc += sqrt(fma(sb, sb, fma(-2.0 * sb, on, oo))); hits += 1.0; }   // |o + s n|, o.n = -on
+    }
+  } else {
   constexpr int RPT = 4;
   for (int k0 = tid * RPT; k0 < P; k0 += nt * RPT) {
     double nx[RPT], ny[RPT], nz[RPT], on[RPT], sb[RPT];
@@ -233,6 +258,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
         hits += 1.0;
       }
     }
+  }
   }
   acc = block_sum(acc, red); hits = block_sum(hits, red);
   if (tid == 0) rec[PWB_REC_AVGD] = 2.0 * (acc / hits);
@@ -1296,7 +1322,8 @@ static int check(const pwb_batch* b) {
 }
 
 static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s, int do_avg) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + 64) + sizeof(int) * (64 + b->max_atoms + PWB_MAX_TYPES + 1);
+  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + 64) + sizeof(int) * (64 + b->max_atoms + PWB_MAX_TYPES + 1 + DG_BINS + 2) +
+              sizeof(unsigned short) * DG_BINS * DG_CAP;
   if (set_smem(k_prepare, sm, c->max_smem)) return 1;
   k_prepare<<<b->n_items, PREP_THREADS, sm, s>>>(*b, w, do_avg);
   c->c.launches++;
