@@ -383,6 +383,10 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   int* wsum = cls + PWB_MAX_TYPES + 1;      // [32]
   int* surv = wsum + 32;                    // [RAY_TILE] ray index of survivors in this tile
   int* spos = surv + RAY_TILE;              // [RAY_TILE] arg-min path step (or -1)
+  DirGrid DG;
+  DG.cnt = spos + RAY_TILE;                 // [DG_BINS]
+  DG.overflow = DG.cnt + DG_BINS;           // [1] (+1 pad)
+  DG.list = (unsigned short*)(DG.overflow + 2);   // [DG_BINS][DG_CAP]
 
   // shift exactly as find_windows does (utilities.py:1379-1393)
   const double cmx = idv[D_COM], cmy = idv[D_COM + 1], cmz = idv[D_COM + 2];
@@ -405,11 +409,29 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
   for (int a = tid; a < n; a += nt) {
     double x = ax[a] - ox, y = ay[a] - oy, z = az[a] - oz;
-    lx[a] = x; ly[a] = y; lz[a] = z; lw[a] = lw[a] - (x * x + y * y + z * z);   // r^2 - |L|^2
+    lx[a] = x; ly[a] = y; lz[a] = z;
+  }
+  __syncthreads();
+  // direction grid over the centroid-relative atoms (radii are still in lw as r^2 here)
+  for (int c = tid; c < DG_BINS; c += nt) DG.cnt[c] = 0;
+  if (tid == 0) *DG.overflow = (n > 65535) ? 1 : 0;
+  __syncthreads();
+  {
+    const double onorm = sqrt(ox * ox + oy * oy + oz * oz);
+    for (int a = tid; a < n; a += nt) {
+      const double x = lx[a], y = ly[a], z = lz[a], ra = sqrt(lw[a]);
+      const double L2 = x * x + y * y + z * z, L = sqrt(L2);
+      lw[a] = lw[a] - L2;                                                       // r^2 - |L|^2
+      if (L <= ra * (1.0 + 1e-9) + 1e-12) { for (int c = 0; c < DG_BINS; c++) dg_push(DG, c, a); continue; }
+      const double alpha = asin(fmin(1.0, ra / L)) + 1e-7, il = 1.0 / L;
+      dg_insert_cap(DG, a, x * il, y * il, z * il, alpha);
+      if (L - ra <= onorm + 1e-9) dg_insert_cap(DG, a, -x * il, -y * il, -z * il, alpha);
+    }
   }
   const double R = idv[D_MAXD] / 2.0;     // max_dim is translation invariant: reuse (utilities.py:1398)
   const int P = n_sampling_points(R, b.adjust);
   __syncthreads();
+  const bool use_grid = *DG.overflow == 0;
   if (tid == 0) {
     idv[D_RADIUS] = R; idv[D_ICOM] = icx; idv[D_ICOM + 1] = icy; idv[D_ICOM + 2] = icz;
     idv[D_SHIFT] = shx; idv[D_SHIFT + 1] = shy; idv[D_SHIFT + 2] = shz;
@@ -440,6 +462,22 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       on[u] = -(ox * nx[u] + oy * ny[u] + oz * nz[u]);
       blk[u] = k >= P;
     }
+    if (use_grid) {
+#pragma unroll
+      for (int u = 0; u < RAY_RPT; u++) {
+        if (blk[u]) continue;
+        const int bin = dg_bin(nx[u], ny[u], nz[u]), m = DG.cnt[bin];
+        const unsigned short* lst = DG.list + bin * DG_CAP;
+        int hit = 0;
+        for (int e = 0; e < m; e++) {
+          const int a = lst[e];
+          const double t = fma(lx[a], nx[u], fma(ly[a], ny[u], lz[a] * nz[u]));
+          const double under = fma(t, t, lw[a]);
+          hit |= (int)(under > 0.0) & (int)(t > on[u]);
+        }
+        blk[u] = hit;
+      }
+    } else {
 #pragma unroll 2
     for (int a = 0; a < n; a++) {
       const double Lx = lx[a], Ly = ly[a], Lz = lz[a], W = lw[a];
@@ -449,6 +487,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
         double under = fma(t, t, W);
         blk[u] |= (int)(under > 0.0) & (int)(t > on[u]);
       }
+    }
     }
     int cntm = 0;
 #pragma unroll
@@ -1344,7 +1383,7 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
 }
 static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
   size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_ACAP) +
-              sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE);
+              sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE + DG_BINS + 2) + sizeof(unsigned short) * DG_BINS * DG_CAP;
   if (set_smem(k_rays, sm, c->max_smem)) return 1;
   k_rays<<<b->n_items, RAY_THREADS, sm, s>>>(*b, w, c->c);
   c->c.launches++;
