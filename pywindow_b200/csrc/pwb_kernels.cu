@@ -916,10 +916,15 @@ __device__ __forceinline__ void uf_union_g(int* parent, int a, int b) {
   }
 }
 
-constexpr int CLB_THREADS = 512;
+// Windowed DBSCAN for one big item, split into phases so that the O(S * window) passes run on many
+// CTAs (grid = blocks x items); phases 3 and 6 are single-CTA ordered scans.
+//   0 count neighbours -> core flags   1 union core pairs   2 flatten   3 number the roots (ordered)
+//   4 labels of the other core points  5 border labels      6 arg-max ray per cluster
+constexpr int CLB_THREADS = 256;
 __global__ void __launch_bounds__(CLB_THREADS)
-k_cluster_big(pwb_batch b, Ws ws) {
-  const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+k_cluster_big(pwb_batch b, Ws ws, int phase) {
+  const int item = blockIdx.y, nt = blockDim.x * gridDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = threadIdx.x;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   if (iiv[I_DEFER] != 2 || (iiv[I_STATUS] & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS | PWB_ST_RAY_CAP))) return;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
@@ -930,23 +935,18 @@ k_cluster_big(pwb_batch b, Ws ws) {
   __shared__ int wsum[32];
   __shared__ unsigned long long cbest[64];
   __shared__ int cidx[64];
-  double munit;
-  if (P > KNN_SMEM_CAP) {
-    double t = 0;
-    for (int sl = 0; sl < BIG_SLICES; sl++) t += U[sl].w;   // fixed order: deterministic
-    munit = t / (10.0 * (double)P);
-  } else munit = 0.0;   // (items deferred only for their size have P <= KNN_SMEM_CAP: not routed here)
-  const double m = R * munit;
+  double t = 0;
+  for (int sl = 0; sl < BIG_SLICES; sl++) t += U[sl].w;     // fixed order: deterministic
+  const double m = R * (t / (10.0 * (double)P));
   const double eps = m + sqrt(m), eps2 = eps * eps;
-  if (tid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; }
+  if (phase == 0 && gtid == 0) { idv[D_EPS] = eps; rec[PWB_REC_EPS] = eps; rec[PWB_REC_NWIN] = 0; iiv[I_NWIN] = 0; }
   if (S == 0) return;
   const int Wk = (int)ceil((eps / R) * P * 0.5) + 2;
   const int* ck = ws.clear_k + (size_t)item * cap;
   const double* ca2 = ws.clear_a2 + (size_t)item * cap;
   int* parent = ws.big_i + (size_t)item * 2 * cap;
-  int* aux = parent + cap;                    // core flag, later the border label
+  int* aux = parent + cap;                    // core flag
   int* label = ws.labels + (size_t)item * cap;
-  const double hR2 = 0.5 * R * R;             // |p|^2/2 for p = R u, |u| = 1 (to rounding)
   // window [jlo, jhi) of clear rays whose ray index is within Wk of ray i's (ck is ascending)
   auto window = [&](int i, int& jlo, int& jhi) {
     const int klo = ck[i] - Wk, khi = ck[i] + Wk;
@@ -962,68 +962,73 @@ k_cluster_big(pwb_batch b, Ws ws) {
     const double dx = R * ui.x - R * uj.x, dy = R * ui.y - R * uj.y, dz = R * ui.z - R * uj.z;
     return dx * dx + dy * dy + dz * dz <= eps2;
   };
-  (void)hR2;
-  for (int i = tid; i < S; i += nt) {
-    int jlo, jhi, c = 0;
-    window(i, jlo, jhi);
-    const double4 ui = U[ck[i]];
-    for (int j = jlo; j < jhi; j++) c += adjacent(ui, j);
-    aux[i] = c >= 5;
-    parent[i] = i;
-  }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    if (!aux[i]) continue;
-    int jlo, jhi;
-    window(i, jlo, jhi);
-    const double4 ui = U[ck[i]];
-    for (int j = jlo; j < i; j++)
-      if (aux[j] && adjacent(ui, j)) uf_union_g(parent, i, j);
-  }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) if (aux[i]) parent[i] = uf_find_halving(parent, i);
-  __syncthreads();
-  int nclus = 0;
-  for (int s0 = 0; s0 < S; s0 += nt) {
-    const int i = s0 + tid;
-    const int isroot = (i < S && aux[i] && parent[i] == i) ? 1 : 0;
-    int tot;
-    const int o = block_excl_scan(isroot, wsum, tot);
-    if (isroot) label[i] = nclus + o;
-    nclus += tot;
-  }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) if (aux[i] && parent[i] != i) label[i] = label[parent[i]];
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    if (aux[i]) continue;
-    int jlo, jhi, best = 0x7fffffff;
-    window(i, jlo, jhi);
-    const double4 ui = U[ck[i]];
-    for (int j = jlo; j < jhi; j++)
-      if (aux[j] && adjacent(ui, j)) best = min(best, label[j]);
-    parent[i] = best;
-  }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) if (!aux[i]) label[i] = (parent[i] == 0x7fffffff) ? -1 : parent[i];
-  const int W = min(nclus, min(b.win_cap, 64));
-  for (int c = tid; c < 64; c += nt) { cbest[c] = 0ull; cidx[c] = 0x7fffffff; }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    const int l = label[i];
-    if (l >= 0 && l < W) atomicMax(&cbest[l], (unsigned long long)__double_as_longlong(ca2[i]));
-  }
-  __syncthreads();
-  for (int i = tid; i < S; i += nt) {
-    const int l = label[i];
-    if (l >= 0 && l < W && (unsigned long long)__double_as_longlong(ca2[i]) == cbest[l]) atomicMin(&cidx[l], i);
-  }
-  __syncthreads();
-  int* wk = ws.win_k + (size_t)item * b.win_cap;
-  for (int c = tid; c < W; c += nt) wk[c] = ck[cidx[c]];
-  if (tid == 0) {
-    iiv[I_NWIN] = W; rec[PWB_REC_NWIN] = W;
-    if (nclus > W) { iiv[I_STATUS] |= PWB_ST_WIN_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+  if (phase == 0) {
+    for (int i = gtid; i < S; i += nt) {
+      int jlo, jhi, c = 0;
+      window(i, jlo, jhi);
+      const double4 ui = U[ck[i]];
+      for (int j = jlo; j < jhi; j++) c += adjacent(ui, j);
+      aux[i] = c >= 5;
+      parent[i] = i;
+    }
+  } else if (phase == 1) {
+    for (int i = gtid; i < S; i += nt) {
+      if (!aux[i]) continue;
+      int jlo, jhi;
+      window(i, jlo, jhi);
+      const double4 ui = U[ck[i]];
+      for (int j = jlo; j < i; j++)
+        if (aux[j] && adjacent(ui, j)) uf_union_g(parent, i, j);
+    }
+  } else if (phase == 2) {
+    for (int i = gtid; i < S; i += nt) if (aux[i]) parent[i] = uf_find_halving(parent, i);
+  } else if (phase == 3) {
+    if (blockIdx.x != 0) return;
+    int nclus = 0;
+    for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+      const int i = s0 + tid;
+      const int isroot = (i < S && aux[i] && parent[i] == i) ? 1 : 0;
+      int tot;
+      const int o = block_excl_scan(isroot, wsum, tot);
+      if (isroot) label[i] = nclus + o;
+      nclus += tot;
+    }
+    if (tid == 0) iiv[I_NWIN] = nclus;        // number of clusters (clamped to the window slots in phase 6)
+  } else if (phase == 4) {
+    // roots were final before phase 3 ran, so parent[i] is a root index here
+    for (int i = gtid; i < S; i += nt) if (aux[i] && parent[i] != i) label[i] = label[parent[i]];
+  } else if (phase == 5) {
+    for (int i = gtid; i < S; i += nt) {
+      if (aux[i]) continue;
+      int jlo, jhi, best = 0x7fffffff;
+      window(i, jlo, jhi);
+      const double4 ui = U[ck[i]];
+      for (int j = jlo; j < jhi; j++)
+        if (aux[j] && adjacent(ui, j)) best = min(best, label[j]);
+      label[i] = (best == 0x7fffffff) ? -1 : best;
+    }
+  } else {
+    if (blockIdx.x != 0) return;
+    const int nclus = iiv[I_NWIN];
+    const int W = min(nclus, min(b.win_cap, 64));
+    for (int c = tid; c < 64; c += blockDim.x) { cbest[c] = 0ull; cidx[c] = 0x7fffffff; }
+    __syncthreads();
+    for (int i = tid; i < S; i += blockDim.x) {
+      const int l = label[i];
+      if (l >= 0 && l < W) atomicMax(&cbest[l], (unsigned long long)__double_as_longlong(ca2[i]));
+    }
+    __syncthreads();
+    for (int i = tid; i < S; i += blockDim.x) {
+      const int l = label[i];
+      if (l >= 0 && l < W && (unsigned long long)__double_as_longlong(ca2[i]) == cbest[l]) atomicMin(&cidx[l], i);
+    }
+    __syncthreads();
+    int* wk = ws.win_k + (size_t)item * b.win_cap;
+    for (int c = tid; c < W; c += blockDim.x) wk[c] = ck[cidx[c]];
+    if (tid == 0) {
+      iiv[I_NWIN] = W; rec[PWB_REC_NWIN] = W;
+      if (nclus > W) { iiv[I_STATUS] |= PWB_ST_WIN_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+    }
   }
 }
 
@@ -1405,8 +1410,12 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   if (b->ray_cap > KNN_SMEM_CAP) {                 // items whose ray count exceeds the shared-memory paths
     k_big_points<<<dim3(64, b->n_items), 256, 0, s>>>(*b, w);
     k_knn_big<<<dim3(BIG_SLICES, b->n_items), 256, 0, s>>>(*b, w);
-    k_cluster_big<<<b->n_items, CLB_THREADS, 0, s>>>(*b, w);
-    c->c.launches += 3;
+    const int cb_blocks = (b->ray_cap + CLB_THREADS - 1) / CLB_THREADS;
+    for (int ph = 0; ph < 7; ph++) {
+      const int gx = (ph == 3 || ph == 6) ? 1 : cb_blocks;
+      k_cluster_big<<<dim3(gx, b->n_items), CLB_THREADS, 0, s>>>(*b, w, ph);
+    }
+    c->c.launches += 9;
   }
   CK(cudaGetLastError());
   return 0;
