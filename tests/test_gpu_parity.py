@@ -233,3 +233,36 @@ def test_edge_cases(eng):
     # water-sized molecule: no cavity, COM inside an atom -> inverted optimiser bounds flag, no crash
     tiny = eng.analyse_molecules([(np.array(["O", "H", "H"]), np.array([[0, 0, 0.0], [0.96, 0, 0], [-0.24, 0.93, 0]]))])
     assert int(tiny.host_records()[0][L.REC_STATUS]) & L.ST_OPT_BOUNDS
+
+
+def test_seeded_synthetic_frames_against_oracle(eng):
+    """The bench workload itself (seeded noisy CC3 MD frames) on the GPU vs the CPU oracle: every
+    deterministic field to 1e-9, window count exact, window diameters 1e-3 A with the oracle started
+    from the GPU's pore centre (the only chaotic quantity, compared separately)."""
+    import pw_oracle as O
+    from pywindow_b200 import _lib as L, synthetic
+    from pywindow_b200.engine import record_windows
+    seeds = np.stack([load_golden(f"md_frame{i:02d}")["coords"] for i in range(20)])
+    el = load_golden("md_frame00")["elements"]
+    X = synthetic.noisy_frames(seeds, 1000, 24)
+    rec = eng.analyse_frames(X, el).host_records()
+    r, m = O.vdw_of(el), O.masses_of(el)
+    near = 0
+    for f in range(X.shape[0]):
+        com = O.center_of_mass(m, X[f])
+        np.testing.assert_allclose(rec[f, L.REC_COM:L.REC_COM + 3], com, atol=1e-9)
+        i1, i2, D = O.max_dim(r, X[f])
+        assert abs(rec[f, L.REC_MAXD] - D) < 1e-9 and (int(rec[f, L.REC_MAXD_A1]), int(rec[f, L.REC_MAXD_A2])) == (i1, i2)
+        pd_, pa = O.pore_diameter(r, X[f], com)
+        assert abs(rec[f, L.REC_PORE_D] - pd_) < 1e-9 and int(rec[f, L.REC_PORE_ATOM]) == pa
+        assert abs(rec[f, L.REC_AVGD] - O.find_average_diameter(r, m, X[f])) < 1e-9
+        c = rec[f, L.REC_OPT_C:L.REC_OPT_C + 3]
+        od, oa = O.pore_diameter(r, X[f], c)
+        assert abs(rec[f, L.REC_OPT_D] - od) < 1e-9 and int(rec[f, L.REC_OPT_ATOM]) == oa
+        near += abs(O.opt_pore_diameter(r, X[f], com)[0] - od) <= 1e-3
+        w = O.find_windows(r, m, X[f], centre=c)
+        g = record_windows(rec[f], warn=False)
+        assert w is not None and g is not None and len(w[0]) == len(g[0]) == 4
+        np.testing.assert_allclose(g[0], w[0], atol=1e-3)
+        np.testing.assert_allclose(g[1], w[1], atol=5e-3)
+    assert near >= 0.6 * X.shape[0]        # free-running pore centre: the reference's own noise floor
