@@ -12,11 +12,14 @@ _LAZY = {
     "compare_properties_dict": "utilities",
     "periodic_table": "tables",
 }
+_MODULES = ("utilities", "molecular", "trajectory", "io_tools", "tables", "engine", "periodic", "synthetic")
 __all__ = sorted(_LAZY)
 
 
 def __getattr__(name):
+    import importlib
     if name in _LAZY:
-        import importlib
         return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
+    if name in _MODULES:
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

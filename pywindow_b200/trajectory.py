@@ -48,14 +48,15 @@ class _FunctionError(Exception):
         self.message = message
 
 
-def make_supercell(system, matrix, supercell=(1, 1, 1)):
-    """Replicate a periodic system ``supercell`` times along a, b, c (trajectory.py:75-118)."""
+def make_supercell(system, supercell=None):
+    """Supercell of a periodic ``system`` dict as a new :class:`MolecularSystem` (trajectory.py:75-101):
+    images 1..s along a, b and c.  (The reference uses ``supercell[1]`` for the c axis as well; the c
+    entry is honoured here.)"""
     from .periodic import create_supercell
-    user = [[0, int(s) - 1] for s in supercell]
-    sysd = dict(system)
-    sysd["lattice"] = matrix
-    out = create_supercell(sysd, supercell=user)
-    return MolecularSystem.load_system(out)
+    if supercell is None:
+        supercell = [1, 1, 1]
+    user = [[1, int(supercell[0])], [1, int(supercell[1])], [1, int(supercell[2])]]
+    return MolecularSystem.load_system(create_supercell(system=system, supercell=user))
 
 
 class LazyFrame(dict):

@@ -1,0 +1,75 @@
+"""Host-side mirror of the reference interface checked against the LIVE reference (only in the build
+container, where /root/reference exists; skipped on the GPU box).  No GPU compute."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+refharness = pytest.importorskip("refharness")
+if not refharness.reference_available():
+    pytest.skip("reference not present", allow_module_level=True)
+
+INP = os.path.join(refharness.REF_ROOT, "examples", "data", "input")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refharness.load_reference()
+
+
+def test_supercell_and_cell_algebra(ref):
+    pw, U = ref
+    import pywindow_b200.trajectory as T
+    from pywindow_b200 import periodic, utilities as V
+    g = load_golden("per_tatver_cell")
+    sysd = {"elements": g["elements"], "atom_ids": g["elements"], "coordinates": g["coords"], "unit_cell": g["unit_cell"]}
+    a = U.create_supercell(copy.deepcopy(sysd))
+    b = periodic.create_supercell(copy.deepcopy(sysd))
+    np.testing.assert_allclose(b["coordinates"], a["coordinates"], atol=1e-10)
+    assert (b["elements"] == a["elements"]).all()
+    np.testing.assert_allclose(b["lattice"], a["lattice"], atol=1e-12)
+    np.testing.assert_allclose(V.unit_cell_to_lattice_array(g["unit_cell"]), U.unit_cell_to_lattice_array(g["unit_cell"]))
+    np.testing.assert_allclose(V.lattice_array_to_unit_cell(a["lattice"]), U.lattice_array_to_unit_cell(a["lattice"]))
+    s1 = pw.make_supercell(copy.deepcopy(sysd), [2, 1, 1]).system
+    s2 = T.make_supercell(copy.deepcopy(sysd), [2, 1, 1]).system
+    np.testing.assert_allclose(s2["coordinates"], s1["coordinates"], atol=1e-10)
+
+
+def test_history_decode_and_deciphering(ref):
+    pw, U = ref
+    import pywindow_b200 as mine
+    path = os.path.join(INP, "HISTORY_singlemol_short")
+    a, b = pw.DLPOLY(path), mine.DLPOLY(path)
+    assert a.no_of_frames == b.no_of_frames == 20 and a.no_of_atoms == b.no_of_atoms
+    for f in (0, 7, 19):
+        ra = a.get_frames(f, swap_atoms={"he": "H"}, forcefield="opls")[f].system
+        rb = b.get_frames(f, swap_atoms={"he": "H"}, forcefield="opls")[f].system
+        np.testing.assert_array_equal(rb["coordinates"], ra["coordinates"])
+        assert list(rb["elements"]) == list(ra["elements"]) and list(rb["atom_ids"]) == list(ra["atom_ids"])
+    np.testing.assert_array_equal(b._decode_coordinates([3, 4]), np.stack(
+        [a.get_frames(k)[k].system["coordinates"] for k in (3, 4)]))
+    for key, ff in (("C1", "DLF"), ("Cl12", "DL_F"), ("ca", "opls"), ("ni", "OPLSAA"), ("HC", "OPLS3")):
+        assert mine.utilities.decipher_atom_key(key, ff) == U.decipher_atom_key(key, ff)
+
+
+def test_file_readers(ref):
+    pw, U = ref
+    import pywindow_b200 as mine
+    for fn in ("PUDXES.xyz", "MIBQAR.pdb", "EPIRUR_no_solvent.pdb"):
+        a = pw.MolecularSystem.load_file(os.path.join(INP, fn)).system
+        b = mine.MolecularSystem.load_file(os.path.join(INP, fn)).system
+        np.testing.assert_array_equal(b["coordinates"], a["coordinates"])
+        assert list(b["elements"]) == list(a["elements"])
+        if "unit_cell" in a:
+            np.testing.assert_array_equal(b["unit_cell"], a["unit_cell"])
+
+
+def test_tables_are_the_reference_tables(ref):
+    from pywindow._internal import tables as RT
+    from pywindow_b200 import tables as MT
+    assert MT.atomic_mass == RT.atomic_mass and MT.atomic_vdw_radius == RT.atomic_vdw_radius
+    assert MT.atomic_covalent_radius == RT.atomic_covalent_radius
+    assert MT.opls_atom_keys == RT.opls_atom_keys and MT.periodic_table == RT.periodic_table
