@@ -393,12 +393,14 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
 // Obj must provide:  void fg(const double* x, double& f, double* g);
 // (f and the bound-aware forward-difference gradient; on device it is warp-cooperative and every
 // lane runs this routine redundantly with identical data, so control flow is warp-uniform.)
-template <int N, class Obj>
-PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd,
+// NBD >= 0: every variable has that bound type, known at compile time (the bound-type tests fold away)
+template <int N, class Obj, int NBD = -1>
+PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd_in,
                             double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out,
                             double* hist_storage) {
   double g[N], f;
-  int iwhere[N];
+  int iwhere[N], nbd[N];
+  for (int i = 0; i < N; i++) nbd[i] = NBD >= 0 ? NBD : nbd_in[i];
   bool cnstnd = false, boxed = true;
   for (int i = 0; i < N; i++) {
     if (nbd[i] > 0) {

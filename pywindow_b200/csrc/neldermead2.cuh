@@ -27,60 +27,84 @@ struct Nm2Sort {
 };
 
 // Obj must provide: double f2(double x, double y)   (warp-cooperative on device)
+//
+// Written as a state machine around ONE call site of the objective: on the device the objective is a
+// few hundred inlined instructions, and the textbook layout (one call per reflection / expansion /
+// contraction / shrink branch) multiplies that by nine in a kernel that already misses in the
+// instruction cache.  The sequence of evaluations and comparisons is scipy's, unchanged.
 template <class Obj>
 PWB_HDN void nelder_mead2(Obj& obj, double x0, double y0, double xatol, double fatol, int maxiter, int maxfun,
                           double* xy_out, double* f_out, int* nfev_out) {
+  enum { INIT, REFLECT, EXPAND, CONTRACT_OUT, CONTRACT_IN, SHRINK };
   double sim[3][2], fs[3];
   sim[0][0] = x0; sim[0][1] = y0;
   sim[1][0] = (x0 != 0) ? (1 + 0.05) * x0 : 0.00025; sim[1][1] = y0;
   sim[2][0] = x0; sim[2][1] = (y0 != 0) ? (1 + 0.05) * y0 : 0.00025;
-  int fcalls = 0;
-  for (int k = 0; k < 3; k++) { fs[k] = obj.f2(sim[k][0], sim[k][1]); fcalls++; }
-  Nm2Sort::sort3(fs, sim);
-  int iterations = 1;
-  while (fcalls < maxfun && iterations < maxiter) {
+  int fcalls = 0, iterations = 0, st = INIT, k = 0;
+  double tx = sim[0][0], ty = sim[0][1];
+  double xb0 = 0, xb1 = 0, xr0 = 0, xr1 = 0, fxr = 0;
+  for (;;) {
+    const double fv = obj.f2(tx, ty); fcalls++;
+    bool end_iter = false, aborted = false, shrink = false;
+    if (st == INIT) {
+      if (k == 0) fs[0] = fv; else if (k == 1) fs[1] = fv; else fs[2] = fv;
+      k++;
+      if (k == 1) { tx = sim[1][0]; ty = sim[1][1]; }
+      else if (k == 2) { tx = sim[2][0]; ty = sim[2][1]; }
+      else { iterations = 0; end_iter = true; }          // falls into the sort + loop head below
+    } else if (st == REFLECT) {
+      fxr = fv;
+      if (fxr < fs[0]) {
+        if (fcalls >= maxfun) { aborted = true; end_iter = true; }
+        else { tx = (1 + 2.0) * xb0 - 2.0 * sim[2][0]; ty = (1 + 2.0) * xb1 - 2.0 * sim[2][1]; st = EXPAND; }
+      } else if (fxr < fs[1]) {
+        sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr; end_iter = true;
+      } else if (fcalls >= maxfun) { aborted = true; end_iter = true; }
+      else if (fxr < fs[2]) {
+        tx = (1 + 0.5) * xb0 - 0.5 * sim[2][0]; ty = (1 + 0.5) * xb1 - 0.5 * sim[2][1]; st = CONTRACT_OUT;
+      } else {
+        tx = (1 - 0.5) * xb0 + 0.5 * sim[2][0]; ty = (1 - 0.5) * xb1 + 0.5 * sim[2][1]; st = CONTRACT_IN;
+      }
+    } else if (st == EXPAND) {
+      if (fv < fxr) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; }
+      else { sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr; }
+      end_iter = true;
+    } else if (st == CONTRACT_OUT) {
+      if (fv <= fxr) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; end_iter = true; }
+      else shrink = true;
+    } else if (st == CONTRACT_IN) {
+      if (fv < fs[2]) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; end_iter = true; }
+      else shrink = true;
+    } else {   // SHRINK: vertex k was just evaluated
+      if (k == 1) fs[1] = fv; else fs[2] = fv;
+      k++;
+      if (k == 3) end_iter = true;
+      else if (fcalls >= maxfun) { aborted = true; end_iter = true; }
+      else {
+        sim[2][0] = sim[0][0] + 0.5 * (sim[2][0] - sim[0][0]);
+        sim[2][1] = sim[0][1] + 0.5 * (sim[2][1] - sim[0][1]);
+        tx = sim[2][0]; ty = sim[2][1];
+      }
+    }
+    if (shrink) {
+      if (fcalls >= maxfun) { aborted = true; end_iter = true; }
+      else {
+        sim[1][0] = sim[0][0] + 0.5 * (sim[1][0] - sim[0][0]);
+        sim[1][1] = sim[0][1] + 0.5 * (sim[1][1] - sim[0][1]);
+        tx = sim[1][0]; ty = sim[1][1]; k = 1; st = SHRINK;
+      }
+    }
+    if (!end_iter) continue;
+    if (!aborted) iterations++;
+    Nm2Sort::sort3(fs, sim);
+    if (!(fcalls < maxfun && iterations < maxiter)) break;
     double dx = fmax(fmax(fabs(sim[1][0] - sim[0][0]), fabs(sim[1][1] - sim[0][1])),
                      fmax(fabs(sim[2][0] - sim[0][0]), fabs(sim[2][1] - sim[0][1])));
     double df = fmax(fabs(fs[0] - fs[1]), fabs(fs[0] - fs[2]));
     if (dx <= xatol && df <= fatol) break;
-    double xb0 = (sim[0][0] + sim[1][0]) / 2, xb1 = (sim[0][1] + sim[1][1]) / 2;
-    double xr0 = (1 + 1.0) * xb0 - 1.0 * sim[2][0], xr1 = (1 + 1.0) * xb1 - 1.0 * sim[2][1];
-    double fxr = obj.f2(xr0, xr1); fcalls++;
-    bool doshrink = false, aborted = false;
-    if (fxr < fs[0]) {
-      if (fcalls >= maxfun) aborted = true;
-      else {
-        double xe0 = (1 + 2.0) * xb0 - 2.0 * sim[2][0], xe1 = (1 + 2.0) * xb1 - 2.0 * sim[2][1];
-        double fxe = obj.f2(xe0, xe1); fcalls++;
-        if (fxe < fxr) { sim[2][0] = xe0; sim[2][1] = xe1; fs[2] = fxe; }
-        else { sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr; }
-      }
-    } else if (fxr < fs[1]) {
-      sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr;
-    } else {
-      if (fcalls >= maxfun) aborted = true;
-      else if (fxr < fs[2]) {
-        double xc0 = (1 + 0.5) * xb0 - 0.5 * sim[2][0], xc1 = (1 + 0.5) * xb1 - 0.5 * sim[2][1];
-        double fxc = obj.f2(xc0, xc1); fcalls++;
-        if (fxc <= fxr) { sim[2][0] = xc0; sim[2][1] = xc1; fs[2] = fxc; }
-        else doshrink = true;
-      } else {
-        double xc0 = (1 - 0.5) * xb0 + 0.5 * sim[2][0], xc1 = (1 - 0.5) * xb1 + 0.5 * sim[2][1];
-        double fxcc = obj.f2(xc0, xc1); fcalls++;
-        if (fxcc < fs[2]) { sim[2][0] = xc0; sim[2][1] = xc1; fs[2] = fxcc; }
-        else doshrink = true;
-      }
-      if (doshrink) {
-        for (int j = 1; j < 3; j++) {
-          if (fcalls >= maxfun) { aborted = true; break; }
-          sim[j][0] = sim[0][0] + 0.5 * (sim[j][0] - sim[0][0]);
-          sim[j][1] = sim[0][1] + 0.5 * (sim[j][1] - sim[0][1]);
-          fs[j] = obj.f2(sim[j][0], sim[j][1]); fcalls++;
-        }
-      }
-    }
-    if (!aborted) iterations++;
-    Nm2Sort::sort3(fs, sim);
+    xb0 = (sim[0][0] + sim[1][0]) / 2; xb1 = (sim[0][1] + sim[1][1]) / 2;
+    xr0 = (1 + 1.0) * xb0 - 1.0 * sim[2][0]; xr1 = (1 + 1.0) * xb1 - 1.0 * sim[2][1];
+    tx = xr0; ty = xr1; st = REFLECT;
   }
   xy_out[0] = sim[0][0]; xy_out[1] = sim[0][1];
   *f_out = fmin(fs[0], fmin(fs[1], fs[2]));

@@ -16,6 +16,7 @@ constexpr int ITEM_I = 32;   // ints of per-item scratch
 constexpr int D_COM = 0, D_MAXD = 3, D_CENTRE = 4, D_RADIUS = 7, D_EPS = 8, D_ICOM = 9, D_SHIFT = 12;
 // item_i slots
 constexpr int I_STATUS = 0, I_P = 1, I_NSURV = 2, I_NCLEAR = 3, I_NWIN = 4, I_N = 5, I_CLS0 = 6;  // cls_start[17]
+constexpr int I_QUEUE = 26;  // (first item of a launch only) work-queue head of k_opt_pore
 constexpr int I_DEFER = 24;   // cluster stage deferred to the large-shared-memory pass
 
 constexpr double PWB_INF = 1e300;
@@ -136,8 +137,7 @@ __device__ __forceinline__ ValIdx block_vi(ValIdx a, bool want_max, double* redv
 // |x_i-q|^2) - r_c): the inner loop has no sqrt and the result is bit-identical because sqrt is
 // monotone.
 struct Bucketed {
-  const double* x; const double* y; const double* z;   // [n] shifted coordinates
-  const double* w;                                     // [n] |x|^2
+  const double4* p;                                    // [n] shifted coordinates x, y, z and w = |x|^2
   const int* cls;                                      // [ncls+1] class starts
   const double* cr;                                    // [ncls] class radius
   int ncls;
@@ -162,9 +162,9 @@ __device__ __forceinline__ void min_clearance_k(const Bucketed& A, const double*
 #pragma unroll
     for (int k = 0; k < K; k++) m[k] = PWB_INF;
     for (int i = b; i < e; i++) {
-      const double X = A.x[i], Y = A.y[i], Z = A.z[i], W = A.w[i];
+      const double4 q = A.p[i];
 #pragma unroll
-      for (int k = 0; k < K; k++) m[k] = fmin(m[k], fma(ax[k], X, fma(ay[k], Y, fma(az[k], Z, W))));
+      for (int k = 0; k < K; k++) m[k] = fmin(m[k], fma(ax[k], q.x, fma(ay[k], q.y, fma(az[k], q.z, q.w))));
     }
     const double rc = A.cr[c];
 #pragma unroll
@@ -180,7 +180,9 @@ __device__ __forceinline__ double min_clearance(const Bucketed& A, double qx, do
 
 // ---- warp-cooperative pore objective (lanes stride over atoms) ---------------------------------
 struct WarpAtoms {
-  const double* x; const double* y; const double* z; const double* r;
+  const double4* p;      // [n] x, y, z (w belongs to the owner: radius in k_opt_pore, |x|^2 in k_windows)
+  const double* r;       // vdW radius of atom i at r[i * rs]
+  int rs;
   int n, lane;
   const int* cls;      // [ncls+1] class starts of the type-bucketed atoms
   int ncls;
@@ -188,11 +190,74 @@ struct WarpAtoms {
 
 __device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
 
+// Warp-wide min of NON-NEGATIVE doubles (squared distances, +inf): their bit patterns are already
+// ordered as unsigned integers, so two REDUX operations suffice.
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+  const unsigned long long k = (unsigned long long)__double_as_longlong(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+
+// Same result as warp_min_clear, bit for bit, with ONE square root per warp instead of one per
+// (lane, class, point): sqrt is monotone, so the squared distances are reduced over the warp first;
+// the reduced value of (class c, point k) is parked in lane c*K + k, all lanes take the root of their
+// own value at once, and a stride-K butterfly finishes the min over classes.
+// `first(c)`, `last(c)` give the class's range, `atom(t)` maps a range position to an atom index.
+template <int K, class First, class Last, class Atom>
+__device__ __forceinline__ void warp_min_clear_rs(const WarpAtoms& A, First first, Last last, Atom atom,
+                                                  const double* px, const double* py, const double* pz, double* out) {
+  constexpr int CPG = 32 / K;                       // classes per group of 32 lanes
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = PWB_INF;
+  for (int c0 = 0; c0 < A.ncls; c0 += CPG) {
+    double mine = PWB_INF;
+    const int cend = min(A.ncls, c0 + CPG);
+    for (int c = c0; c < cend; c++) {
+      const int cb = first(c), ce = last(c);
+      if (cb == ce) continue;
+      double m[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = PWB_INF;
+      for (int t = cb + A.lane; t < ce; t += 32) {
+        const double4 q = A.p[atom(t)];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+          m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
+        }
+      }
+      const int slot = (c - c0) * K;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const double red = warp_min_nonneg(m[k]);
+        if (A.lane == slot + k) mine = red;
+      }
+    }
+    const int myc = c0 + A.lane / K;
+    double v = PWB_INF;
+    if (mine < PWB_INF) v = sqrt(mine) - A.r[A.cls[myc] * A.rs];
+    if (K == 1) {
+      out[0] = dmin(out[0], warp_min(v));
+    } else {
+#pragma unroll
+      for (int s = K; s < 32; s <<= 1) v = dmin(v, shfl_xor_d(v, s));
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = dmin(out[k], __shfl_sync(0xffffffffu, v, k));
+    }
+  }
+}
+
 // min_i(|x_i - p_k| - r_i) for K points; lanes stride over the atoms of one class at a time so the
 // sqrt is taken once per (lane, class, point) instead of once per (atom, point).
 template <int K>
 __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double* px, const double* py,
                                                const double* pz, double* out) {
+  if constexpr (K >= 4) {   // measured: pays for the 4-point finite-difference stencil, not for K = 1, 2
+    warp_min_clear_rs<K>(A, [&](int c) { return A.cls[c]; }, [&](int c) { return A.cls[c + 1]; },
+                         [](int t) { return t; }, px, py, pz, out);
+  } else {
   double v[K];
 #pragma unroll
   for (int k = 0; k < K; k++) v[k] = PWB_INF;
@@ -203,19 +268,21 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
 #pragma unroll
     for (int k = 0; k < K; k++) m[k] = PWB_INF;
     for (int i = cb + A.lane; i < ce; i += 32) {
-      const double ax = A.x[i], ay = A.y[i], az = A.z[i];
+      const double4 q = A.p[i];
+      const double ax = q.x, ay = q.y, az = q.z;
 #pragma unroll
       for (int k = 0; k < K; k++) {
         double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
         m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
       }
     }
-    const double rc = A.r[cb];
+    const double rc = A.r[cb * A.rs];
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
   }
 #pragma unroll
   for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);
+  }
 }
 
 // ---- direction grid: which atoms can a ray from the centroid hit at all? ---------------------------
@@ -313,8 +380,9 @@ __device__ __forceinline__ void warp_build_near(const WarpAtoms& A, NearList& N,
       const int i = base + A.lane;
       bool keep = false;
       if (i < ce) {
-        const double dx = A.x[i] - cx, dy = A.y[i] - cy, dz = A.z[i] - cz;
-        keep = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i] <= thr;
+        const double4 q = A.p[i];
+        const double dx = q.x - cx, dy = q.y - cy, dz = q.z - cz;
+        keep = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i * A.rs] <= thr;
       }
       const unsigned mask = __ballot_sync(0xffffffffu, keep);
       if (keep) N.idx[pos + __popc(mask & ((1u << A.lane) - 1u))] = (unsigned short)i;
@@ -348,14 +416,15 @@ __device__ __forceinline__ void warp_min_clear_near(const WarpAtoms& A, const Ne
     for (int k = 0; k < K; k++) m[k] = PWB_INF;
     for (int t = cb + A.lane; t < ce; t += 32) {
       const int i = N.idx[t];
-      const double ax = A.x[i], ay = A.y[i], az = A.z[i];
+      const double4 q = A.p[i];
+      const double ax = q.x, ay = q.y, az = q.z;
 #pragma unroll
       for (int k = 0; k < K; k++) {
         double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
         m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
       }
     }
-    const double rc = A.r[A.cls[c]];
+    const double rc = A.r[A.cls[c] * A.rs];
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
   }
@@ -382,9 +451,9 @@ __device__ __forceinline__ void min_clearance_k_near(const Bucketed& A, const Ne
     for (int k = 0; k < K; k++) m[k] = PWB_INF;
     for (int t = b; t < e; t++) {
       const int i = N.idx[t];
-      const double X = A.x[i], Y = A.y[i], Z = A.z[i], W = A.w[i];
+      const double4 q = A.p[i];
 #pragma unroll
-      for (int k = 0; k < K; k++) m[k] = dmin(m[k], fma(ax[k], X, fma(ay[k], Y, fma(az[k], Z, W))));
+      for (int k = 0; k < K; k++) m[k] = dmin(m[k], fma(ax[k], q.x, fma(ay[k], q.y, fma(az[k], q.z, q.w))));
     }
     const double rc = A.cr[c];
 #pragma unroll
@@ -396,8 +465,9 @@ __device__ __forceinline__ void min_clearance_k_near(const Bucketed& A, const Ne
 __device__ __forceinline__ ValIdx warp_pore_argmin(const WarpAtoms& A, const int* orig, double cx, double cy, double cz) {
   ValIdx b; b.v = PWB_INF; b.i = 0x7fffffff;
   for (int i = A.lane; i < A.n; i += 32) {
-    double dx = A.x[i] - cx, dy = A.y[i] - cy, dz = A.z[i] - cz;
-    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i]; c.i = orig[i];
+    const double4 q = A.p[i];
+    double dx = q.x - cx, dy = q.y - cy, dz = q.z - cz;
+    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - A.r[i * A.rs]; c.i = orig[i];
     b = vi_min(b, c);
   }
   return warp_vi_min(b);

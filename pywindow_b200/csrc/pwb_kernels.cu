@@ -270,14 +270,14 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 constexpr int OPT_WARPS = 4;
 
 struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-point differences
-  WarpAtoms A; const double* lo; const double* hi; const int* nbd; int nfev;
+  WarpAtoms A; const double* lo; const double* hi; int nfev;   // all three variables boxed (nbd = 2)
   __device__ void fg(const double* x, double& f, double* g) {
     nfev += 4;
     double px[4], py[4], pz[4], h[3], m[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
 #pragma unroll
-    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], nbd[i], lo[i], hi[i]);
+    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], 2, lo[i], hi[i]);
     px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
     warp_min_clear<4>(A, px, py, pz, m);
     f = -(m[0] * 2.0);
@@ -286,26 +286,28 @@ struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-p
   }
 };
 
-__global__ void __launch_bounds__(OPT_WARPS * 32, 8)
-k_opt_pore(pwb_batch b, Ws ws) {
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int item = blockIdx.x * (blockDim.x >> 5) + w;      // warps per CTA chosen at launch (<= OPT_WARPS)
-  if (item >= b.n_items) return;
+#ifndef OPT_MINB
+#define OPT_MINB 8
+#endif
+// doubles of shared memory per warp: double4[NA] atoms, the L-BFGS ring, class starts (17 ints, padded), bounds
+#define OPT_WARP_DOUBLES(NA) ((NA) * 4 + 2 * LB_M * 3 + 10 + 6)
+// one item on one warp; `smw` is the warp's private shared memory
+__device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, const int item, const int lane, double* smw) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
   double* rec = b.records + (size_t)item * b.rec_stride;
   if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* x = sm + (size_t)w * (NA * 4 + 2 * LB_M * 3);
-  double* y = x + NA; double* z = y + NA; double* r = z + NA;
-  double* hist = r + NA;                                      // [2*LB_M*3] L-BFGS (s, y) ring, one copy per warp
+  double4* p4 = (double4*)smw;                                // x, y, z, radius
+  double* hist = (double*)(p4 + NA);                          // [2*LB_M*3] L-BFGS (s, y) ring, one copy per warp
+  int* cls = (int*)(hist + 2 * LB_M * 3);                     // [PWB_MAX_TYPES+1] class starts
+  if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
-    x[a] = q[0]; y[a] = q[1]; z[a] = q[2]; r[a] = q[3];
+    p4[a] = make_double4(q[0], q[1], q[2], q[3]);
   }
   __syncwarp();
-  WarpAtoms A{x, y, z, r, n, lane, iiv + I_CLS0, b.n_types};
+  WarpAtoms A{p4, (const double*)p4 + 3, 4, n, lane, cls, b.n_types};
   const int* orig = ws.atom_idx + off;
   double c[3] = {idv[D_COM], idv[D_COM + 1], idv[D_COM + 2]};
   double fopt = 0; int nit = 0, st = 0, nfev = 0;
@@ -319,12 +321,13 @@ k_opt_pore(pwb_batch b, Ws ws) {
       if (lane == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
       return;
     }
-    double lo[3], hi[3];
-    int nbd[3] = {2, 2, 2};
+    double* lo = (double*)(cls + 20);                          // [3], [3]: box bounds, one copy per warp
+    double* hi = lo + 3;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
-    DevPoreObj3 obj{A, lo, hi, nbd, 0};
-    st = lbfgsb_minimize<3>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
+    for (int i = 0; i < 3; i++) if (lane == i) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
+    __syncwarp();
+    DevPoreObj3 obj{A, lo, hi, 0};
+    st = lbfgsb_minimize<3, DevPoreObj3, 2>(obj, c, lo, hi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
     nfev = obj.nfev;
   }
   ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
@@ -333,6 +336,25 @@ k_opt_pore(pwb_batch b, Ws ws) {
     rec[PWB_REC_OPT_D] = 2.0 * pa.v; rec[PWB_REC_OPT_ATOM] = pa.i;
     rec[PWB_REC_OPT_C] = c[0]; rec[PWB_REC_OPT_C + 1] = c[1]; rec[PWB_REC_OPT_C + 2] = c[2];
     rec[PWB_REC_OPT_NIT] = nit; rec[PWB_REC_OPT_STOP] = st; rec[PWB_REC_OPT_NFEV] = nfev;
+  }
+}
+
+// Warps pull items from a queue (one atomic per item): the iteration counts of the optimiser vary by
+// 10x between frames, so a static item -> warp map leaves CTAs waiting for their slowest warp and the
+// last wave mostly empty.
+__global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)
+k_opt_pore(pwb_batch b, Ws ws) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* smw = sm + (size_t)w * OPT_WARP_DOUBLES(b.max_atoms);
+  int* queue = ws.item_i + I_QUEUE;                           // zeroed by run_opt before the launch
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= b.n_items) break;
+    opt_pore_item(b, ws, item, lane, smw);
+    __syncwarp();
   }
 }
 
@@ -1036,6 +1058,8 @@ k_cluster_big(pwb_batch b, Ws ws, int phase) {
 // k_windows: window_analysis (utilities.py:1191-1361), one warp per (item, window)
 // =================================================================================================
 constexpr int WIN_WARPS = 4;
+// doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage ring, even
+#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + 2 * LB_M) + 1) & ~(size_t)1)
 
 struct DevZObj {   // optimise_z, utilities.py:1174-1188
   WarpAtoms A; double lo;
@@ -1063,23 +1087,21 @@ __device__ __forceinline__ double angle_between(double x0, double x1, double x2,
   return acos(first);
 }
 
-__global__ void __launch_bounds__(WIN_WARPS * 32, 7)
-k_windows(pwb_batch b, Ws ws) {
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + w;        // warps per CTA chosen at launch (<= WIN_WARPS)
-  const int item = gw / b.win_cap, win = gw - item * b.win_cap;
-  if (item >= b.n_items) return;
+#ifndef WIN_MINB
+#define WIN_MINB 7
+#endif
+// one (item, window) on one warp; `smw` is the warp's private shared memory (WIN_WARP_DOUBLES)
+__device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, const int item, const int win,
+                                            const int lane, double* smw) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
-  if (win >= iiv[I_NWIN]) return;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
   double* rec = b.records + (size_t)item * b.rec_stride;
   double* out = rec + PWB_REC_WIN0 + 4 * win;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
   const int NAp = (NA + 3) & ~3;
-  double* x = sm + (size_t)w * (NA * 5 + PWB_MAX_TYPES + 32 + NAp / 4 + 2 * LB_M);
-  double* y = x + NA; double* z = y + NA; double* r = z + NA; double* w2 = r + NA;
-  double* cr = w2 + NA;                      // [PWB_MAX_TYPES]
+  double4* p4 = (double4*)smw;               // x, y, z, |x|^2 (shifted, later rotated)
+  double* r = (double*)(p4 + NA);
+  double* cr = r + NA;                       // [PWB_MAX_TYPES]
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
   int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
   unsigned short* nidx = (unsigned short*)(cr + PWB_MAX_TYPES + 32);   // [NA] near-list atom indices
@@ -1087,13 +1109,13 @@ k_windows(pwb_batch b, Ws ws) {
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
-    x[a] = q[0] - shx; y[a] = q[1] - shy; z[a] = q[2] - shz; r[a] = q[3];
-    w2[a] = x[a] * x[a] + y[a] * y[a] + z[a] * z[a];
+    const double X = q[0] - shx, Y = q[1] - shy, Z = q[2] - shz;
+    p4[a] = make_double4(X, Y, Z, X * X + Y * Y + Z * Z); r[a] = q[3];
   }
   if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
   if (lane < PWB_MAX_TYPES) cr[lane] = lane < b.n_types ? b.type_vdw[lane] : 0.0;
   __syncwarp();
-  Bucketed B{x, y, z, w2, cls, cr, b.n_types};
+  Bucketed B{p4, cls, cr, b.n_types};
   const int P = iiv[I_P];
   const double R = idv[D_RADIUS];
   // ---- rescan of the arg-max ray with increment2 (utilities.py:1221-1227)
@@ -1108,9 +1130,10 @@ k_windows(pwb_batch b, Ws ws) {
     const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
     const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
     for (int a = lane; a < n; a += 32) {
-      const double g = fma(x[a], cxs, fma(y[a], cys, z[a] * czs));
+      const double4 q = p4[a];
+      const double g = fma(q.x, cxs, fma(q.y, cys, q.z * czs));
       const double j0 = floor(fmin(fmax(g * icc, 0.0), jmax)), j1 = j0 + 1.0;
-      const double g2 = -2.0 * g, wv = w2[a];
+      const double g2 = -2.0 * g, wv = q.w;
       const double d0 = fma(j0, fma(j0, cc, g2), wv), d1 = fma(j1, fma(j1, cc, g2), wv);
       ValIdx c0; c0.v = sqrt(fmax(d0, 0.0)) - r[a]; c0.i = (int)j0;
       ValIdx c1; c1.v = sqrt(fmax(d1, 0.0)) - r[a]; c1.i = (int)j1;
@@ -1145,21 +1168,21 @@ k_windows(pwb_batch b, Ws ws) {
   sincos(a1, &s1, &c1);
   sincos(a2, &s2, &c2);
   for (int a = lane; a < n; a += 32) {
-    double X0 = x[a], Y0 = y[a], Z0 = z[a];
+    double X0 = p4[a].x, Y0 = p4[a].y, Z0 = p4[a].z;
     double X1 = c1 * X0 + (-s1) * Y0, Y1 = s1 * X0 + c1 * Y0, Z1 = Z0;         // Rz(a1)
     double X2 = c2 * X1 + s2 * Z1, Y2 = Y1, Z2 = (-s2) * X1 + c2 * Z1;          // Ry(a2)
-    x[a] = X2; y[a] = Y2; z[a] = Z2 - new_z;
-    w2[a] = x[a] * x[a] + y[a] * y[a] + z[a] * z[a];
+    const double Z3 = Z2 - new_z;
+    p4[a] = make_double4(X2, Y2, Z3, X2 * X2 + Y2 * Y2 + Z3 * Z3);
   }
   __syncwarp();
-  WarpAtoms A{x, y, z, r, n, lane, cls, b.n_types};
+  WarpAtoms A{p4, r, 1, n, lane, cls, b.n_types};
   double m0[1], zero = 0.0;
   warp_min_clear<1>(A, &zero, &zero, &zero, m0);
   const double d0 = m0[0] * 2.0;
   // ---- z stage: L-BFGS-B from 0 with lower bound -new_z (utilities.py:1296-1305)
-  double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nbd1[1] = {1}, nitz;
+  double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nitz;
   DevZObj zo{A, -new_z};
-  lbfgsb_minimize<1>(zo, zc, zlo, zhi, nbd1, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
+  lbfgsb_minimize<1, DevZObj, 1>(zo, zc, zlo, zhi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
   const double wz = zc[0];
   // ---- xy stage: 20x20 brute grid (first arg-min, row-major) + Nelder-Mead (utilities.py:1307-1316)
   const double glo = -d0 / 2, ghi = d0 / 2;
@@ -1202,6 +1225,19 @@ k_windows(pwb_batch b, Ws ws) {
     out[1] = X2 + idv[D_ICOM]; out[2] = Y2 + idv[D_ICOM + 1]; out[3] = Z2 + idv[D_ICOM + 2];
     if (diam < 0) atomicOr(&iiv[I_STATUS], PWB_ST_WIN_NEGATIVE);
   }
+}
+
+// Static (item, window) -> warp map: a work queue like k_opt_pore's was measured 45 % SLOWER here (warps
+// of a CTA drift into different phases of this 200 KB kernel and miss in the instruction cache).
+__global__ void __launch_bounds__(WIN_WARPS * 32, WIN_MINB)
+k_windows(pwb_batch b, Ws ws) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + w;        // warps per CTA chosen at launch (<= WIN_WARPS)
+  const int item = gw / b.win_cap, win = gw - item * b.win_cap;
+  if (item >= b.n_items) return;
+  if (win >= ws.item_i[(size_t)item * ITEM_I + I_NWIN]) return;
+  window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_WARP_DOUBLES(b.max_atoms));
 }
 
 // final status word (window kernels OR flags into item_i after the record status was written)
@@ -1257,7 +1293,7 @@ using namespace pwb;
 
 constexpr int PWB_MAX_CHUNKS = 8;
 struct pwb_ctx {
-  Ctx c; int* d_tmp; int max_smem;
+  Ctx c; int* d_tmp; int max_smem, num_sms;
   int chunks;                                   // sub-batches pipelined over internal streams
   cudaStream_t streams[PWB_MAX_CHUNKS];
   cudaEvent_t fork, join[PWB_MAX_CHUNKS];
@@ -1320,6 +1356,7 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
   CK(cudaMemset(c->c.knn_unit, 0, sizeof(double) * ray_table_cap));
   CK(cudaMemset(c->c.knn_need, 0, sizeof(int) * ray_table_cap));
   CK(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->chunks = 1;
   for (int g = 0; g < PWB_MAX_CHUNKS; g++) {
     CK(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
@@ -1376,12 +1413,18 @@ static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
 }
 static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
   // fewer warps per CTA for very large molecules so the per-warp atom tiles still fit shared memory
-  const size_t per_warp = sizeof(double) * ((size_t)b->max_atoms * 4 + 2 * LB_M * 3);
+  const size_t per_warp = sizeof(double) * OPT_WARP_DOUBLES((size_t)b->max_atoms);
   int wpb = OPT_WARPS;
   while (wpb > 1 && per_warp * wpb > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb;
   if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
-  k_opt_pore<<<(b->n_items + wpb - 1) / wpb, wpb * 32, sm, s>>>(*b, w);
+  CK(cudaMemsetAsync(w.item_i + I_QUEUE, 0, sizeof(int), s));
+  int ctas = (b->n_items + wpb - 1) / wpb;
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_opt_pore, wpb * 32, sm));
+  const int resident = c->num_sms * (per_sm > 0 ? per_sm : 1);
+  if (ctas > resident) ctas = resident;
+  k_opt_pore<<<ctas, wpb * 32, sm, s>>>(*b, w);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1421,7 +1464,7 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  const size_t per_warp = sizeof(double) * ((size_t)b->max_atoms * 5 + PWB_MAX_TYPES + 32 + (((size_t)b->max_atoms + 3) & ~(size_t)3) / 4 + 2 * LB_M);
+  const size_t per_warp = sizeof(double) * WIN_WARP_DOUBLES((size_t)b->max_atoms);
   int wpb = WIN_WARPS;
   while (wpb > 1 && per_warp * wpb + 64 > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb + 64;

@@ -1,10 +1,11 @@
 """Per-source-line instruction counts / stall samples of one kernel: joins the SASS view of an .ncu-rep
 (by instruction address) with nvdisasm line info of the cubin inside libpwb.so.
-usage: ncu_lines.py report.ncu-rep kernel_regex mangled_substring [top]"""
+usage: ncu_lines.py report.ncu-rep kernel_regex mangled_substring [top] [sort column, e.g. stall_long_sb]"""
 import csv, os, re, subprocess, sys, tempfile
 from collections import Counter
 rep, kern, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+sortcol = sys.argv[5] if len(sys.argv) > 5 else None
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "pywindow_b200", "csrc", "libpwb.so")
 tmp = tempfile.mkdtemp()
@@ -32,6 +33,8 @@ hdr = rows[1]
 end = next((i for i in range(2, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))
 data = [r for r in rows[2:end] if len(r) == len(hdr)]
 ie, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
+if sortcol:
+    si = hdr.index(sortcol)
 base = int(data[0][0], 16)
 byaddr = dict(seq)
 ci, cs = Counter(), Counter()
@@ -47,7 +50,9 @@ for r in data:
 ti, ts = sum(ci.values()), sum(cs.values())
 print(f"{kern}: {len(data)} SASS instr, {len(seq)} with line info, {miss} unmatched; dynamic {ti}")
 src = {}
-for k, v in ci.most_common(top):
+order = cs.most_common(top) if sortcol else ci.most_common(top)
+for k, _ in order:
+    v = ci[k]
     f, l = k
     if f not in src:
         p = os.path.join(root, "pywindow_b200", "csrc", f)
