@@ -56,68 +56,55 @@ PWB_HD double lb_fd_step(double x, int nbd, double lo, double hi) {
 }
 
 // ---- More-Thuente safeguarded step (MINPACK-2 dcstep; scipy/optimize/_dcsrch.py:dcstep)
+// The four cases of dcstep each carry their own cubic (one sqrt, five to seven divisions).  Here the
+// cubic is evaluated ONCE on case-selected operands -- on the GPU the four inlined copies were a
+// quarter of each optimiser kernel's code, and those kernels are instruction-cache bound.  Every
+// expression keeps the operation order of the original; case 4 uses 3(fy-fp)/(stp-sty), which is
+// 3(fp-fy)/(sty-stp) with both signs flipped and therefore rounds identically.
 PWB_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy,
                       double& stp, double fp, double dp, bool& brackt, double stpmin, double stpmax) {
-  double sgn_dp = (dp > 0) - (dp < 0), sgn_dx = (dx > 0) - (dx < 0);
-  double sgnd = sgn_dp * sgn_dx;
-  double stpf, stpc, stpq, theta, s, gamma, p, q, r;
-  if (fp > fx) {
-    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp < stx) gamma = -gamma;
-    p = (gamma - dx) + theta;
-    q = ((gamma - dx) + gamma) + dp;
-    r = p / q;
-    stpc = stx + r * (stp - stx);
-    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+  const double sgn_dp = (dp > 0) - (dp < 0), sgn_dx = (dx > 0) - (dx < 0);
+  const double sgnd = sgn_dp * sgn_dx;
+  const int cs = (fp > fx) ? 1 : (sgnd < 0.0) ? 2 : (fabs(dp) < fabs(dx)) ? 3 : 4;
+  const bool far_end = cs == 4;                       // cubic through (sty, stp) instead of (stx, stp)
+  const double fa = far_end ? fy : fx, sta = far_end ? sty : stx, da = far_end ? dy : dx;
+  const double theta = 3.0 * (fa - fp) / (stp - sta) + da + dp;
+  const double s = fmax(fabs(theta), fmax(fabs(da), fabs(dp)));
+  double rad = (theta / s) * (theta / s) - (da / s) * (dp / s);
+  if (cs == 3) rad = fmax(0.0, rad);
+  double gamma = s * sqrt(rad);
+  if (cs == 1 ? (stp < stx) : (stp > sta)) gamma = -gamma;
+  const double e = cs == 1 ? dx : dp;
+  const double p = (gamma - e) + theta;
+  const double q = cs == 3 ? (gamma + (dx - dp)) + gamma : ((gamma - e) + gamma) + (cs == 1 ? dp : da);
+  const double r = p / q;
+  double stpf;
+  if (cs == 1) {
+    const double stpc = stx + r * (stp - stx);
+    const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
     stpf = (fabs(stpc - stx) <= fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
     brackt = true;
-  } else if (sgnd < 0.0) {
-    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
-    if (stp > stx) gamma = -gamma;
-    p = (gamma - dp) + theta;
-    q = ((gamma - dp) + gamma) + dx;
-    r = p / q;
-    stpc = stp + r * (stx - stp);
-    stpq = stp + (dp / (dp - dx)) * (stx - stp);
-    stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
-    brackt = true;
-  } else if (fabs(dp) < fabs(dx)) {
-    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
-    if (stp > stx) gamma = -gamma;
-    p = (gamma - dp) + theta;
-    q = (gamma + (dx - dp)) + gamma;
-    r = p / q;
-    if (r < 0 && gamma != 0) stpc = stp + r * (stx - stp);
-    else if (stp > stx) stpc = stpmax;
-    else stpc = stpmin;
-    stpq = stp + (dp / (dp - dx)) * (stx - stp);
-    if (brackt) {
-      stpf = (fabs(stpc - stp) < fabs(stpq - stp)) ? stpc : stpq;
-      if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
-      else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
-    } else {
-      stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
-      stpf = fmin(fmax(stpf, stpmin), stpmax);
-    }
-  } else {
-    if (brackt) {
-      theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-      s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
-      gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
-      if (stp > sty) gamma = -gamma;
-      p = (gamma - dp) + theta;
-      q = ((gamma - dp) + gamma) + dy;
-      r = p / q;
-      stpc = stp + r * (sty - stp);
-      stpf = stpc;
-    } else if (stp > stx) stpf = stpmax;
+  } else if (cs == 4) {
+    if (brackt) stpf = stp + r * (sty - stp);
+    else if (stp > stx) stpf = stpmax;
     else stpf = stpmin;
+  } else {
+    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    double stpc = stp + r * (stx - stp);
+    if (cs == 2) {
+      stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+      brackt = true;
+    } else {
+      if (!(r < 0 && gamma != 0)) stpc = (stp > stx) ? stpmax : stpmin;
+      if (brackt) {
+        stpf = (fabs(stpc - stp) < fabs(stpq - stp)) ? stpc : stpq;
+        if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+        else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+      } else {
+        stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+        stpf = fmin(fmax(stpf, stpmin), stpmax);
+      }
+    }
   }
   if (fp > fx) {
     sty = stp; fy = fp; dy = dp;
@@ -154,14 +141,15 @@ struct LbLineSearch {
     if (stp == stpmin && (f > ftest || g >= gtest)) task = WARN;
     if (f <= ftest && fabs(g) <= gtol * -ginit) task = CONV;
     if (task != FG) return task;
-    if (stage == 1 && f <= fx && f > ftest) {
-      double fm = f - stp * gtest, fxm = fx - stx * gtest, fym = fy - sty * gtest;
-      double gm = g - gtest, gxm = gx - gtest, gym = gy - gtest;
-      lb_dcstep(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
-      fx = fxm + stx * gtest; fy = fym + sty * gtest; gx = gxm + gtest; gy = gym + gtest;
-    } else {
-      lb_dcstep(stx, fx, gx, sty, fy, gy, stp, f, g, brackt, stmin, stmax);
+    // stage 1 works on the modified function f - stp*gtest; one dcstep call site serves both forms
+    const bool modified = stage == 1 && f <= fx && f > ftest;
+    double fm = f, gm = g;
+    if (modified) {
+      fm = f - stp * gtest; fx = fx - stx * gtest; fy = fy - sty * gtest;
+      gm = g - gtest; gx = gx - gtest; gy = gy - gtest;
     }
+    lb_dcstep(stx, fx, gx, sty, fy, gy, stp, fm, gm, brackt, stmin, stmax);
+    if (modified) { fx = fx + stx * gtest; fy = fy + sty * gtest; gx = gx + gtest; gy = gy + gtest; }
     if (brackt) {
       if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
       width1 = width;

@@ -401,32 +401,26 @@ __device__ __forceinline__ bool near_valid(const NearList& N, double x, double y
   return dx * dx + dy * dy + dz * dz <= N.rho2;
 }
 
-// lanes stride over the kept atoms (optimiser objectives)
+// lanes stride over the kept atoms (optimiser objectives).  The list is short (the atoms lining one
+// window, typically 20-50), so one flat pass with a square root per atom beats the class-wise loops of
+// warp_min_clear: with one or two atoms per lane those were mostly loop overhead.  Same values, and min
+// does not care about the order.
 template <int K>
 __device__ __forceinline__ void warp_min_clear_near(const WarpAtoms& A, const NearList& N, const double* px,
                                                     const double* py, const double* pz, double* out) {
   double v[K];
 #pragma unroll
   for (int k = 0; k < K; k++) v[k] = PWB_INF;
-  for (int c = 0; c < A.ncls; c++) {
-    const int cb = N.cs[c], ce = N.cs[c + 1];
-    if (cb == ce) continue;
-    double m[K];
+  const int nn = N.cs[A.ncls];
+  for (int t = A.lane; t < nn; t += 32) {
+    const int i = N.idx[t];
+    const double4 q = A.p[i];
+    const double ri = A.r[i * A.rs];
 #pragma unroll
-    for (int k = 0; k < K; k++) m[k] = PWB_INF;
-    for (int t = cb + A.lane; t < ce; t += 32) {
-      const int i = N.idx[t];
-      const double4 q = A.p[i];
-      const double ax = q.x, ay = q.y, az = q.z;
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        double dx = ax - px[k], dy = ay - py[k], dz = az - pz[k];
-        m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
-      }
+    for (int k = 0; k < K; k++) {
+      const double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+      v[k] = dmin(v[k], sqrt(dx * dx + dy * dy + dz * dz) - ri);
     }
-    const double rc = A.r[A.cls[c] * A.rs];
-#pragma unroll
-    for (int k = 0; k < K; k++) v[k] = dmin(v[k], sqrt(m[k]) - rc);
   }
 #pragma unroll
   for (int k = 0; k < K; k++) out[k] = warp_min(v[k]);

@@ -1058,6 +1058,9 @@ k_cluster_big(pwb_batch b, Ws ws, int phase) {
 // k_windows: window_analysis (utilities.py:1191-1361), one warp per (item, window)
 // =================================================================================================
 constexpr int WIN_WARPS = 4;
+#ifndef WIN_TIGHT_RHO
+#define WIN_TIGHT_RHO 0.5
+#endif
 // doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage ring, even
 #define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + 2 * LB_M) + 1) & ~(size_t)1)
 
@@ -1073,7 +1076,19 @@ struct DevZObj {   // optimise_z, utilities.py:1174-1188
 };
 struct DevXYObj {  // optimise_xy, utilities.py:1164-1171
   WarpAtoms A; NearList N; double z;
+  // tight list: the <= 32 atoms that can attain the minimum within sqrt(trho2) of (tx, ty, z), one per
+  // lane, in registers.  Nelder-Mead rarely leaves that disc, so its objective is load-free.
+  double tx, ty, trho2, ax, ay, az, ar; bool have;
   __device__ double f2(double x, double y) {
+    const double ex = x - tx, ey = y - ty;
+    if (ex * ex + ey * ey <= trho2) {
+      double v = PWB_INF;
+      if (have) {
+        const double dx = ax - x, dy = ay - y, dz = az - z;
+        v = sqrt(dx * dx + dy * dy + dz * dz) - ar;
+      }
+      return -(warp_min(v) * 2.0);
+    }
     double m[1];
     if (near_valid(N, x, y, z)) warp_min_clear_near<1>(A, N, &x, &y, &z, m);
     else warp_min_clear<1>(A, &x, &y, &z, m);
@@ -1207,7 +1222,40 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
   const double x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo), y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
-  DevXYObj xo{A, NL, wz};
+  DevXYObj xo{A, NL, wz, x0, y0, -1.0, 0.0, 0.0, 0.0, 0.0, false};
+  {
+    // same 1-Lipschitz argument as warp_build_near, radius WIN_TIGHT_RHO around the grid optimum
+    unsigned short* tidx = (unsigned short*)(ncs + PWB_MAX_TYPES + 2);   // [32] scratch
+    double mc[1];
+    warp_min_clear_near<1>(A, NL, &x0, &y0, &wz, mc);
+    const double thr = mc[0] + 2.0 * WIN_TIGHT_RHO + 1e-9;
+    const int nn = NL.cs[A.ncls];
+    int pos = 0;
+    for (int base = 0; base < nn && pos <= 32; base += 32) {
+      const int t = base + lane;
+      bool keep = false; int i = 0;
+      if (t < nn) {
+        i = NL.idx[t];
+        const double4 q = p4[i];
+        const double dx = q.x - x0, dy = q.y - y0, dz = q.z - wz;
+        keep = sqrt(dx * dx + dy * dy + dz * dz) - r[i] <= thr;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      const int at = pos + __popc(mask & ((1u << lane) - 1u));
+      if (keep && at < 32) tidx[at] = (unsigned short)i;
+      pos += __popc(mask);
+    }
+    __syncwarp();
+    if (pos <= 32) {
+      const double re = WIN_TIGHT_RHO - 1e-6;
+      xo.trho2 = re * re;
+      if (lane < pos) {
+        const int i = tidx[lane];
+        const double4 q = p4[i];
+        xo.ax = q.x; xo.ay = q.y; xo.az = q.z; xo.ar = r[i]; xo.have = true;
+      }
+    }
+  }
   double xy[2], fxy; int nfev;
   nelder_mead2(xo, x0, y0, 1e-4, 1e-4, 400, 400, xy, &fxy, &nfev);
   double mf[1];
