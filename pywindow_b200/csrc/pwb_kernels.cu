@@ -53,7 +53,10 @@ __device__ __noinline__ ValIdx rare_pair_max(ValIdx mb, double d2, double rr, in
   return vi_max(mb, c);
 }
 
-__global__ void __launch_bounds__(PREP_THREADS)
+#ifndef PREP_MINB
+#define PREP_MINB 4
+#endif
+__global__ void __launch_bounds__(PREP_THREADS, PREP_MINB)
 k_prepare(pwb_batch b, Ws ws, int do_avg) {
   extern __shared__ double sm[];
   const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -122,27 +125,59 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   mx = block_sum(mx, red); my = block_sum(my, red); mz = block_sum(mz, red); mt = block_sum(mt, red);
   const double cx = mx / mt, cy = my / mt, cz = mz / mt;
   // ---- pore diameter at the centre of mass (utilities.py:375-388)
+  // rho_a = |x_a - com| + r_a (kept in sw: the masses are done with) bounds every pair: d_ij + r_i + r_j
+  // <= rho_i + rho_j.
   ValIdx pb; pb.v = PWB_INF; pb.i = 0x7fffffff;
+  ValIdx fa; fa.v = -PWB_INF; fa.i = 0x7fffffff;
+  __syncthreads();                      // everyone has read the masses in sw
   for (int a = tid; a < n; a += nt) {
     double dx = sx[a] - cx, dy = sy[a] - cy, dz = sz[a] - cz;
-    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - sr[a]; c.i = a;
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    ValIdx c; c.v = d - sr[a]; c.i = a;
     pb = vi_min(pb, c);
+    c.v = d + sr[a]; sw[a] = c.v;
+    fa = vi_max(fa, c);
   }
   pb = block_vi(pb, false, red, redi);
+  fa = block_vi(fa, true, red, redi);   // outermost atom
   // ---- maximum dimension (utilities.py:355-372): upper triangle incl. diagonal, first arg-max.
-  // Row i is spread over the block (j = i + tid); the sqrt is only taken when the pair can beat the
-  // thread's running maximum: d + ri + rj > best  <=>  d^2 > (best - ri - rj)^2 (guarded by 1e-12).
+  // Exact pruning: the outermost atom and its farthest partner give a lower bound LB; an atom with
+  // rho_i + rho_max < LB cannot be part of a maximal pair.  For a cage that leaves the outer shell
+  // (~1/4 of the atoms, 1/16 of the pairs).  Among the kept pairs the sqrt is only taken when the pair
+  // can beat the thread's running maximum: d + ri + rj > best <=> d^2 > (best - ri - rj)^2.
   ValIdx mb; mb.v = -PWB_INF; mb.i = 0x7fffffff;
   {
+    const double xi = sx[fa.i], yi = sy[fa.i], zi = sz[fa.i], ri = sr[fa.i];
+    for (int j = tid; j < n; j += nt) {
+      double dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
+      ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) + (ri + sr[j]);
+      c.i = fa.i <= j ? fa.i * n + j : j * n + fa.i;
+      mb = vi_max(mb, c);
+    }
+  }
+  mb = block_vi(mb, true, red, redi);
+  int* cand = stype;                    // the types are in the workspace by now; reuse as candidate list
+  __shared__ int s_ncand;
+  if (tid == 0) s_ncand = 0;
+  __syncthreads();
+  {
+    const double need = mb.v - fa.v - 1e-9;
+    for (int a = tid; a < n; a += nt) if (sw[a] >= need) cand[atomicAdd(&s_ncand, 1)] = a;
+  }
+  __syncthreads();
+  {
+    const int m = s_ncand;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    for (int i = wid; i < n; i += nw) {
+    for (int u = wid; u < m; u += nw) {
+      const int i = cand[u];
       const double xi = sx[i], yi = sy[i], zi = sz[i], ri = sr[i];
-      for (int j = i + lane; j < n; j += 32) {
+      for (int v = u + lane; v < m; v += 32) {
+        const int j = cand[v];
         double dx = xi - sx[j], dy = yi - sy[j], dz = zi - sz[j];
         double d2 = dx * dx + dy * dy + dz * dz;
         double rr = ri + sr[j];
         double thr = (mb.v - rr) * (1.0 - 1e-12);
-        if (thr < 0 || d2 >= thr * thr) mb = rare_pair_max(mb, d2, rr, i * n + j);
+        if (thr < 0 || d2 >= thr * thr) mb = rare_pair_max(mb, d2, rr, i <= j ? i * n + j : j * n + i);
       }
     }
   }
@@ -386,7 +421,10 @@ __device__ __forceinline__ void ray_dir(int k, int P, double R, double& px, doub
   nr = sqrt(px * px + py * py + pz * pz);
 }
 
-__global__ void __launch_bounds__(RAY_THREADS)
+#ifndef RAY_MINB
+#define RAY_MINB 4
+#endif
+__global__ void __launch_bounds__(RAY_THREADS, RAY_MINB)
 k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   extern __shared__ double sm[];
   const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -1470,6 +1508,7 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   int ctas = (b->n_items + wpb - 1) / wpb;
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_opt_pore, wpb * 32, sm));
+  if (const char* e = getenv("PWB_OPT_CTAS_PER_SM")) { int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
   const int resident = c->num_sms * (per_sm > 0 ? per_sm : 1);
   if (ctas > resident) ctas = resident;
   k_opt_pore<<<ctas, wpb * 32, sm, s>>>(*b, w);
