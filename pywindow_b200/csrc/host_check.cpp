@@ -63,7 +63,7 @@ int pwbh_opt_pore(const double* X, const double* r, int n, const double* com, do
   if (pr < 0) return 1;
   PoreObj3 o{a, lo, hi, nbd, 0};
   double f; int nit;
-  double hist[2 * pwb::LB_M * 3];
+  double hist[LB_STORAGE(3)];
   int st = pwb::lbfgsb_minimize<3>(o, x, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &f, &nit, hist);
   out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = f; out[4] = nit; out[5] = st; out[6] = o.nfev;
   return 0;
@@ -75,7 +75,7 @@ int pwbh_opt_z(const double* X, const double* r, int n, double lb, double* out) 
   int nbd[1] = {1};
   ZObj1 o{a, lb, 0};
   double f; int nit;
-  double hist[2 * pwb::LB_M];
+  double hist[LB_STORAGE(1)];
   int st = pwb::lbfgsb_minimize<1>(o, x, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &f, &nit, hist);
   out[0] = x[0]; out[1] = f; out[2] = nit; out[3] = st; out[4] = o.nfev;
   return 0;

@@ -27,6 +27,8 @@
 namespace pwb {
 
 constexpr int LB_M = 10;
+// doubles of caller storage lbfgsb_minimize<N> needs: (s, y) ring, z / d / t / r, line-search record
+#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20)
 constexpr double LB_EPSMCH = 2.220446049250313e-16;
 constexpr double LB_FD_STEP = 1e-8;
 
@@ -162,6 +164,8 @@ struct LbLineSearch {
     return FG;
   }
 };
+
+static_assert(sizeof(LbLineSearch) <= 20 * sizeof(double), "LB_STORAGE reserves 20 doubles for the line-search record");
 
 // The (s, y) ring lives in caller-provided storage (2*LB_M*N doubles): shared memory on the device, so
 // the 32 lanes that run the optimiser redundantly share ONE copy instead of 32 local-memory copies.
@@ -411,7 +415,13 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
   double theta = 1.0;
   if (sbgnrm <= pgtol) { *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }
 
-  double z[N], d[N], t[N], r[N], B[N][N];
+  // Step vectors and the line-search record live in caller storage behind the (s, y) ring: on the
+  // device that is shared memory, ONE copy per warp.  As thread-local arrays they were spilled around
+  // every objective call, 32 copies per warp, and thrashed the small L1 left beside the atom tiles.
+  double* z = hist_storage + 2 * LB_M * N;
+  double* d = z + N; double* t = d + N; double* r = t + N;
+  LbLineSearch& ls = *reinterpret_cast<LbLineSearch*>(r + N);
+  double B[N][N];
   while (true) {
     lb_build_B<N>(H, theta, B);
     if (!cnstnd && H.col > 0) { for (int i = 0; i < N; i++) z[i] = x[i]; }
@@ -446,7 +456,6 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
     for (int i = 0; i < N; i++) { t[i] = x[i]; r[i] = g[i]; }
     double fold = f, gd = 0, gdold = 0;
     int ifun = 0, iback = 0, info = 0;
-    LbLineSearch ls;
     ls.ftol = 1e-3; ls.gtol = 0.9; ls.xtol = 0.1; ls.stpmin = 0; ls.stpmax = stpmx;
     bool started = false, newx = false;
     while (true) {
@@ -466,6 +475,9 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
       else { for (int i = 0; i < N; i++) x[i] = stp * d[i] + t[i]; }
       if (iback >= maxls) break;
       obj.fg(x, f, g);
+#ifdef __CUDA_ARCH__
+      __syncwarp();
+#endif
     }
     if (!newx) {
       for (int i = 0; i < N; i++) { x[i] = t[i]; g[i] = r[i]; }

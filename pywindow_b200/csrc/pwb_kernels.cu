@@ -325,7 +325,7 @@ struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-p
 #define OPT_MINB 8
 #endif
 // doubles of shared memory per warp: double4[NA] atoms, the L-BFGS ring, class starts (17 ints, padded), bounds
-#define OPT_WARP_DOUBLES(NA) ((NA) * 4 + 2 * LB_M * 3 + 10 + 6)
+#define OPT_WARP_DOUBLES(NA) ((NA) * 4 + LB_STORAGE(3) + 10 + 6)
 // one item on one warp; `smw` is the warp's private shared memory
 __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, const int item, const int lane, double* smw) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
@@ -334,8 +334,8 @@ __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, 
   if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
   double4* p4 = (double4*)smw;                                // x, y, z, radius
-  double* hist = (double*)(p4 + NA);                          // [2*LB_M*3] L-BFGS (s, y) ring, one copy per warp
-  int* cls = (int*)(hist + 2 * LB_M * 3);                     // [PWB_MAX_TYPES+1] class starts
+  double* hist = (double*)(p4 + NA);                          // [LB_STORAGE(3)] L-BFGS state, one copy per warp
+  int* cls = (int*)(hist + LB_STORAGE(3));                     // [PWB_MAX_TYPES+1] class starts
   if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -1100,7 +1100,7 @@ constexpr int WIN_WARPS = 4;
 #define WIN_TIGHT_RHO 0.5
 #endif
 // doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage ring, even
-#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + 2 * LB_M) + 1) & ~(size_t)1)
+#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + LB_STORAGE(1)) + 1) & ~(size_t)1)
 
 struct DevZObj {   // optimise_z, utilities.py:1174-1188
   WarpAtoms A; double lo;
@@ -1158,7 +1158,7 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
   int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
   unsigned short* nidx = (unsigned short*)(cr + PWB_MAX_TYPES + 32);   // [NA] near-list atom indices
-  double* hist = cr + PWB_MAX_TYPES + 32 + NAp / 4;                     // [2*LB_M] z-stage L-BFGS ring
+  double* hist = cr + PWB_MAX_TYPES + 32 + NAp / 4;                     // [LB_STORAGE(1)] z-stage L-BFGS state
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
