@@ -1141,7 +1141,7 @@ __device__ __forceinline__ double angle_between(double x0, double x1, double x2,
 }
 
 #ifndef WIN_MINB
-#define WIN_MINB 7
+#define WIN_MINB 6
 #endif
 // one (item, window) on one warp; `smw` is the warp's private shared memory (WIN_WARP_DOUBLES)
 __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, const int item, const int win,
