@@ -426,7 +426,7 @@ __device__ __forceinline__ void ray_dir(int k, int P, double R, double& px, doub
 #endif
 __global__ void __launch_bounds__(RAY_THREADS, RAY_MINB)
 k_rays(pwb_batch b, Ws ws, Ctx ctx) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
@@ -434,8 +434,8 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   const int status0 = iiv[I_STATUS];
   if (status0 & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS)) return;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* ax = sm; double* ay = ax + NA; double* az = ay + NA; double* aw = az + NA;   // shifted, bucketed, |x|^2
-  double* lx = aw + NA; double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
+  double4* ap = (double4*)sm;                 // [NA] shifted, bucketed atoms: x, y, z, |x|^2
+  double* lx = (double*)(ap + NA); double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
   double* red = lw + NA;                    // 64
   double* cr = red + 64;                    // [PWB_MAX_TYPES]
   double* sa = cr + PWB_MAX_TYPES;          // [RAY_ACAP] path clearances of the current sub-pass
@@ -462,13 +462,13 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   for (int a = tid; a < n; a += nt) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
     double x = q[0] - shx, y = q[1] - shy, z = q[2] - shz;
-    ax[a] = x; ay[a] = y; az[a] = z; aw[a] = x * x + y * y + z * z;
+    ap[a] = make_double4(x, y, z, x * x + y * y + z * z);
     lw[a] = q[3] * q[3];
     ox += x; oy += y; oz += z;
   }
   ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
   for (int a = tid; a < n; a += nt) {
-    double x = ax[a] - ox, y = ay[a] - oy, z = az[a] - oz;
+    double x = ap[a].x - ox, y = ap[a].y - oy, z = ap[a].z - oz;
     lx[a] = x; ly[a] = y; lz[a] = z;
   }
   __syncthreads();
@@ -560,30 +560,28 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     n_surv_total += nsurv;
     // ---- stepped path clearance (utilities.py:1100-1129).  The reference evaluates
     // a_j = min_i(|x_i - q_j| - r_i) at every step q_j = j*chunk and keeps min_j a_j, its first arg-min
-    // and "all a_j > 0".  For a fixed atom |x_i - q_j| is convex in j, so min_j is attained at one of the
-    // two steps bracketing the atom's projection: min_j min_i = min_i min_{j in {j0, j0+1}} -- 2 instead
-    // of chunks+1 evaluations per atom, same value, same arg-min (ties -> smaller j).
-    // |x - j*chunk|^2 = |x|^2 + j*(j*|chunk|^2 - 2 x.chunk).
+    // and "all a_j > 0".  For a fixed atom |x_i - q_j|^2 = |x|^2 + j*(j*|chunk|^2 - 2 x.chunk) is a
+    // parabola in j, so min_j is attained at the step nearest to the atom's projection (clamped to the
+    // path; an exact half-way projection takes the smaller step, the reference's first arg-min):
+    // min_j min_i = min_i d_i(j_i) -- ONE instead of chunks+1 evaluations per atom.
     for (int s = tid; s < nsurv; s += nt) {
       double px, py, pz, nr;
       ray_dir(surv[s], P, R, px, py, pz, nr);
       const int chunks = (int)py_floordiv(nr, b.increment);
       const double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
       const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
-      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0), gmax = cc * (jmax + 0.5);
+      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
       double bestv = PWB_INF, bestj = 0.0;
       for (int c = 0; c < b.n_types; c++) {
         const int cb = cls[c], ce = cls[c + 1];
         if (cb == ce) continue;
         double m = PWB_INF, mj = 0.0;
         for (int a = cb; a < ce; a++) {
-          const double g = fma(ax[a], cxs, fma(ay[a], cys, az[a] * czs));
-          const double gc = dmin(gmax, g > 0.0 ? g : 0.0);
-          const double j0 = floor(gc * icc), j1 = j0 + 1.0;
-          const double w = aw[a], g2 = -2.0 * g;
-          const double d0 = fma(j0, fma(j0, cc, g2), w), d1 = fma(j1, fma(j1, cc, g2), w);
-          const bool first = d0 <= d1;                       // ties -> smaller step
-          const double dm = first ? d0 : d1, jm = first ? j0 : j1;
+          const double4 q = ap[a];
+          const double g = fma(q.x, cxs, fma(q.y, cys, q.z * czs));
+          double jm = ceil(fma(g, icc, -0.5));               // nearest step to the projection, ties -> smaller
+          jm = dmin(jmax, jm > 0.0 ? jm : 0.0);
+          const double dm = fma(jm, fma(jm, cc, -2.0 * g), q.w);
           if (dm < m) { m = dm; mj = jm; }
         }
         const double v = sqrt(fmax(m, 0.0)) - cr[c];
