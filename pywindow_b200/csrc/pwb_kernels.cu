@@ -1097,8 +1097,9 @@ constexpr int WIN_WARPS = 4;
 #ifndef WIN_TIGHT_RHO
 #define WIN_TIGHT_RHO 0.5
 #endif
-// doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage ring, even
-#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + LB_STORAGE(1)) + 1) & ~(size_t)1)
+// doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage state +
+// coarse grid values and candidate list (100 + 76), even
+#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + LB_STORAGE(1) + 176) + 1) & ~(size_t)1)
 
 struct DevZObj {   // optimise_z, utilities.py:1174-1188
   WarpAtoms A; double lo;
@@ -1241,19 +1242,60 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   // only atoms that can touch a sphere centred within the grid square (+ slack for the simplex) matter
   NearList NL; NL.idx = nidx; NL.cs = ncs;
   warp_build_near(A, NL, 0.0, 0.0, wz, fabs(d0) * 0.7071067811865476 + 0.25);
+  // Exact branch and bound over the 400 grid points.  The clearance is 1-Lipschitz, so after the coarse
+  // 10 x 10 sub-lattice (even ix, iy) has been evaluated, a remaining point can only reach the best
+  // coarse value c* if its even-even neighbour (at most gstep*sqrt(2) away) has clearance >= c* minus
+  // that distance.  Only those candidates (the cap of the clearance cone, typically 20-40 points) are
+  // evaluated; every evaluated value is computed exactly as before and the arg-min rule (value, then
+  // row-major index) does not depend on the evaluation order.
+  double* cgrid = hist + LB_STORAGE(1);                        // [100] coarse clearances
+  unsigned short* clist = (unsigned short*)(cgrid + 100);      // [300] candidate grid indices
   ValIdx gb; gb.v = PWB_INF; gb.i = 0x7fffffff;
-  for (int g = lane; g < 400; g += 64) {
+  int nwork = 128;                                             // slots 0..127: coarse points (100 used)
+  bool built = false;
+  for (int base = 0; base < nwork || !built; base += 64) {
+    if (base >= 128 && !built) {
+      built = true;
+      __syncwarp();
+      const double cstar = -(warp_vi_min(gb).v) * 0.5;
+      int pos = 0;
+      for (int g0 = 0; g0 < 400; g0 += 32) {
+        const int g = g0 + lane;
+        bool cand = false;
+        if (g < 400) {
+          const int ix = g / 20, iy = g - ix * 20;
+          const int odd = (ix & 1) + (iy & 1);
+          if (odd) {
+            const double reach = fabs(gstep) * (odd == 2 ? 1.4142135623730951 : 1.0);
+            cand = cgrid[(ix >> 1) * 10 + (iy >> 1)] + reach * (1.0 + 1e-12) + 1e-9 >= cstar;
+          }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, cand);
+        if (cand) clist[pos + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)g;
+        pos += __popc(mask);
+      }
+      __syncwarp();
+      nwork = 128 + pos;
+      if (base >= nwork) break;
+    }
     double gxp[2], gyp[2], gzp[2] = {wz, wz}, gv[2];
+    int gi[2];
 #pragma unroll
     for (int v = 0; v < 2; v++) {
-      int gg = min(g + 32 * v, 399);
-      int ix = gg / 20, iy = gg - ix * 20;
+      const int t = base + lane + 32 * v;
+      if (t < 128) { const int c = min(t, 99), cx = c / 10; gi[v] = cx * 40 + (c - cx * 10) * 2; }
+      else gi[v] = clist[min(t, nwork - 1) - 128];
+      const int ix = gi[v] / 20, iy = gi[v] - ix * 20;
       gxp[v] = __dadd_rn(__dmul_rn((double)ix, gstep), glo); gyp[v] = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
     }
     min_clearance_k_near<2>(B, NL, gxp, gyp, gzp, gv);
-    ValIdx c; c.v = -(gv[0] * 2.0); c.i = g;
-    gb = vi_min(gb, c);
-    if (g + 32 < 400) { c.v = -(gv[1] * 2.0); c.i = g + 32; gb = vi_min(gb, c); }
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+      const int t = base + lane + 32 * v;
+      if (t < 100) cgrid[t] = gv[v];
+      ValIdx c; c.v = -(gv[v] * 2.0); c.i = gi[v];
+      gb = vi_min(gb, c);
+    }
   }
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
