@@ -11,20 +11,9 @@
 
 namespace pwb {
 
-struct Nm2Sort {
-  // stable insertion sort of three (f, x, y) vertices by f ascending
-  PWB_HD static void sort3(double* f, double (*s)[2]) {
-    for (int i = 1; i < 3; i++) {
-      double fi = f[i], xi = s[i][0], yi = s[i][1];
-      int j = i - 1;
-      while (j >= 0 && f[j] > fi) {
-        f[j + 1] = f[j]; s[j + 1][0] = s[j][0]; s[j + 1][1] = s[j][1];
-        j--;
-      }
-      f[j + 1] = fi; s[j + 1][0] = xi; s[j + 1][1] = yi;
-    }
-  }
-};
+// stable ascending sort of three (f, x, y) vertices -- the insertion sort scipy's np.argsort(kind=stable)
+// amounts to for three elements -- on scalars, so the simplex stays in registers on the device
+#define PWB_NM_SWAP(a, b) { double t_; t_ = f##a; f##a = f##b; f##b = t_; t_ = x##a; x##a = x##b; x##b = t_; t_ = y##a; y##a = y##b; y##b = t_; }
 
 // Obj must provide: double f2(double x, double y)   (warp-cooperative on device)
 //
@@ -33,82 +22,82 @@ struct Nm2Sort {
 // contraction / shrink branch) multiplies that by nine in a kernel that already misses in the
 // instruction cache.  The sequence of evaluations and comparisons is scipy's, unchanged.
 template <class Obj>
-PWB_HDN void nelder_mead2(Obj& obj, double x0, double y0, double xatol, double fatol, int maxiter, int maxfun,
+PWB_HDN void nelder_mead2(Obj& obj, double xs, double ys, double xatol, double fatol, int maxiter, int maxfun,
                           double* xy_out, double* f_out, int* nfev_out) {
   enum { INIT, REFLECT, EXPAND, CONTRACT_OUT, CONTRACT_IN, SHRINK };
-  double sim[3][2], fs[3];
-  sim[0][0] = x0; sim[0][1] = y0;
-  sim[1][0] = (x0 != 0) ? (1 + 0.05) * x0 : 0.00025; sim[1][1] = y0;
-  sim[2][0] = x0; sim[2][1] = (y0 != 0) ? (1 + 0.05) * y0 : 0.00025;
+  double x0 = xs, y0 = ys, f0 = 0;                              // vertex 0 (best after sorting)
+  double x1 = (xs != 0) ? (1 + 0.05) * xs : 0.00025, y1 = ys, f1 = 0;
+  double x2 = xs, y2 = (ys != 0) ? (1 + 0.05) * ys : 0.00025, f2 = 0;
   int fcalls = 0, iterations = 0, st = INIT, k = 0;
-  double tx = sim[0][0], ty = sim[0][1];
+  double tx = x0, ty = y0;
   double xb0 = 0, xb1 = 0, xr0 = 0, xr1 = 0, fxr = 0;
   for (;;) {
     const double fv = obj.f2(tx, ty); fcalls++;
     bool end_iter = false, aborted = false, shrink = false;
     if (st == INIT) {
-      if (k == 0) fs[0] = fv; else if (k == 1) fs[1] = fv; else fs[2] = fv;
+      if (k == 0) f0 = fv; else if (k == 1) f1 = fv; else f2 = fv;
       k++;
-      if (k == 1) { tx = sim[1][0]; ty = sim[1][1]; }
-      else if (k == 2) { tx = sim[2][0]; ty = sim[2][1]; }
+      if (k == 1) { tx = x1; ty = y1; }
+      else if (k == 2) { tx = x2; ty = y2; }
       else { iterations = 0; end_iter = true; }          // falls into the sort + loop head below
     } else if (st == REFLECT) {
       fxr = fv;
-      if (fxr < fs[0]) {
+      if (fxr < f0) {
         if (fcalls >= maxfun) { aborted = true; end_iter = true; }
-        else { tx = (1 + 2.0) * xb0 - 2.0 * sim[2][0]; ty = (1 + 2.0) * xb1 - 2.0 * sim[2][1]; st = EXPAND; }
-      } else if (fxr < fs[1]) {
-        sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr; end_iter = true;
+        else { tx = (1 + 2.0) * xb0 - 2.0 * x2; ty = (1 + 2.0) * xb1 - 2.0 * y2; st = EXPAND; }
+      } else if (fxr < f1) {
+        x2 = xr0; y2 = xr1; f2 = fxr; end_iter = true;
       } else if (fcalls >= maxfun) { aborted = true; end_iter = true; }
-      else if (fxr < fs[2]) {
-        tx = (1 + 0.5) * xb0 - 0.5 * sim[2][0]; ty = (1 + 0.5) * xb1 - 0.5 * sim[2][1]; st = CONTRACT_OUT;
+      else if (fxr < f2) {
+        tx = (1 + 0.5) * xb0 - 0.5 * x2; ty = (1 + 0.5) * xb1 - 0.5 * y2; st = CONTRACT_OUT;
       } else {
-        tx = (1 - 0.5) * xb0 + 0.5 * sim[2][0]; ty = (1 - 0.5) * xb1 + 0.5 * sim[2][1]; st = CONTRACT_IN;
+        tx = (1 - 0.5) * xb0 + 0.5 * x2; ty = (1 - 0.5) * xb1 + 0.5 * y2; st = CONTRACT_IN;
       }
     } else if (st == EXPAND) {
-      if (fv < fxr) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; }
-      else { sim[2][0] = xr0; sim[2][1] = xr1; fs[2] = fxr; }
+      if (fv < fxr) { x2 = tx; y2 = ty; f2 = fv; }
+      else { x2 = xr0; y2 = xr1; f2 = fxr; }
       end_iter = true;
     } else if (st == CONTRACT_OUT) {
-      if (fv <= fxr) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; end_iter = true; }
+      if (fv <= fxr) { x2 = tx; y2 = ty; f2 = fv; end_iter = true; }
       else shrink = true;
     } else if (st == CONTRACT_IN) {
-      if (fv < fs[2]) { sim[2][0] = tx; sim[2][1] = ty; fs[2] = fv; end_iter = true; }
+      if (fv < f2) { x2 = tx; y2 = ty; f2 = fv; end_iter = true; }
       else shrink = true;
     } else {   // SHRINK: vertex k was just evaluated
-      if (k == 1) fs[1] = fv; else fs[2] = fv;
+      if (k == 1) f1 = fv; else f2 = fv;
       k++;
       if (k == 3) end_iter = true;
       else if (fcalls >= maxfun) { aborted = true; end_iter = true; }
       else {
-        sim[2][0] = sim[0][0] + 0.5 * (sim[2][0] - sim[0][0]);
-        sim[2][1] = sim[0][1] + 0.5 * (sim[2][1] - sim[0][1]);
-        tx = sim[2][0]; ty = sim[2][1];
+        x2 = x0 + 0.5 * (x2 - x0);
+        y2 = y0 + 0.5 * (y2 - y0);
+        tx = x2; ty = y2;
       }
     }
     if (shrink) {
       if (fcalls >= maxfun) { aborted = true; end_iter = true; }
       else {
-        sim[1][0] = sim[0][0] + 0.5 * (sim[1][0] - sim[0][0]);
-        sim[1][1] = sim[0][1] + 0.5 * (sim[1][1] - sim[0][1]);
-        tx = sim[1][0]; ty = sim[1][1]; k = 1; st = SHRINK;
+        x1 = x0 + 0.5 * (x1 - x0);
+        y1 = y0 + 0.5 * (y1 - y0);
+        tx = x1; ty = y1; k = 1; st = SHRINK;
       }
     }
     if (!end_iter) continue;
     if (!aborted) iterations++;
-    Nm2Sort::sort3(fs, sim);
+    if (f0 > f1) PWB_NM_SWAP(0, 1)
+    if (f1 > f2) { PWB_NM_SWAP(1, 2) if (f0 > f1) PWB_NM_SWAP(0, 1) }
     if (!(fcalls < maxfun && iterations < maxiter)) break;
-    double dx = fmax(fmax(fabs(sim[1][0] - sim[0][0]), fabs(sim[1][1] - sim[0][1])),
-                     fmax(fabs(sim[2][0] - sim[0][0]), fabs(sim[2][1] - sim[0][1])));
-    double df = fmax(fabs(fs[0] - fs[1]), fabs(fs[0] - fs[2]));
+    double dx = fmax(fmax(fabs(x1 - x0), fabs(y1 - y0)), fmax(fabs(x2 - x0), fabs(y2 - y0)));
+    double df = fmax(fabs(f0 - f1), fabs(f0 - f2));
     if (dx <= xatol && df <= fatol) break;
-    xb0 = (sim[0][0] + sim[1][0]) / 2; xb1 = (sim[0][1] + sim[1][1]) / 2;
-    xr0 = (1 + 1.0) * xb0 - 1.0 * sim[2][0]; xr1 = (1 + 1.0) * xb1 - 1.0 * sim[2][1];
+    xb0 = (x0 + x1) / 2; xb1 = (y0 + y1) / 2;
+    xr0 = (1 + 1.0) * xb0 - 1.0 * x2; xr1 = (1 + 1.0) * xb1 - 1.0 * y2;
     tx = xr0; ty = xr1; st = REFLECT;
   }
-  xy_out[0] = sim[0][0]; xy_out[1] = sim[0][1];
-  *f_out = fmin(fs[0], fmin(fs[1], fs[2]));
+  xy_out[0] = x0; xy_out[1] = y0;
+  *f_out = fmin(f0, fmin(f1, f2));
   *nfev_out = fcalls;
 }
+#undef PWB_NM_SWAP
 
 }  // namespace pwb
