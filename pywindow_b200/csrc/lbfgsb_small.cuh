@@ -28,7 +28,8 @@ namespace pwb {
 
 constexpr int LB_M = 10;
 // doubles of caller storage lbfgsb_minimize<N> needs: (s, y) ring, z / d / t / r, line-search record
-#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20)
+// and the small work arrays of the Cauchy / subspace steps (x, g, iwhere: 3N; B: N*N; scratch: 4N + 3N*N)
+#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20 + 7 * (N) + 4 * (N) * (N))
 constexpr double LB_EPSMCH = 2.220446049250313e-16;
 constexpr double LB_FD_STEP = 1e-8;
 
@@ -178,7 +179,8 @@ struct LbHistory {
 
 // B = theta*I, then BFGS updates with the stored pairs (oldest -> newest).
 template <int N>
-PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double (&B)[N][N]) {
+PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double* Bm) {
+  double B[N][N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) B[i][j] = (i == j) ? theta : 0.0;
   for (int k = 0; k < H.col; k++) {
@@ -194,31 +196,32 @@ PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double (&B)[N][N]) {
     for (int i = 0; i < N; i++)
       for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] * iys - Bs[i] * Bs[j] * isBs;
   }
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) Bm[i * N + j] = B[i][j];
 }
 
 // Solve A d = b for the leading nf x nf SPD system by Cholesky; false if not positive definite.
 template <int N>
-PWB_HD bool lb_spd_solve(int nf, double (&A)[N][N], double* b) {
-  double Lm[N][N];
+PWB_HD bool lb_spd_solve(int nf, const double* A, double* b, double* Lm) {   // A, Lm: [N][N] row-major
   for (int i = 0; i < nf; i++) {
     for (int j = 0; j <= i; j++) {
-      double s = A[i][j];
-      for (int k = 0; k < j; k++) s -= Lm[i][k] * Lm[j][k];
+      double s = A[i * N + j];
+      for (int k = 0; k < j; k++) s -= Lm[i * N + k] * Lm[j * N + k];
       if (i == j) {
         if (!(s > 0)) return false;
-        Lm[i][i] = sqrt(s);
-      } else Lm[i][j] = s / Lm[j][j];
+        Lm[i * N + i] = sqrt(s);
+      } else Lm[i * N + j] = s / Lm[j * N + j];
     }
   }
   for (int i = 0; i < nf; i++) {
     double s = b[i];
-    for (int k = 0; k < i; k++) s -= Lm[i][k] * b[k];
-    b[i] = s / Lm[i][i];
+    for (int k = 0; k < i; k++) s -= Lm[i * N + k] * b[k];
+    b[i] = s / Lm[i * N + i];
   }
   for (int i = nf - 1; i >= 0; i--) {
     double s = b[i];
-    for (int k = i + 1; k < nf; k++) s -= Lm[k][i] * b[k];
-    b[i] = s / Lm[i][i];
+    for (int k = i + 1; k < nf; k++) s -= Lm[k * N + i] * b[k];
+    b[i] = s / Lm[i * N + i];
   }
   return true;
 }
@@ -240,13 +243,14 @@ PWB_HD double lb_projgr(const double* x, const double* g, const double* lo, cons
 // Generalized Cauchy point along the projected steepest-descent path (cauchy in L-BFGS-B 3.0).
 template <int N>
 PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const int* nbd, const double* g,
-                      int* iwhere, const double (&B)[N][N], double theta, double sbgnrm, double* z) {
+                      int* iwhere, const double* B, double theta, double sbgnrm, double* z, double* scratch) {
   for (int i = 0; i < N; i++) z[i] = x[i];
   if (sbgnrm <= 0) return;
   bool bnded = true;
   int nbreak = 0, nunb = 0;
-  double d[N], tb[N];
-  bool isb[N], fixed[N];
+  // work arrays in caller storage: they are indexed by the run-time break-point index
+  double* d = scratch; double* tb = d + N; double* zz = tb + N; double* Bz = zz + N;
+  int* isb = reinterpret_cast<int*>(Bz + N); int* fixed = isb + N;
   double f1 = 0;
   for (int i = 0; i < N; i++) {
     double neggi = -g[i], tl = 0, tu = 0;
@@ -273,7 +277,7 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
   double f2_org = -theta * f1;
   double f2 = 0;
   for (int i = 0; i < N; i++)
-    for (int j = 0; j < N; j++) f2 += d[i] * B[i][j] * d[j];
+    for (int j = 0; j < N; j++) f2 += d[i] * B[i * N + j] * d[j];
   double dtm = -f1 / f2, tsum = 0;
   if (nbreak > 0) {
     int nleft = nbreak;
@@ -295,12 +299,11 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
       if (dibp > 0) { z[ibp] = hi[ibp]; iwhere[ibp] = 2; }
       else { z[ibp] = lo[ibp]; iwhere[ibp] = 1; }
       if (nleft == 0 && nbreak == N) return;   // every variable sits on a bound
-      double zz[N], Bz[N];
       for (int i = 0; i < N; i++) zz[i] = fixed[i] ? z[i] - x[i] : tsum * d[i];
       f1 = 0; f2 = 0;
       for (int i = 0; i < N; i++) {
         double a = 0, b = 0;
-        for (int j = 0; j < N; j++) { a += B[i][j] * zz[j]; b += B[i][j] * d[j]; }
+        for (int j = 0; j < N; j++) { a += B[i * N + j] * zz[j]; b += B[i * N + j] * d[j]; }
         Bz[i] = a;
         f1 += d[i] * (g[i] + Bz[i]);
         f2 += d[i] * b;
@@ -322,21 +325,21 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
 // Returns false if the reduced Hessian is not positive definite (caller refreshes the memory).
 template <int N>
 PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const double* hi, const int* nbd,
-                     const int* iwhere, const double (&B)[N][N], double* z) {
-  int ind[N], nf = 0;
+                     const int* iwhere, const double* B, double* z, double* scratch) {
+  double* zx = scratch; double* rr = zx + N; double* xp = rr + N; double* A = xp + N; double* Lm = A + N * N;
+  int* ind = reinterpret_cast<int*>(Lm + N * N);
+  int nf = 0;
   for (int i = 0; i < N; i++) if (iwhere[i] <= 0) ind[nf++] = i;
   if (nf == 0) return true;
-  double zx[N], rr[N], A[N][N];
   for (int i = 0; i < N; i++) zx[i] = z[i] - x[i];
   for (int a = 0; a < nf; a++) {
     int i = ind[a];
     double s = g[i];
-    for (int j = 0; j < N; j++) s += B[i][j] * zx[j];
+    for (int j = 0; j < N; j++) s += B[i * N + j] * zx[j];
     rr[a] = -s;
-    for (int b = 0; b < nf; b++) A[a][b] = B[i][ind[b]];
+    for (int b = 0; b < nf; b++) A[a * N + b] = B[i * N + ind[b]];
   }
-  if (!lb_spd_solve<N>(nf, A, rr)) return false;   // rr now holds d on the free set
-  double xp[N];
+  if (!lb_spd_solve<N>(nf, A, rr, Lm)) return false;   // rr now holds d on the free set
   for (int i = 0; i < N; i++) xp[i] = z[i];
   bool iword = false;
   for (int a = 0; a < nf; a++) {
@@ -390,8 +393,17 @@ template <int N, class Obj, int NBD = -1>
 PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd_in,
                             double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out,
                             double* hist_storage) {
-  double g[N], f;
-  int iwhere[N], nbd[N];
+  // x, g, iwhere and B are indexed by run-time variable numbers in the Cauchy / subspace steps; as
+  // thread-local arrays that forces them into local memory, so they live in caller storage too
+  double* const store = hist_storage + 2 * LB_M * N + 4 * N + 20;
+  double* const xs = store; double* g = xs + N; double* B = g + N;
+  int* iwhere = reinterpret_cast<int*>(B + N * N);
+  double* const scratch = B + N * N + N;                       // [4N + 3N*N]: cauchy / subsm work arrays
+  double* const x_out = x;
+  for (int i = 0; i < N; i++) xs[i] = x[i];
+  x = xs;
+  double f;
+  int nbd[N];
   for (int i = 0; i < N; i++) nbd[i] = NBD >= 0 ? NBD : nbd_in[i];
   bool cnstnd = false, boxed = true;
   for (int i = 0; i < N; i++) {
@@ -413,7 +425,7 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
   H.Y = reinterpret_cast<double (*)[N]>(hist_storage + LB_M * N);
   H.col = 0; H.head = 0;
   double theta = 1.0;
-  if (sbgnrm <= pgtol) { *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }
+  if (sbgnrm <= pgtol) { for (int i = 0; i < N; i++) x_out[i] = x[i]; *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }
 
   // Step vectors and the line-search record live in caller storage behind the (s, y) ring: on the
   // device that is shared memory, ONE copy per warp.  As thread-local arrays they were spilled around
@@ -421,15 +433,14 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
   double* z = hist_storage + 2 * LB_M * N;
   double* d = z + N; double* t = d + N; double* r = t + N;
   LbLineSearch& ls = *reinterpret_cast<LbLineSearch*>(r + N);
-  double B[N][N];
   while (true) {
     lb_build_B<N>(H, theta, B);
     if (!cnstnd && H.col > 0) { for (int i = 0; i < N; i++) z[i] = x[i]; }
-    else lb_cauchy<N>(x, lo, hi, nbd, g, iwhere, B, theta, sbgnrm, z);
+    else lb_cauchy<N>(x, lo, hi, nbd, g, iwhere, B, theta, sbgnrm, z, scratch);
     int nfree = 0;
     for (int i = 0; i < N; i++) if (iwhere[i] <= 0) nfree++;
     if (nfree != 0 && H.col != 0) {
-      if (!lb_subsm<N>(x, g, lo, hi, nbd, iwhere, B, z)) { H.col = 0; H.head = 0; theta = 1.0; continue; }
+      if (!lb_subsm<N>(x, g, lo, hi, nbd, iwhere, B, z, scratch)) { H.col = 0; H.head = 0; theta = 1.0; continue; }
     }
     // ---- line search (lnsrlb)
     double dtd = 0;
@@ -508,6 +519,7 @@ PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double*
     for (int i = 0; i < N; i++) { H.S[slot][i] = d[i]; H.Y[slot][i] = r[i]; }
     theta = rr / dr;
   }
+  for (int i = 0; i < N; i++) x_out[i] = x[i];
   *f_out = f;
   *nit_out = iter;
   return status;

@@ -325,7 +325,7 @@ struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-p
 #define OPT_MINB 8
 #endif
 // doubles of shared memory per warp: double4[NA] atoms, the L-BFGS ring, class starts (17 ints, padded), bounds
-#define OPT_WARP_DOUBLES(NA) ((NA) * 4 + LB_STORAGE(3) + 10 + 6)
+#define OPT_WARP_DOUBLES(NA) ((((NA) * 4 + LB_STORAGE(3) + 10 + 6) + 1) & ~(size_t)1)   // even: double4 tiles
 // one item on one warp; `smw` is the warp's private shared memory
 __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, const int item, const int lane, double* smw) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;

@@ -26,7 +26,8 @@ for ln in lines:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+\S", ln)
     if m:
         seq.append((int(m.group(1), 16), cur))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+skip = os.environ.get("NCU_SKIP", "0")
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--launch-skip", skip, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
