@@ -154,7 +154,7 @@ def run_reference(args):
     sample = (f"{per_step} frames/step x {args.steps} steps of the same synthetic CC3 workload; oracle port "
               "(batched numpy + the reference's own scipy optimiser calls), one process per core; the unmodified "
               "reference measured 0.39 frames/s/core in the build container (BASELINE.md)")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "frames/s full_analysis (CC3 traj)", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -368,12 +368,32 @@ def run_ours(args):
                          "sample": f"{n_cpu} frames of the same synthetic workload in {cpu_dt:.1f} s; oracle port "
                                    "(batched numpy + scipy optimisers), one process per core"},
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner from C
+# when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole run and the
+# line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

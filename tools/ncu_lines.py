@@ -7,7 +7,7 @@ rep, kern, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 sortcol = sys.argv[5] if len(sys.argv) > 5 else None
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "pywindow_b200", "csrc", "libpwb.so")
+so = os.environ.get("PWB_SO", os.path.join(root, "pywindow_b200", "csrc", "libpwb.so"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("pwb_kernels") and f.endswith(".cubin") and "periodic" not in f][0]

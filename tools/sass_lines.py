@@ -7,7 +7,7 @@ mangled = sys.argv[1]
 pat = re.compile(sys.argv[2] if len(sys.argv) > 2 else r"\b(LDL|STL)\b")
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "pywindow_b200", "csrc", "libpwb.so")
+so = os.environ.get("PWB_SO", os.path.join(root, "pywindow_b200", "csrc", "libpwb.so"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.startswith("pwb_kernels") and f.endswith(".cubin")][0]
