@@ -17,6 +17,7 @@ constexpr int D_COM = 0, D_MAXD = 3, D_CENTRE = 4, D_RADIUS = 7, D_EPS = 8, D_IC
 // item_i slots
 constexpr int I_STATUS = 0, I_P = 1, I_NSURV = 2, I_NCLEAR = 3, I_NWIN = 4, I_N = 5, I_CLS0 = 6;  // cls_start[17]
 constexpr int I_QUEUE = 26;  // (first item of a launch only) work-queue head of k_opt_pore
+constexpr int I_TILES_PREP = 28, I_TILES_RAYS = 29;   // CTAs of a multi-CTA item that have finished (self-resetting)
 constexpr int I_DEFER = 24;   // cluster stage deferred to the large-shared-memory pass
 
 constexpr double PWB_INF = 1e300;

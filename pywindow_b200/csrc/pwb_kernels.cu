@@ -44,6 +44,7 @@ struct Ctx {
 // k_prepare
 // =================================================================================================
 constexpr int PREP_THREADS = 256;
+constexpr int AVG_TILE = 1024;       // average-diameter rays per tile (4 per thread)
 
 // Rarely taken paths kept out of line so the compiler does not if-convert a double-precision sqrt
 // (~40 instructions) into the hot loops.
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(PREP_THREADS, PREP_MINB)
 k_prepare(pwb_batch b, Ws ws, int do_avg) {
   extern __shared__ double sm[];
   const int item = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  // blockIdx.y > 0: extra CTAs that only share the average-diameter rays of a huge item (see the tile loop)
+  const bool lead = blockIdx.y == 0;
   const int off = b.item_off[item];
   const int n = b.item_off[item + 1] - off;
   double* rec = b.records + (size_t)item * b.rec_stride;
@@ -84,7 +87,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   for (int c = tid; c <= PWB_MAX_TYPES; c += nt) cnt[c] = 0;
   __syncthreads();
   if (n <= 0 || n > NA) {
-    if (tid == 0) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
+    if (tid == 0 && lead) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
     return;
   }
   const int* tp = b.atom_type + (b.shared_types ? 0 : off);
@@ -100,18 +103,20 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   }
   __syncthreads();
   if (s_bad) {
-    if (tid == 0) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
+    if (tid == 0 && lead) { rec[PWB_REC_STATUS] = PWB_ST_BAD_ITEM; iiv[I_STATUS] = PWB_ST_BAD_ITEM; iiv[I_N] = 0; }
     return;
   }
   if (tid == 0) {
     for (int c = 1; c <= PWB_MAX_TYPES; c++) cnt[c] += cnt[c - 1];   // cnt[c] = start of class c
-    for (int c = 0; c <= PWB_MAX_TYPES; c++) iiv[I_CLS0 + c] = cnt[c < b.n_types ? c : b.n_types];
-    iiv[I_N] = n;
-    iiv[I_STATUS] = 0;
+    if (lead) {
+      for (int c = 0; c <= PWB_MAX_TYPES; c++) iiv[I_CLS0 + c] = cnt[c < b.n_types ? c : b.n_types];
+      iiv[I_N] = n;
+      iiv[I_STATUS] = 0;
+    }
   }
   __syncthreads();
   // stable bucket scatter to the workspace (x, y, z, r) + original index
-  for (int a = tid; a < n; a += nt) {
+  for (int a = tid; a < n && lead; a += nt) {
     int t = stype[a], rank = 0;
     for (int j = 0; j < a; j++) rank += (stype[j] == t);
     int pos = cnt[t] + rank;
@@ -183,7 +188,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   }
   mb = block_vi(mb, true, red, redi);
   const double D = mb.v;
-  if (tid == 0) {
+  if (tid == 0 && lead) {
     rec[PWB_REC_STATUS] = 0;
     rec[PWB_REC_NATOMS] = n;
     rec[PWB_REC_COM] = cx; rec[PWB_REC_COM + 1] = cy; rec[PWB_REC_COM + 2] = cz;
@@ -191,7 +196,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     rec[PWB_REC_PORE_D] = 2.0 * pb.v; rec[PWB_REC_PORE_ATOM] = pb.i;
     idv[D_COM] = cx; idv[D_COM + 1] = cy; idv[D_COM + 2] = cz; idv[D_MAXD] = D;
   }
-  if (!do_avg) return;
+  if (!do_avg) return;                  // (launched with gridDim.y = 1 then)
   // ---- average diameter (utilities.py:1586-1650, :1556-1583): sphere radius = D (not D/2).
   // Atom i counts for ray n iff r_i^2 - d_i^2 > 0 and |o+(t-h)n| < |o+(t+h)n| <=> t + o.n > 0; the exit
   // point is o + s n with s = t + sqrt(r_i^2 - d_i^2) and |o + s n| grows with s, so the farthest exit
@@ -244,9 +249,17 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   const double oo = ox * ox + oy * oy + oz * oz;
   dg_build(DG, sx, sy, sz, sr, n, sqrt(oo));
   const bool use_grid = *DG.overflow == 0;
+  // Rays are processed in tiles of AVG_TILE; the per-tile sums are added in tile order, so the result does
+  // not depend on how many CTAs (gridDim.y) share the tiles of one item.
+  const int ntiles = (P + AVG_TILE - 1) / AVG_TILE;
+  const bool solo = gridDim.y == 1 && ntiles == 1;
+  double* part = ws.clear_a2 + (size_t)item * b.ray_cap;     // [ntiles][2] partial sums (free until k_rays)
+  double acc_all = 0, hits_all = 0;
+  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+  const int base = tile * AVG_TILE, tend = min(P, base + AVG_TILE);
   double acc = 0, hits = 0;
   if (use_grid) {
-    for (int k = tid; k < P; k += nt) {
+    for (int k = base + tid; k < tend; k += nt) {
       double px, py, pz;
       spiral_point(k, P, D, px, py, pz);
       const double nr = sqrt(px * px + py * py + pz * pz);
@@ -265,7 +278,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     }
   } else {
   constexpr int RPT = 4;
-  for (int k0 = tid * RPT; k0 < P; k0 += nt * RPT) {
+  for (int k0 = base + tid * RPT; k0 < tend; k0 += nt * RPT) {
     double nx[RPT], ny[RPT], nz[RPT], on[RPT], sb[RPT];
 #pragma unroll
     for (int u = 0; u < RPT; u++) {
@@ -287,7 +300,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     }
 #pragma unroll
     for (int u = 0; u < RPT; u++) {
-      if (k0 + u < P && sb[u] > -PWB_INF) {
+      if (k0 + u < tend && sb[u] > -PWB_INF) {
         double s = sb[u];
         acc += sqrt(fma(s, s, fma(-2.0 * s, on[u], oo)));     // |o + s n|, o.n = -on
         hits += 1.0;
@@ -296,7 +309,28 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   }
   }
   acc = block_sum(acc, red); hits = block_sum(hits, red);
-  if (tid == 0) rec[PWB_REC_AVGD] = 2.0 * (acc / hits);
+  if (solo) { acc_all = acc; hits_all = hits; }
+  else if (tid == 0) { part[2 * tile] = acc; part[2 * tile + 1] = hits; }
+  }
+  if (!solo) {
+    // the last CTA of the item to arrive adds the tile sums in tile order
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      s_last = 1;
+      if (gridDim.y > 1) {
+        const int prev = atomicAdd(&iiv[I_TILES_PREP], 1);
+        s_last = prev == (int)gridDim.y - 1;
+        if (s_last) iiv[I_TILES_PREP] = 0;
+      }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) for (int t = 0; t < ntiles; t++) { acc_all += __ldcg(&part[2 * t]); hits_all += __ldcg(&part[2 * t + 1]); }
+  }
+  if (tid == 0) rec[PWB_REC_AVGD] = 2.0 * (acc_all / hits_all);
 }
 
 // =================================================================================================
@@ -433,6 +467,8 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   double* rec = b.records + (size_t)item * b.rec_stride;
   const int status0 = iiv[I_STATUS];
   if (status0 & (PWB_ST_BAD_ITEM | PWB_ST_OPT_BOUNDS)) return;
+  // blockIdx.y > 0: extra CTAs sharing the ray tiles of a huge item (config 5: 1e5 rays on one molecule)
+  const bool lead = blockIdx.y == 0;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
   double4* ap = (double4*)sm;                 // [NA] shifted, bucketed atoms: x, y, z, |x|^2
   double* lx = (double*)(ap + NA); double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
@@ -492,7 +528,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   const int P = n_sampling_points(R, b.adjust);
   __syncthreads();
   const bool use_grid = *DG.overflow == 0;
-  if (tid == 0) {
+  if (tid == 0 && lead) {
     idv[D_RADIUS] = R; idv[D_ICOM] = icx; idv[D_ICOM + 1] = icy; idv[D_ICOM + 2] = icz;
     idv[D_SHIFT] = shx; idv[D_SHIFT + 1] = shy; idv[D_SHIFT + 2] = shz;
     iiv[I_P] = P;
@@ -500,14 +536,21 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     if (P >= 2 && P < ctx.table_cap && P <= KNN_SMEM_CAP) ctx.knn_need[P] = 1;
   }
   if (P > b.ray_cap || (P <= KNN_SMEM_CAP && P >= ctx.table_cap) || P < 2) {
-    if (tid == 0) { iiv[I_STATUS] |= PWB_ST_RAY_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; iiv[I_NCLEAR] = 0; iiv[I_NSURV] = 0; }
+    if (tid == 0 && lead) { iiv[I_STATUS] |= PWB_ST_RAY_CAP; rec[PWB_REC_STATUS] = iiv[I_STATUS]; iiv[I_NCLEAR] = 0; iiv[I_NSURV] = 0; }
     return;
   }
   int* out_k = ws.clear_k + (size_t)item * b.ray_cap;
   int* out_pos = ws.clear_pos + (size_t)item * b.ray_cap;
   double* out_a2 = ws.clear_a2 + (size_t)item * b.ray_cap;
+  // Tiles of RAY_TILE rays; the clear rays of a tile are written at the tile's own offset (they fit: at most
+  // RAY_TILE of them) and, when an item has more than one tile, packed in tile order afterwards -- by
+  // whichever CTA of the item finishes last -- so the lists stay sorted by ray index whatever gridDim.y is.
+  const int ntiles = (P + RAY_TILE - 1) / RAY_TILE;
+  const bool solo = gridDim.y == 1 && ntiles == 1;
+  int* tile_cnt = ws.labels + (size_t)item * b.ray_cap;      // [ntiles] clear rays, [ntiles] survivors (free until k_cluster)
   int n_clear = 0, n_surv_total = 0;
-  for (int base = 0; base < P; base += RAY_TILE) {
+  for (int base = blockIdx.y * RAY_TILE; base < P; base += gridDim.y * RAY_TILE) {
+    n_clear = 0;
     // ---- pre-test (utilities.py:1132-1161), RAY_RPT consecutive rays per thread, branch free:
     // atom i counts iff r_i^2 - d_i^2 > 0 (d_i about the line through the centroid o) and
     // |o+(t-h)n| < |o+(t+h)n|  <=>  t + o.n > 0   (both norms expand to |o|^2+2s(o.n)+s^2, h > 0)
@@ -598,10 +641,43 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       int ok = (s < nsurv && spos[s] >= 0) ? 1 : 0;
       int tot;
       int oo = block_excl_scan(ok, wsum, tot);
-      if (ok) { out_k[n_clear + oo] = surv[s]; out_pos[n_clear + oo] = spos[s]; out_a2[n_clear + oo] = sa[s]; }
+      if (ok) { out_k[base + n_clear + oo] = surv[s]; out_pos[base + n_clear + oo] = spos[s]; out_a2[base + n_clear + oo] = sa[s]; }
       n_clear += tot;
     }
+    if (!solo && tid == 0) { tile_cnt[base / RAY_TILE] = n_clear; tile_cnt[ntiles + base / RAY_TILE] = nsurv; }
     __syncthreads();
+  }
+  if (!solo) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      s_last = 1;
+      if (gridDim.y > 1) {
+        const int prev = atomicAdd(&iiv[I_TILES_RAYS], 1);
+        s_last = prev == (int)gridDim.y - 1;
+        if (s_last) iiv[I_TILES_RAYS] = 0;
+      }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    n_clear = 0; n_surv_total = 0;
+    for (int t = 0; t < ntiles; t++) {
+      const int c = __ldcg(&tile_cnt[t]), src = t * RAY_TILE;
+      n_surv_total += __ldcg(&tile_cnt[ntiles + t]);
+      if (src != n_clear) {
+        for (int e0 = 0; e0 < c; e0 += nt) {               // dest <= src: read, barrier, write
+          const int e = e0 + tid;
+          int k = 0, ps = 0; double a2 = 0;
+          if (e < c) { k = __ldcg(&out_k[src + e]); ps = __ldcg(&out_pos[src + e]); a2 = __ldcg(&out_a2[src + e]); }
+          __syncthreads();
+          if (e < c) { out_k[n_clear + e] = k; out_pos[n_clear + e] = ps; out_a2[n_clear + e] = a2; }
+          __syncthreads();
+        }
+      }
+      n_clear += c;
+    }
   }
   if (tid == 0) {
     iiv[I_NCLEAR] = n_clear; iiv[I_NSURV] = n_surv_total;
@@ -1528,11 +1604,25 @@ static int check(const pwb_batch* b) {
   return 0;
 }
 
+// CTAs per item for the ray-tiled kernels: one for a batch that already fills the GPU, up to the number of ray
+// tiles when a few huge items (config 5: ~1e5 rays on one molecule) would otherwise run on a handful of SMs
+static int tile_ctas(const pwb_ctx* c, const pwb_batch* b, int tile) {
+  const int tiles = (b->ray_cap + tile - 1) / tile;
+  int want = (2 * c->num_sms) / (b->n_items > 0 ? b->n_items : 1);
+  if (want > tiles) want = tiles;
+  if (want > 128) want = 128;
+  return want < 1 ? 1 : want;
+}
 static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s, int do_avg) {
   size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + 64) + sizeof(int) * (64 + b->max_atoms + PWB_MAX_TYPES + 1 + DG_BINS + 2) +
               sizeof(unsigned short) * DG_BINS * DG_CAP;
   if (set_smem(k_prepare, sm, c->max_smem)) return 1;
-  k_prepare<<<b->n_items, PREP_THREADS, sm, s>>>(*b, w, do_avg);
+  const dim3 grid((unsigned)b->n_items, do_avg ? (unsigned)tile_ctas(c, b, AVG_TILE) : 1u);
+  // per-item "tiles done" counters of the multi-CTA paths (k_prepare average diameter, k_rays); self-resetting
+  // afterwards, only ever touched when an item is shared by several CTAs
+  if (tile_ctas(c, b, RAY_TILE) > 1)
+    CK(cudaMemset2DAsync(w.item_i + I_TILES_PREP, sizeof(int) * ITEM_I, 0, 2 * sizeof(int), (size_t)b->n_items, s));
+  k_prepare<<<grid, PREP_THREADS, sm, s>>>(*b, w, do_avg);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1560,7 +1650,8 @@ static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s)
   size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_ACAP) +
               sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE + DG_BINS + 2) + sizeof(unsigned short) * DG_BINS * DG_CAP;
   if (set_smem(k_rays, sm, c->max_smem)) return 1;
-  k_rays<<<b->n_items, RAY_THREADS, sm, s>>>(*b, w, c->c);
+  const dim3 grid((unsigned)b->n_items, (unsigned)tile_ctas(c, b, RAY_TILE));
+  k_rays<<<grid, RAY_THREADS, sm, s>>>(*b, w, c->c);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
