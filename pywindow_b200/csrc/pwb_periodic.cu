@@ -101,6 +101,174 @@ k_dm_prepare(DmArgs A) {
   }
 }
 
+// Periodic images of atom b bonded to atom a: the minimum image offset m0, then the offsets around it that can
+// be within the cut-off at all -- |delta f_c| <= |delta x| * |row c of inv(lattice)|, so an image needs
+// |df_c - m_c| <= tau_c on every axis; for ordinary cells that leaves at most the minimum image and rejects
+// > 99 % of the pairs after three subtractions.  Appends (image key << 20 | b) to list.
+__device__ __forceinline__ void dm_pair_images(const DmArgs& A, const double (&L)[9], double taux, double tauy, double tauz,
+                                               double max_dist, double ax, double ay, double az, double afx, double afy,
+                                               double afz, double rs, double bx, double by, double bz, double bfx,
+                                               double bfy, double bfz, int bb, unsigned* list, int& n, int& overflow) {
+  const double dfx = afx - bfx, dfy = afy - bfy, dfz = afz - bfz;
+  const double m0x = rint(dfx), m0y = rint(dfy), m0z = rint(dfz);
+  const double ex = dfx - m0x, ey = dfy - m0y, ez = dfz - m0z;
+  if (fabs(ex) - 1.0 > taux || fabs(ey) - 1.0 > tauy || fabs(ez) - 1.0 > tauz) return;
+  if (taux < 0.5 && tauy < 0.5 && tauz < 0.5 && (fabs(ex) > taux || fabs(ey) > tauy || fabs(ez) > tauz)) return;
+  for (int ia = -1; ia <= 1; ia++) {
+    if (fabs(ex - ia) > taux) continue;
+    for (int ib = -1; ib <= 1; ib++) {
+      if (fabs(ey - ib) > tauy) continue;
+      for (int ic = -1; ic <= 1; ic++) {
+        if (fabs(ez - ic) > tauz) continue;
+        const double ma = m0x + ia, mb = m0y + ib, mc = m0z + ic;
+        double X, Y, Z;
+        if (ma == 0 && mb == 0 && mc == 0) { X = bx; Y = by; Z = bz; }
+        else {
+          double fx = bfx + ma, fy = bfy + mb, fz = bfz + mc;
+          X = round8(L[0] * fx + L[1] * fy + L[2] * fz);
+          Y = round8(L[3] * fx + L[4] * fy + L[5] * fz);
+          Z = round8(L[6] * fx + L[7] * fy + L[8] * fz);
+        }
+        double dx = ax - X, dy = ay - Y, dz = az - Z;
+        double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 >= max_dist * max_dist) continue;
+        double d = sqrt(d2);
+        if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
+          int ka = (int)ma + 4, kb = (int)mb + 4, kc = (int)mc + 4;
+          if (ka < 0 || ka > 8 || kb < 0 || kb > 8 || kc < 0 || kc > 8) continue;   // > 4 cells away: unreachable
+          unsigned key = ((unsigned)(ka * 81 + kb * 9 + kc) << 20) | (unsigned)bb;
+          if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void dm_store_bonds(const DmArgs& A, int f, int a, unsigned* list, int n, int overflow) {
+  // sort by (image key, atom): ascending supercell index after translation
+  for (int i = 1; i < n; i++) {
+    unsigned v = list[i];
+    int j = i - 1;
+    while (j >= 0 && list[j] > v) { list[j + 1] = list[j]; j--; }
+    list[j + 1] = v;
+  }
+  unsigned* out = A.adj + ((size_t)f * A.N + a) * DM_ADJ_CAP;
+  for (int i = 0; i < n; i++) out[i] = list[i];
+  A.deg[(size_t)f * A.N + a] = n;
+  if (overflow) atomicOr(&A.status[f], 1);
+}
+
+// Bond table with a cell list (periodic + rebuild): one CTA per frame.  Atoms are binned by wrapped fractional
+// coordinates into G_c = floor(1 / tau_c) <= 16 bins per axis (tau_c = the largest fractional distance a bond
+// can span on axis c), so every bonded image of b lies in the 27 bins around a's; an axis too short for three
+// bins is not binned.  The pair test is dm_pair_images, unchanged, on ~20 candidates instead of N.
+constexpr int DM_CL_THREADS = 256, DM_CL_MAXG = 12;
+constexpr int DM_CL_NB = DM_CL_MAXG * DM_CL_MAXG * DM_CL_MAXG;
+// shared memory: bin starts + cursors, then the atoms SORTED BY BIN (7 doubles + index each), so that the
+// candidate loop streams contiguous shared memory instead of chasing indices through global memory
+#define DM_CL_SMEM(N) (sizeof(int) * (2 * DM_CL_NB + 2) + (size_t)(N) * (7 * sizeof(double) + sizeof(int)) + 16)
+__global__ void __launch_bounds__(DM_CL_THREADS, 2)
+k_dm_bonds_cells(DmArgs A, double max_dist) {
+  extern __shared__ __align__(16) double smd[];
+  const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, N = A.N;
+  double* qx = smd; double* qy = qx + N; double* qz = qy + N;           // rounded Cartesian
+  double* qfx = qz + N; double* qfy = qfx + N; double* qfz = qfy + N;    // fractional
+  double* qc = qfz + N;                                                  // covalent radius
+  int* qi = (int*)(qc + N);                                              // atom index
+  int* bstart = qi + N;                    // [NB + 1]
+  int* bcur = bstart + DM_CL_NB + 1;       // [NB]
+  __shared__ int G[3];
+  __shared__ double tau[3];
+  const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
+  const double* frac = A.frac + (size_t)f * N * 3;
+  const double* xr = A.xr + (size_t)f * N * 3;
+  double L[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) L[i] = fd[i];
+  if (tid < 3) {
+    const double md = max_dist + 1e-6;     // slack for the 8-decimal rounding of the coordinates
+    const double* r = fd + 9 + 3 * tid;
+    const double t = md * sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) * (1.0 + 1e-9);
+    tau[tid] = t;
+    int g = (int)floor(1.0 / (t * (1.0 + 1e-9) + 1e-12));
+    G[tid] = g < 3 ? 1 : (g > DM_CL_MAXG ? DM_CL_MAXG : g);
+  }
+  __syncthreads();
+  const int Gx = G[0], Gy = G[1], Gz = G[2], nb = Gx * Gy * Gz;
+  const double taux = tau[0], tauy = tau[1], tauz = tau[2];
+  for (int c = tid; c <= nb; c += nt) bstart[c] = 0;
+  __syncthreads();
+  auto bin_of = [&](double fx, double fy, double fz) {
+    const int bx = min(Gx - 1, max(0, (int)((fx - floor(fx)) * Gx)));
+    const int by = min(Gy - 1, max(0, (int)((fy - floor(fy)) * Gy)));
+    const int bz = min(Gz - 1, max(0, (int)((fz - floor(fz)) * Gz)));
+    return (bx * Gy + by) * Gz + bz;
+  };
+  for (int a = tid; a < N; a += nt) atomicAdd(&bstart[bin_of(frac[3 * a], frac[3 * a + 1], frac[3 * a + 2]) + 1], 1);
+  __syncthreads();
+  // inclusive scan of the counts: each thread owns a contiguous chunk, chunk totals scanned by one warp
+  {
+    __shared__ int csum[DM_CL_THREADS];
+    const int per = (nb + nt - 1) / nt, c0 = 1 + tid * per, c1 = min(nb + 1, c0 + per);
+    int t = 0;
+    for (int c = c0; c < c1; c++) t += bstart[c];
+    csum[tid] = t;
+    __syncthreads();
+    if (tid < 32) {
+      int carry = 0;
+      for (int base = 0; base < nt; base += 32) {
+        int v = csum[base + tid], x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
+        csum[base + tid] = carry + x - v;              // exclusive prefix of the chunk
+        carry += __shfl_sync(0xffffffffu, x, 31);
+      }
+    }
+    __syncthreads();
+    int run = csum[tid];
+    for (int c = c0; c < c1; c++) { run += bstart[c]; bstart[c] = run; }
+  }
+  __syncthreads();
+  for (int c = tid; c < nb; c += nt) bcur[c] = bstart[c];
+  __syncthreads();
+  for (int a = tid; a < N; a += nt) {
+    const double fx = frac[3 * a], fy = frac[3 * a + 1], fz = frac[3 * a + 2];
+    const int pos = atomicAdd(&bcur[bin_of(fx, fy, fz)], 1);
+    qfx[pos] = fx; qfy[pos] = fy; qfz[pos] = fz;
+    qx[pos] = xr[3 * a]; qy[pos] = xr[3 * a + 1]; qz[pos] = xr[3 * a + 2];
+    qc[pos] = A.type_cov[A.atom_type[a]];
+    qi[pos] = a;
+  }
+  __syncthreads();
+  // one thread per sorted slot: its own data is already in shared memory
+  for (int sa = tid; sa < N; sa += nt) {
+    const int a = qi[sa];
+    unsigned list[DM_ADJ_CAP];
+    int n = 0, overflow = 0;
+    if (!A.type_terminal[A.atom_type[a]]) {
+      const double ax = qx[sa], ay = qy[sa], az = qz[sa], afx = qfx[sa], afy = qfy[sa], afz = qfz[sa], acov = qc[sa];
+      const int bin = bin_of(afx, afy, afz);
+      const int bz = bin % Gz, by = (bin / Gz) % Gy, bx = bin / (Gz * Gy);
+      // (no unrolling: with the 27-image test inlined, unrolled bin loops made a 1.5 MB kernel that spent
+      // 92 % of its time waiting for instructions)
+#pragma unroll 1
+      for (int ox = (Gx > 1 ? -1 : 0); ox <= (Gx > 1 ? 1 : 0); ox++)
+#pragma unroll 1
+        for (int oy = (Gy > 1 ? -1 : 0); oy <= (Gy > 1 ? 1 : 0); oy++) {
+          const int cx = (bx + ox + Gx) % Gx, cy = (by + oy + Gy) % Gy;
+#pragma unroll 1
+          for (int oz = (Gz > 1 ? -1 : 0); oz <= (Gz > 1 ? 1 : 0); oz++) {
+            const int c = (cx * Gy + cy) * Gz + (bz + oz + Gz) % Gz;
+#pragma unroll 1
+            for (int t = bstart[c]; t < bstart[c + 1]; t++)
+              dm_pair_images(A, L, taux, tauy, tauz, max_dist, ax, ay, az, afx, afy, afz, acov + qc[t],
+                             qx[t], qy[t], qz[t], qfx[t], qfy[t], qfz[t], qi[t], list, n, overflow);
+          }
+        }
+    }
+    dm_store_bonds(A, f, a, list, n, overflow);
+  }
+}
+
 // bond table: one thread per (frame, parent atom); tiles of atoms staged in shared memory
 constexpr int DM_TILE = 128;
 __global__ void __launch_bounds__(DM_TILE)
@@ -152,57 +320,12 @@ k_dm_bonds(DmArgs A, double max_dist) {
         }
         continue;
       }
-      // minimum image offset m0, then the offsets around it that can be within the cut-off at all:
-      // |delta f_c| <= |delta x| * |row c of inv(lattice)|, so an image needs |df_c - m_c| <= tau_c on
-      // every axis; for ordinary cells that leaves at most the minimum image and rejects >99 % of the
-      // pairs after three subtractions.
-      const double dfx = afx - sfx[j], dfy = afy - sfy[j], dfz = afz - sfz[j];
-      const double m0x = rint(dfx), m0y = rint(dfy), m0z = rint(dfz);
-      const double ex = dfx - m0x, ey = dfy - m0y, ez = dfz - m0z;
-      if (fabs(ex) - 1.0 > taux || fabs(ey) - 1.0 > tauy || fabs(ez) - 1.0 > tauz) continue;
-      if (taux < 0.5 && tauy < 0.5 && tauz < 0.5 && (fabs(ex) > taux || fabs(ey) > tauy || fabs(ez) > tauz)) continue;
-      for (int ia = -1; ia <= 1; ia++) {
-        if (fabs(ex - ia) > taux) continue;
-        for (int ib = -1; ib <= 1; ib++) {
-          if (fabs(ey - ib) > tauy) continue;
-          for (int ic = -1; ic <= 1; ic++) {
-            if (fabs(ez - ic) > tauz) continue;
-            const double ma = m0x + ia, mb = m0y + ib, mc = m0z + ic;
-            double X, Y, Z;
-            if (ma == 0 && mb == 0 && mc == 0) { X = sx[j]; Y = sy[j]; Z = sz[j]; }
-            else {
-              double fx = sfx[j] + ma, fy = sfy[j] + mb, fz = sfz[j] + mc;
-              X = round8(L[0] * fx + L[1] * fy + L[2] * fz);
-              Y = round8(L[3] * fx + L[4] * fy + L[5] * fz);
-              Z = round8(L[6] * fx + L[7] * fy + L[8] * fz);
-            }
-            double dx = ax - X, dy = ay - Y, dz = az - Z;
-            double d2 = dx * dx + dy * dy + dz * dz;
-            if (d2 >= max_dist * max_dist) continue;
-            double d = sqrt(d2);
-            if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
-              int ka = (int)ma + 4, kb = (int)mb + 4, kc = (int)mc + 4;
-              if (ka < 0 || ka > 8 || kb < 0 || kb > 8 || kc < 0 || kc > 8) continue;   // > 4 cells away: unreachable
-              unsigned key = ((unsigned)(ka * 81 + kb * 9 + kc) << 20) | (unsigned)bb;
-              if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
-            }
-          }
-        }
-      }
+      dm_pair_images(A, L, taux, tauy, tauz, max_dist, ax, ay, az, afx, afy, afz, rs,
+                     sx[j], sy[j], sz[j], sfx[j], sfy[j], sfz[j], bb, list, n, overflow);
     }
   }
   if (a >= A.N) return;
-  // sort by (image key, atom): ascending supercell index after translation
-  for (int i = 1; i < n; i++) {
-    unsigned v = list[i];
-    int j = i - 1;
-    while (j >= 0 && list[j] > v) { list[j + 1] = list[j]; j--; }
-    list[j + 1] = v;
-  }
-  unsigned* out = A.adj + ((size_t)f * A.N + a) * DM_ADJ_CAP;
-  for (int i = 0; i < n; i++) out[i] = list[i];
-  A.deg[(size_t)f * A.N + a] = n;
-  if (overflow) atomicOr(&A.status[f], 1);
+  dm_store_bonds(A, f, a, list, n, overflow);
 }
 
 // flood fill: one warp per frame; lane 0 walks the graph, all lanes do the O(N) steps
@@ -396,8 +519,14 @@ int pwb_discrete_molecules(int F, int N, int rebuild, double tol, double max_cov
   A.rem = (unsigned char*)(p + L.rem); A.front = (int*)(p + L.front);
   A.n_mol = n_mol; A.mol_off = mol_off; A.out_src = out_src; A.out_xyz = out_xyz; A.status = status;
   k_dm_prepare<<<F, 128, 0, s>>>(A);
-  dim3 g((N + DM_TILE - 1) / DM_TILE, F);
-  k_dm_bonds<<<g, DM_TILE, 0, s>>>(A, 2 * max_cov + tol);
+  const size_t cl_smem = DM_CL_SMEM(N);
+  if (rebuild && lattice && cl_smem <= 110 * 1024) {       // two CTAs per SM; larger cells take the all-pairs kernel
+    if (cl_smem > 48 * 1024) cudaFuncSetAttribute(k_dm_bonds_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem);
+    k_dm_bonds_cells<<<F, DM_CL_THREADS, cl_smem, s>>>(A, 2 * max_cov + tol);
+  } else {
+    dim3 g((N + DM_TILE - 1) / DM_TILE, F);
+    k_dm_bonds<<<g, DM_TILE, 0, s>>>(A, 2 * max_cov + tol);
+  }
   k_dm_fill<<<(F + DM_FILL_WARPS - 1) / DM_FILL_WARPS, DM_FILL_WARPS * 32, 0, s>>>(A);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pwb_set_error(cudaGetErrorString(e)); return 1; }
