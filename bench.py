@@ -276,14 +276,19 @@ def run_ours(args):
     stage_ms = np.array([[ev[k].elapsed_time(ev[k + 1]) for k in range(len(stage_list))] for ev in events]).mean(axis=0)
     eng.set_chunks(args.chunks)
 
-    # ---- end-to-end: host (pinned) coords -> C ABI host entry -> host records, every step
+    # ---- end-to-end: host (pinned) coords -> C ABI host entry -> host records, every step; one field of every
+    # step's records is summed on the host before the next step is submitted.  (Keeping two batches in flight
+    # with pwb_full_analysis_host_async was measured 6 % SLOWER: the interleaved kernels of two batches lose more
+    # than the hidden copy latency gains, see DESIGN.md.)
     state = {}
     for i in range(max(1, args.warmup)):
         eng.analyse_frames_host(host_batches[i % N_ROTATE], elements, ray_cap=ray_cap, state=state)
     barrier()
     t0 = time.perf_counter()
+    e2e_checksum = 0.0
     for i in range(args.steps):
         h_rec = eng.analyse_frames_host(host_batches[(args.warmup + i) % N_ROTATE], elements, ray_cap=ray_cap, state=state)
+        e2e_checksum += float(h_rec[:, L.REC_PORE_D].sum())
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -155,6 +155,12 @@ int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
  * the per-frame loop of Trajectory.analysis (trajectory.py:473-586) binds to.                      */
 int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream);
+/* Same without the final synchronisation (h_records must be pinned): the records are valid once
+ * `stream` has been synchronised.  With two calls in flight on two streams -- each with its own staging
+ * buffers and workspace -- the copies of one batch overlap the kernels of the other, which is how a
+ * trajectory reader that decodes batch i+1 while batch i is analysed uses it.                       */
+int pwb_full_analysis_host_async(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
+                                 double* d_coords, double* d_records, int total_atoms, void* stream);
 
 /* ---- periodic cells -------------------------------------------------------------------------
  * discrete_molecules (utilities.py:820-1085) for F cell-frames of N atoms each; with `rebuild` the

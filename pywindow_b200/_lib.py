@@ -25,7 +25,7 @@ EXPORTS = [
     "pwb_abi_version", "pwb_last_error", "pwb_ctx_create", "pwb_ctx_destroy", "pwb_ctx_set_chunks", "pwb_workspace_bytes",
     "pwb_workspace_layout", "pwb_ray_capacity", "pwb_frame_scalars", "pwb_average_diameter",
     "pwb_opt_pore", "pwb_ray_search", "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch",
-    "pwb_full_analysis_host", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
+    "pwb_full_analysis_host", "pwb_full_analysis_host_async", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
     "pwb_dm_workspace_layout", "pwb_discrete_molecules", "pwb_set_error", "pwb_history_index",
     "pwb_history_decode",
 ]
@@ -83,6 +83,8 @@ def load():
         getattr(L, name).restype = ci
     L.pwb_full_analysis_host.argtypes = [vp, ctypes.POINTER(Batch), vp, vp, vp, vp, ci, vp]
     L.pwb_full_analysis_host.restype = ci
+    L.pwb_full_analysis_host_async.argtypes = [vp, ctypes.POINTER(Batch), vp, vp, vp, vp, ci, vp]
+    L.pwb_full_analysis_host_async.restype = ci
     L.pwb_dm_workspace_bytes.argtypes = [ci, ci, ci]
     L.pwb_dm_workspace_bytes.restype = ctypes.c_size_t
     L.pwb_discrete_molecules.argtypes = [ci, ci, ci, ctypes.c_double, ctypes.c_double, vp, vp, ci, vp, ci, vp, vp,

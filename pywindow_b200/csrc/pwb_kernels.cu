@@ -1499,6 +1499,8 @@ struct pwb_ctx {
   int chunks;                                   // sub-batches pipelined over internal streams
   cudaStream_t streams[PWB_MAX_CHUNKS];
   cudaEvent_t fork, join[PWB_MAX_CHUNKS];
+  cudaStream_t copy_stream;                    // host -> device copies of the *_host entry points
+  cudaEvent_t h2d[PWB_MAX_CHUNKS];
 };
 
 static thread_local char g_err[512] = "";
@@ -1563,8 +1565,10 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
   for (int g = 0; g < PWB_MAX_CHUNKS; g++) {
     CK(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->join[g], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->h2d[g], cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   *out = c;
   return 0;
 }
@@ -1575,8 +1579,9 @@ int pwb_ctx_set_chunks(pwb_ctx* c, int chunks) {
 int pwb_ctx_destroy(pwb_ctx* c) {
   if (!c) return 0;
   cudaFree(c->c.knn_unit); cudaFree(c->c.knn_need); cudaFree(c->d_tmp);
-  for (int g = 0; g < PWB_MAX_CHUNKS; g++) { cudaStreamDestroy(c->streams[g]); cudaEventDestroy(c->join[g]); }
+  for (int g = 0; g < PWB_MAX_CHUNKS; g++) { cudaStreamDestroy(c->streams[g]); cudaEventDestroy(c->join[g]); cudaEventDestroy(c->h2d[g]); }
   cudaEventDestroy(c->fork);
+  cudaStreamDestroy(c->copy_stream);
   delete c;
   return 0;
 }
@@ -1759,9 +1764,15 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       if (b->ray_cap > KNN_SMEM_CAP) { u.big_pts += (size_t)first * b->ray_cap * 4; u.big_i += (size_t)first * b->ray_cap * 2; }
       cudaStream_t sg = c->streams[g];
       CK(cudaStreamWaitEvent(sg, c->fork, 0));
-      if (chunk_copies)
+      if (chunk_copies) {
+        // The copies go to their own stream so that, with two calls in flight, the next batch's input
+        // arrives while this batch's kernels still occupy the chunk streams.
+        if (g == 0) CK(cudaStreamWaitEvent(c->copy_stream, c->fork, 0));
         CK(cudaMemcpyAsync((double*)b->coords + 3 * apf * first, h_coords + 3 * apf * first,
-                           sizeof(double) * 3 * apf * count, cudaMemcpyHostToDevice, sg));
+                           sizeof(double) * 3 * apf * count, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->h2d[g], c->copy_stream));
+        CK(cudaStreamWaitEvent(sg, c->h2d[g], 0));
+      }
       if (run_stages(c, &t, u, sg)) return 1;
       if (h_records)
         CK(cudaMemcpyAsync(h_records + (size_t)first * b->rec_stride, t.records,
@@ -1829,6 +1840,18 @@ int pwb_full_analysis_host(pwb_ctx* c, const pwb_batch* b, const double* h_coord
   if (batch_impl(c, &t, s, h_coords, h_records)) return 1;
   CK(cudaStreamSynchronize(s));
   return 0;
+}
+
+// Same without the final synchronisation: the records are valid once `stream` has been synchronised.  Two
+// calls in flight on two streams (each with its own staging buffers and workspace) overlap one batch's copies
+// with the other's kernels.
+int pwb_full_analysis_host_async(pwb_ctx* c, const pwb_batch* b, const double* h_coords, double* h_records,
+                                 double* d_coords, double* d_records, int total_atoms, void* stream) {
+  pwb_batch t = *b;
+  t.coords = d_coords;
+  t.records = d_records;
+  t.total_atoms = total_atoms;
+  return batch_impl(c, &t, (cudaStream_t)stream, h_coords, h_records);
 }
 
 }  // extern "C"

@@ -197,9 +197,12 @@ class Engine:
 
     # ------------------------------------------------------------------ host-buffer path (e2e)
     def analyse_frames_host(self, coords_host, elements, *, ray_cap, out=None, stages=_lib.STAGE_ALL,
-                            adjust=1.0, increment=1.0, increment2=0.1, pore_opt=True, state=None):
+                            adjust=1.0, increment=1.0, increment2=0.1, pore_opt=True, state=None, wait=True):
         """Host numpy/pinned [F,N,3] in, host records out: H2D + kernels + D2H inside the call
-        (``pwb_full_analysis_host``).  ``state`` caches device staging buffers between calls."""
+        (``pwb_full_analysis_host``).  ``state`` caches device staging buffers between calls.
+        ``wait=False`` (``pwb_full_analysis_host_async``) returns at once; the pinned records are valid after
+        the current torch stream has been synchronised -- alternate two ``state`` dicts on two streams to
+        overlap one batch's copies with the other's kernels."""
         F, N = int(coords_host.shape[0]), int(coords_host.shape[1])
         with torch.cuda.device(self.device):
             st = state if state is not None else {}
@@ -229,9 +232,11 @@ class Engine:
                                                True, N, None, stages, adjust, increment, increment2, pore_opt,
                                                ray_cap)
             b.workspace, b.workspace_bytes = st["ws"].data_ptr(), st["layout"].total
-            _lib.check(self.lib.pwb_full_analysis_host(self._ctx, ctypes.byref(b), h_ptr, h_rec.data_ptr(),
-                                                       st["d_coords"].data_ptr(), st["d_rec"].data_ptr(),
-                                                       F * N, stream))
+            entry = self.lib.pwb_full_analysis_host if wait else self.lib.pwb_full_analysis_host_async
+            if not wait:
+                st["h_in"] = coords_host          # keep the source alive until the copy has run
+            _lib.check(entry(self._ctx, ctypes.byref(b), h_ptr, h_rec.data_ptr(),
+                              st["d_coords"].data_ptr(), st["d_rec"].data_ptr(), F * N, stream))
             return h_rec
 
 

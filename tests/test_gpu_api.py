@@ -110,3 +110,15 @@ def test_host_buffer_entry_point_matches_device_path():
     a = eng.analyse_frames(X, el)
     h = eng.analyse_frames_host(X, el, ray_cap=a.ray_cap).numpy().copy()
     np.testing.assert_array_equal(a.host_records(), h)
+    # asynchronous entry, two batches in flight on two streams with separate staging state
+    import torch
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    states, outs = [{}, {}], []
+    Xp = [torch.from_numpy(X.copy()).pin_memory(), torch.from_numpy(X[::-1].copy()).pin_memory()]
+    for k in range(2):
+        with torch.cuda.stream(streams[k]):
+            outs.append(eng.analyse_frames_host(Xp[k], el, ray_cap=a.ray_cap, state=states[k], wait=False))
+    for k in range(2):
+        streams[k].synchronize()
+    np.testing.assert_array_equal(outs[0].numpy(), h)
+    np.testing.assert_array_equal(outs[1].numpy(), h[::-1])
