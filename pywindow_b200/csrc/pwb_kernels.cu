@@ -800,7 +800,7 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
     label[i] = 0;                                  // neighbour counter in pass 1
   }
   __syncthreads();
-  const double eps2 = eps * eps;
+  const double eps2 = eps * eps, epsz = eps * (1.0 + 1e-12) + 1e-9;
   // ---- adjacency as a bit matrix in shared memory (one FP64 test per ordered pair, once); core
   // flags, components (min-label propagation with pointer jumping) and border labels are then pure
   // integer work on the bit rows.  Falls back to recomputing distances if S is too large for the tile.
@@ -814,9 +814,13 @@ k_cluster(pwb_batch b, Ws ws, Ctx ctx, int pass, unsigned budget) {
       const double hi = a.w - 0.5 * eps2;
       const int jb = w << 5, jn = min(32, S - jb);
       unsigned bits = 0;
-      for (int t = 0; t < jn; t++) {
-        const double4 o = pt[jb + t];
-        bits |= (unsigned)(fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi) << t;
+      // the clear rays are sorted by spiral index, i.e. by descending z: a word whose z range is more than
+      // eps away from z_i cannot hold a neighbour (consecutive i share the verdict, so whole warps skip)
+      if (a.z - epsz <= pt[jb].z && a.z + epsz >= pt[jb + jn - 1].z) {
+        for (int t = 0; t < jn; t++) {
+          const double4 o = pt[jb + t];
+          bits |= (unsigned)(fma(a.x, o.x, fma(a.y, o.y, fma(a.z, o.z, -o.w))) >= hi) << t;
+        }
       }
       adj[it] = bits;
     }
