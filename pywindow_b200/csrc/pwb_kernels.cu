@@ -613,25 +613,29 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       const int chunks = (int)py_floordiv(nr, b.increment);
       const double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
       const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
-      const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
-      double bestv = PWB_INF, bestj = 0.0;
+      const int jmax = chunks > 0 ? chunks - 1 : 0;
+      double bestv = PWB_INF;
+      int bestj = 0;
       for (int c = 0; c < b.n_types; c++) {
         const int cb = cls[c], ce = cls[c + 1];
         if (cb == ce) continue;
-        double m = PWB_INF, mj = 0.0;
+        double m = PWB_INF;
+        int mj = 0;
         for (int a = cb; a < ce; a++) {
           const double4 q = ap[a];
           const double g = fma(q.x, cxs, fma(q.y, cys, q.z * czs));
-          double jm = ceil(fma(g, icc, -0.5));               // nearest step to the projection, ties -> smaller
-          jm = dmin(jmax, jm > 0.0 ? jm : 0.0);
+          // nearest step to the projection (ties -> smaller), clamped to the path: round up in the conversion,
+          // clamp as integers (one min-max instruction instead of two double selects)
+          const int ji = min(jmax, max(0, __double2int_ru(fma(g, icc, -0.5))));
+          const double jm = (double)ji;
           const double dm = fma(jm, fma(jm, cc, -2.0 * g), q.w);
-          if (dm < m) { m = dm; mj = jm; }
+          if (dm < m) { m = dm; mj = ji; }
         }
         const double v = sqrt(fmax(m, 0.0)) - cr[c];
         if (v < bestv || (v == bestv && mj < bestj)) { bestv = v; bestj = mj; }
       }
       const bool clear = chunks > 0 && bestv > 0.0;
-      spos[s] = clear ? (int)bestj : -1;
+      spos[s] = clear ? bestj : -1;
       sa[s] = bestv * 2.0;
     }
     __syncthreads();
