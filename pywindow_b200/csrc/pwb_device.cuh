@@ -296,7 +296,7 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
 // The pre-test of find_windows and the average-diameter sampling both ask, for ~1e3 rays from the
 // centroid o, which of the N vdW spheres the ray's LINE intersects.  Sphere i subtends a cap of angular
 // radius asin(r_i/|L_i|) around +-L_i/|L_i| (L_i = x_i - o); caps are rasterised (conservatively: bounding
-// box in z = cos(theta) and phi, plus 1e-7 rad) into a 16 x 32 grid of direction bins, so a ray only
+// box in z = cos(theta) and phi, plus a 1e-7 rad margin) into a 16 x 32 grid of direction bins, so a ray only
 // tests the handful of atoms listed in its bin.  The tests themselves are unchanged (exact, FP64).
 constexpr int DG_NZ = 16, DG_NPHI = 32, DG_BINS = DG_NZ * DG_NPHI, DG_CAP = 24;
 constexpr double DG_PI = 3.141592653589793;
@@ -316,19 +316,26 @@ __device__ __forceinline__ void dg_push(const DirGrid& G, int bin, int a) {
   if (pos < DG_CAP) G.list[bin * DG_CAP + pos] = (unsigned short)a; else *G.overflow = 1;
 }
 
-__device__ __forceinline__ void dg_insert_cap(const DirGrid& G, int a, double ux, double uy, double uz, double alpha) {
-  const double tc = acos(fmin(1.0, fmax(-1.0, uz)));
-  const double tlo = tc - alpha, thi = tc + alpha;
-  const double zhi = tlo <= 0.0 ? 1.0 : cos(tlo), zlo = thi >= DG_PI ? -1.0 : cos(thi);
+// Cap of angular radius alpha = asin(sa) around the unit vector u, rasterised conservatively WITHOUT
+// inverse trigonometry: with ct = u_z, st = sqrt(1 - u_z^2), ca = sqrt(1 - sa^2) the cap spans
+// z in [ct ca - st sa, ct ca + st sa] (a pole inside the cap extends that to +-1 and to every phi), and its
+// half-width in phi is asin(sa / st) <= x + (pi/2 - 1) x^3 (asin is convex on [0, 1]).  `sa` already carries
+// the caller's safety margin; supersets only cost extra exact tests.
+__device__ __forceinline__ void dg_insert_cap(const DirGrid& G, int a, double ux, double uy, double uz, double sa) {
+  const double ct = fmin(1.0, fmax(-1.0, uz));
+  const double st = sqrt(fmax(0.0, 1.0 - ct * ct)), ca = sqrt(fmax(0.0, 1.0 - sa * sa));
+  const bool north = ct >= ca, south = -ct >= ca;          // theta_c - alpha <= 0, theta_c + alpha >= pi
+  const double zhi = north ? 1.0 : fmin(1.0, ct * ca + st * sa + 1e-9);
+  const double zlo = south ? -1.0 : fmax(-1.0, ct * ca - st * sa - 1e-9);
   int iz0 = (int)floor((zlo + 1.0) * (DG_NZ * 0.5) - 1e-9), iz1 = (int)floor((zhi + 1.0) * (DG_NZ * 0.5) + 1e-9);
   iz0 = iz0 < 0 ? 0 : iz0; iz1 = iz1 >= DG_NZ ? DG_NZ - 1 : iz1;
-  bool full = tlo <= 0.0 || thi >= DG_PI;
+  bool full = north || south;
   int ip0 = 0, ip1 = DG_NPHI - 1;
   if (!full) {
-    const double sr = sin(alpha) / sin(tc);
-    if (sr >= 1.0) full = true;
+    const double sr = sa / st;
+    if (!(sr < 1.0)) full = true;
     else {
-      const double dphi = asin(sr) + 1e-7, pc = atan2(uy, ux) + DG_PI;
+      const double dphi = sr + (0.5 * DG_PI - 1.0) * sr * sr * sr + 1e-7, pc = atan2(uy, ux) + DG_PI;
       ip0 = (int)floor((pc - dphi) * (DG_NPHI / (2.0 * DG_PI)));
       ip1 = (int)floor((pc + dphi) * (DG_NPHI / (2.0 * DG_PI)));
       if (ip1 - ip0 + 1 >= DG_NPHI) full = true;
@@ -353,12 +360,12 @@ __device__ __forceinline__ void dg_build(const DirGrid& G, const double* Lx, con
       for (int c = 0; c < DG_BINS; c++) dg_push(G, c, a);
       continue;
     }
-    const double alpha = asin(fmin(1.0, ra / L)) + 1e-7;
+    const double sa = fmin(1.0, ra / L + 2e-7);          // sin of the cap radius, with a margin of > 1e-7 rad
     const double il = 1.0 / L;
-    dg_insert_cap(G, a, x * il, y * il, z * il, alpha);
+    dg_insert_cap(G, a, x * il, y * il, z * il, sa);
     // the line also meets the sphere on the far side of o; that only counts if x.n > 0 can still hold,
     // i.e. for atoms closer to the centroid than the centroid is to the origin
-    if (L - ra <= onorm + 1e-9) dg_insert_cap(G, a, -x * il, -y * il, -z * il, alpha);
+    if (L - ra <= onorm + 1e-9) dg_insert_cap(G, a, -x * il, -y * il, -z * il, sa);
   }
   __syncthreads();
 }

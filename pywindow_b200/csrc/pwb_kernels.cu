@@ -519,9 +519,9 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       const double L2 = x * x + y * y + z * z, L = sqrt(L2);
       lw[a] = lw[a] - L2;                                                       // r^2 - |L|^2
       if (L <= ra * (1.0 + 1e-9) + 1e-12) { for (int c = 0; c < DG_BINS; c++) dg_push(DG, c, a); continue; }
-      const double alpha = asin(fmin(1.0, ra / L)) + 1e-7, il = 1.0 / L;
-      dg_insert_cap(DG, a, x * il, y * il, z * il, alpha);
-      if (L - ra <= onorm + 1e-9) dg_insert_cap(DG, a, -x * il, -y * il, -z * il, alpha);
+      const double sa = fmin(1.0, ra / L + 2e-7), il = 1.0 / L;   // sin of the cap radius + margin (see dg_build)
+      dg_insert_cap(DG, a, x * il, y * il, z * il, sa);
+      if (L - ra <= onorm + 1e-9) dg_insert_cap(DG, a, -x * il, -y * il, -z * il, sa);
     }
   }
   const double R = idv[D_MAXD] / 2.0;     // max_dim is translation invariant: reuse (utilities.py:1398)
