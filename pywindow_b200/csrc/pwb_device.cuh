@@ -306,8 +306,16 @@ struct DirGrid { unsigned short* list; int* cnt; int* overflow; };   // list[DG_
 __device__ __forceinline__ int dg_bin(double nx, double ny, double nz) {
   int iz = (int)floor((nz + 1.0) * (DG_NZ * 0.5));
   iz = iz < 0 ? 0 : (iz >= DG_NZ ? DG_NZ - 1 : iz);
-  int ip = (int)floor((atan2(ny, nx) + DG_PI) * (DG_NPHI / (2.0 * DG_PI)));
-  ip = ip < 0 ? 0 : (ip >= DG_NPHI ? DG_NPHI - 1 : ip);
+  // phi bin = floor((atan2(ny, nx) + pi) / (pi/16)) without the atan2: sixteenths of pi inside the first quadrant
+  // by three comparisons against tan(k pi/16), then the quadrant from the signs.  A direction within rounding
+  // of a bin boundary may land on either side; the caps are rasterised with a 1e-7 rad margin, so both bins
+  // list every atom it can meet.
+  static_assert(DG_NPHI == 32, "phi binning below assumes 32 bins");
+  const double a = fabs(nx), c = fabs(ny);
+  constexpr double T1 = 0.19891236737965800, T2 = 0.41421356237309503, T3 = 0.66817863791929890;
+  const int q8 = c <= a ? (int)(c > a * T1) + (int)(c > a * T2) + (int)(c > a * T3)
+                        : 7 - ((int)(a > c * T1) + (int)(a > c * T2) + (int)(a > c * T3));
+  const int ip = ny >= 0.0 ? (nx >= 0.0 ? 16 + q8 : 31 - q8) : (nx >= 0.0 ? 15 - q8 : q8);
   return iz * DG_NPHI + ip;
 }
 
