@@ -72,3 +72,20 @@ def test_translation_covariance_with_forced_centres(data):
     d = np.abs(wa[:, :, 0] - wb[:, :, 0])
     assert np.quantile(d, 0.999) < 1e-3 and (d < 5e-2).all()       # window stage is well conditioned
     assert (np.abs(wb[:, :, 1:] - wa[:, :, 1:] - t) < 0.2).all()
+
+
+def test_ray_tiling_is_independent_of_the_cta_count():
+    """Dense ray sets (adjust = 8: ~7e3 rays, 7 tiles) are shared by several CTAs when the batch is small and run
+    on one CTA per item when the batch fills the GPU: per-tile results are packed / summed in tile order, so the
+    records must be bit-identical either way (and equal the single-tile order for the default ray count)."""
+    from pywindow_b200.engine import Engine
+    g = load_golden("md_frame05")
+    eng = Engine(0)
+    X1 = g["coords"][None]
+    alone = eng.analyse_frames(X1, g["elements"], adjust=8.0).host_records()        # gridDim.y = number of tiles
+    many = eng.analyse_frames(np.repeat(X1, 400, axis=0), g["elements"], adjust=8.0).host_records()   # gridDim.y = 1
+    assert alone[0, 16] > 4096                                                   # PWB_REC_NRAYS: the multi-tile path
+    np.testing.assert_array_equal(many, np.repeat(alone, 400, axis=0))
+    few = eng.analyse_frames(np.repeat(X1, 3, axis=0), g["elements"]).host_records()   # default rays, 2 CTAs per item
+    lots = eng.analyse_frames(np.repeat(X1, 400, axis=0), g["elements"]).host_records()
+    np.testing.assert_array_equal(lots[:3], few)

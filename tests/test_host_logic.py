@@ -155,3 +155,18 @@ def test_native_history_decoder_is_bit_exact(tmp_path):
         np.testing.assert_array_equal(lattice[f], fr["lattice"])
         assert fr["velocities"].shape == (n, 3) and fr["forces"].shape == (n, 3)
     np.testing.assert_array_equal(t._decode_coordinates([3, 0]), xyz[[3, 0]])
+
+
+def test_direction_bin_formula_matches_atan2():
+    """csrc/pwb_device.cuh:dg_bin locates the phi bin of a direction with three comparisons against tan(k pi/16)
+    per quadrant instead of atan2; the restatement here must agree with floor((atan2(y, x) + pi) / (pi/16))."""
+    rng = np.random.default_rng(7)
+    v = rng.normal(size=(500000, 2))
+    x, y = v[:, 0], v[:, 1]
+    ref = np.clip(np.floor((np.arctan2(y, x) + np.pi) * (32 / (2 * np.pi))).astype(int), 0, 31)
+    a, c = np.abs(x), np.abs(y)
+    t1, t2, t3 = 0.19891236737965800, 0.41421356237309503, 0.66817863791929890
+    q8 = np.where(c <= a, (c > a * t1).astype(int) + (c > a * t2) + (c > a * t3),
+                  7 - ((a > c * t1).astype(int) + (a > c * t2) + (a > c * t3)))
+    ip = np.where(y >= 0, np.where(x >= 0, 16 + q8, 31 - q8), np.where(x >= 0, 15 - q8, q8))
+    assert (ip == ref).all()
