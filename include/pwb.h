@@ -191,6 +191,17 @@ int64_t pwb_history_index(const char* buf, int64_t len, int64_t* starts, int64_t
 int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
                            int natoms, int keytrj, int imcon, double* xyz, double* lattice, int threads);
 
+/* Multi-frame XYZ (trajectory.py:792-915) and multi-model PDB (trajectory.py:917-1045) trajectories, same
+ * contract as the HISTORY pair: pwb_xyz_index maps the frames (byte range + atom count each; returns the number
+ * of frames, or -(1 + byte offset) of a line that should hold an atom count), pwb_xyz_decode / pwb_pdb_decode
+ * parse n frames of `natoms` atoms on `threads` host threads (0 = all) into xyz[n][natoms][3], bit-identical to
+ * Python's float(); they return 0 or 1 + the index of the first malformed frame.                          */
+int64_t pwb_xyz_index(const char* buf, int64_t len, int64_t* starts, int64_t* ends, int32_t* natoms, int64_t cap);
+int64_t pwb_xyz_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
+                       int natoms, double* xyz, int threads);
+int64_t pwb_pdb_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
+                       int natoms, double* xyz, int threads);
+
 /* Measurement utility: sustained FMA throughput of the FP32 (fp64 = 0) or FP64 (fp64 = 1) pipe in
  * TFLOP/s, timed with CUDA events (the roofline denominator of this compute-bound path).          */
 int pwb_fma_peak(pwb_ctx*, int fp64, void* stream, double* tflops);

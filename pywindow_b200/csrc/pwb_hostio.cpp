@@ -75,6 +75,27 @@ inline const char* parse_double(const char* p, const char* end, double* out, boo
   return p;
 }
 
+// run one_frame(f) for f in [0, n) on a pool of host threads; 0 or 1 + index of the first failing frame
+template <class F>
+static int64_t decode_frames(int64_t n, int threads, F one_frame) {
+  std::atomic<int64_t> next(0), bad(0);
+  auto work = [&]() {
+    while (true) {
+      const int64_t f = next.fetch_add(1);
+      if (f >= n) break;
+      if (!one_frame(f)) { int64_t z = 0; bad.compare_exchange_strong(z, f + 1); }
+    }
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if ((int64_t)nt > n) nt = (int)(n > 0 ? n : 1);
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return bad.load();
+}
+
 }  // namespace
 
 extern "C" {
@@ -139,6 +160,81 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
   work();
   for (auto& th : pool) th.join();
   return bad.load();
+}
+
+
+// ---- multi-frame XYZ (trajectory.py:792-915): natoms / comment / natoms lines "El x y z" -------------------
+// Frame map: byte range and atom count of every frame (blank lines between frames are skipped).  Returns the
+// number of frames found (may exceed cap: call again with larger arrays), or -(1 + byte offset) of a line
+// that should hold an atom count and does not.
+int64_t pwb_xyz_index(const char* buf, int64_t len, int64_t* starts, int64_t* ends, int32_t* natoms, int64_t cap) {
+  const char* end = buf + len;
+  const char* p = buf;
+  int64_t n = 0;
+  while (p < end) {
+    const char* q = p;
+    while (q < end && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+    if (q >= end) break;
+    if (*q == '\n') { p = q + 1; continue; }                   // blank line
+    int64_t na = 0; int digits = 0;
+    while (q < end && *q >= '0' && *q <= '9') { na = na * 10 + (*q - '0'); q++; digits++; if (na > 2000000000) break; }
+    if (!digits || (q < end && *q != ' ' && *q != '\t' && *q != '\r' && *q != '\n')) return -(1 + (int64_t)(p - buf));
+    const char* e = skip_line(p, end);                          // count line
+    for (int64_t i = 0; i < na + 1 && e < end; i++) e = skip_line(e, end);   // comment + atoms
+    if (n < cap) { starts[n] = (int64_t)(p - buf); ends[n] = (int64_t)(e - buf); natoms[n] = (int32_t)na; }
+    n++;
+    p = e;
+  }
+  return n;
+}
+
+// Decode n XYZ frames of `natoms` atoms each into xyz[n][natoms][3].  Returns 0, or 1 + index of the first
+// malformed frame.
+int64_t pwb_xyz_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n, int natoms,
+                       double* xyz, int threads) {
+  return decode_frames(n, threads, [&](int64_t f) {
+    const char* p = buf + starts[f];
+    const char* end = buf + (ends[f] <= len ? ends[f] : len);
+    p = skip_line(p, end);                                      // atom count
+    p = skip_line(p, end);                                      // comment
+    double* o = xyz + (size_t)f * natoms * 3;
+    bool ok = true;
+    for (int a = 0; a < natoms && ok; a++) {
+      if (p >= end) return false;
+      while (p < end && (*p == ' ' || *p == '\t')) p++;
+      while (p < end && *p != ' ' && *p != '\t' && *p != '\n') p++;          // element / atom id token
+      for (int c = 0; c < 3 && ok; c++) p = parse_double(p, end, &o[3 * a + c], &ok);
+      p = skip_line(p, end);
+    }
+    return ok;
+  });
+}
+
+// Decode n PDB models (trajectory.py:1013-1045; fixed columns 31-38, 39-46, 47-54 of ATOM / HETATM records)
+// of `natoms` atoms each into xyz[n][natoms][3].  Returns 0, or 1 + index of the first malformed frame
+// (wrong atom count, short record, unparsable field).
+int64_t pwb_pdb_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n, int natoms,
+                       double* xyz, int threads) {
+  return decode_frames(n, threads, [&](int64_t f) {
+    const char* p = buf + starts[f];
+    const char* end = buf + (ends[f] <= len ? ends[f] : len);
+    double* o = xyz + (size_t)f * natoms * 3;
+    int a = 0;
+    bool ok = true;
+    while (p < end && ok) {
+      const char* e = skip_line(p, end);
+      if (e - p >= 6 && (memcmp(p, "ATOM  ", 6) == 0 || memcmp(p, "HETATM", 6) == 0)) {
+        if (a >= natoms || e - p < 54) return false;
+        for (int c = 0; c < 3 && ok; c++) {
+          const char* q = parse_double(p + 30 + 8 * c, p + 38 + 8 * c, &o[3 * a + c], &ok);
+          while (ok && q < p + 38 + 8 * c) { if (*q != ' ') ok = false; q++; }   // trailing junk inside the field
+        }
+        a++;
+      }
+      p = e;
+    }
+    return ok && a == natoms;
+  });
 }
 
 }  // extern "C"

@@ -401,32 +401,58 @@ class DLPOLY(Trajectory):
         return _float_block(lines[first + 1::stride]).reshape(-1, 3)
 
 
+def _native_xyz_like(traj, entry, frames, natoms):
+    """Shared driver of pwb_xyz_decode / pwb_pdb_decode: frames -> [F, natoms, 3] float64."""
+    lib = _lib.load()
+    n = len(frames)
+    starts = np.array([traj.trajectory_map[f][0] for f in frames], dtype=np.int64)
+    ends = np.array([traj.trajectory_map[f][1] for f in frames], dtype=np.int64)
+    xyz = np.empty((n, natoms, 3), dtype=np.float64)
+    with traj.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+        buf = np.frombuffer(mm, dtype=np.uint8)
+        bad = int(getattr(lib, entry)(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, natoms,
+                                      xyz.ctypes.data, 0))
+        del buf
+    if bad:
+        raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {natoms} atoms)")
+    return xyz
+
+
+
 class XYZ(Trajectory):
     """Multi-frame XYZ file: every frame is ``natoms`` / comment / natoms atom lines."""
 
     def __init__(self, filepath):
         super().__init__(filepath)
-        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            pos, size, k = 0, len(mm), 0
-            while pos < size:
-                eol = mm.find(b"\n", pos)
-                eol = size if eol < 0 else eol
-                tok = mm[pos:eol].split()
-                if not tok:
-                    pos = eol + 1
-                    continue
-                try:
-                    natoms = int(tok[0])
-                except ValueError:
-                    raise _FormatError(f"expected an atom count at byte {pos} of {self.filepath}") from None
-                end = eol
-                for _ in range(natoms + 1):
-                    nxt = mm.find(b"\n", end + 1)
-                    end = size if nxt < 0 else nxt
-                self.trajectory_map[k] = [pos, min(end + 1, size)]
-                k += 1
-                pos = end + 1
-        self.no_of_frames = k
+        # frame map by the native indexer (pwb_xyz_index): byte range and atom count of every frame
+        lib = _lib.load()
+        self._natoms = np.zeros(0, dtype=np.int32)
+        if self.filepath.stat().st_size:
+            with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+                buf = np.frombuffer(mm, dtype=np.uint8)
+                cap = 1 << 16
+                while True:
+                    starts, ends = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64)
+                    natoms = np.empty(cap, dtype=np.int32)
+                    n = int(lib.pwb_xyz_index(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data,
+                                              natoms.ctypes.data, cap))
+                    if n <= cap:
+                        break
+                    cap = n
+                del buf
+            if n < 0:
+                raise _FormatError(f"expected an atom count at byte {-n - 1} of {self.filepath}")
+            for k in range(n):
+                self.trajectory_map[k] = [int(starts[k]), int(ends[k])]
+            self._natoms = natoms[:n].copy()
+        self.no_of_frames = len(self.trajectory_map)
+
+    def _decode_coordinates(self, frames):
+        """[F,N,3] through the multi-threaded C++ decoder (pwb_xyz_decode) when the frames share one atom count."""
+        counts = {int(self._natoms[f]) for f in frames}
+        if len(counts) != 1:
+            return super()._decode_coordinates(frames)
+        return _native_xyz_like(self, "pwb_xyz_decode", frames, counts.pop())
 
     def _decode_frame(self, raw):
         lines = bytes(raw).decode("utf-8").split("\n")
@@ -453,6 +479,15 @@ class PDB(Trajectory):
                 self.trajectory_map[k] = [start, size]
                 k += 1
         self.no_of_frames = k
+
+    def _decode_coordinates(self, frames):
+        """[F,N,3] through the multi-threaded C++ decoder (pwb_pdb_decode); the atom count is the first frame's."""
+        if not frames:
+            return super()._decode_coordinates(frames)
+        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            start, end = self.trajectory_map[frames[0]]
+            natoms = len(self._decode_frame(mm[start:end])["coordinates"])
+        return _native_xyz_like(self, "pwb_pdb_decode", frames, natoms)
 
     def _decode_frame(self, raw):
         lines = bytes(raw).decode("utf-8").split("\n")

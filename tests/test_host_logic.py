@@ -170,3 +170,56 @@ def test_direction_bin_formula_matches_atan2():
                   7 - ((a > c * t1).astype(int) + (a > c * t2) + (a > c * t3)))
     ip = np.where(y >= 0, np.where(x >= 0, 16 + q8, 31 - q8), np.where(x >= 0, 15 - q8, q8))
     assert (ip == ref).all()
+
+
+def test_native_xyz_and_pdb_decoders_are_bit_exact(tmp_path):
+    """pwb_xyz_index / pwb_xyz_decode / pwb_pdb_decode (C++, threaded) against the Python per-frame decoders:
+    awkward number formats, blank lines between frames, a numeric comment line (the reference's XYZ mapper
+    mis-splits there), mixed atom counts (Python fallback), malformed frames."""
+    from pywindow_b200.trajectory import PDB, XYZ, Trajectory, _FormatError, _TrajectoryError
+    rng = np.random.default_rng(5)
+    n, F = 23, 9
+    fmts = ["%.17E", "%12.4E", "%20.10f", "%.3f", "%.17g", "%25.16e"]
+    X = rng.normal(0, 30, size=(F, n, 3)) * 10.0 ** rng.integers(-8, 4, size=(F, n, 1))
+    path = tmp_path / "t.xyz"
+    with open(path, "w") as fh:
+        for f in range(F):
+            fh.write("  %d  \n%s\n" % (n, "42" if f == 2 else "frame %d energy -1.5" % f))
+            for a in range(n):
+                fh.write("C%d\t" % (a % 3) + "  ".join(fmts[(f + a) % len(fmts)] % v for v in X[f, a]) + "  extra\n")
+            if f % 3 == 0:
+                fh.write("\n  \n")
+    t = XYZ(path)
+    assert t.no_of_frames == F and (t._natoms == n).all()
+    native = t._decode_coordinates(list(range(F)))
+    np.testing.assert_array_equal(native, Trajectory._decode_coordinates(t, list(range(F))))   # Python float()
+    np.testing.assert_array_equal(t._decode_coordinates([4, 1]), native[[4, 1]])
+    # mixed atom counts: per-frame map is still right, batch decode refuses / falls back consistently
+    with open(tmp_path / "mixed.xyz", "w") as fh:
+        fh.write("1\nc\nC 0 0 0\n2\nc\nC 0 0 0\nH 1 0 0\n")
+    m = XYZ(tmp_path / "mixed.xyz")
+    assert m.no_of_frames == 2 and list(m._natoms) == [1, 2]
+    assert m._decode_coordinates([1]).shape == (1, 2, 3)
+    with pytest.raises(_TrajectoryError):
+        m._decode_coordinates([0, 1])
+    (tmp_path / "bad.xyz").write_text("3\nc\nC 0 0 0\nC 1 0 0\nC x 0 0\n")
+    with pytest.raises(_TrajectoryError):
+        XYZ(tmp_path / "bad.xyz")._decode_coordinates([0])
+    (tmp_path / "bad2.xyz").write_text("abc\nc\n")
+    with pytest.raises(_FormatError):
+        XYZ(tmp_path / "bad2.xyz")
+    # PDB: fixed columns, fields that touch each other, HETATM records, other records in between
+    ppath = tmp_path / "t.pdb"
+    Xp = np.round(rng.uniform(-999, 9999, size=(F, n, 3)), 3)
+    with open(ppath, "w") as fh:
+        for f in range(F):
+            fh.write("REMARK frame %d\nCRYST1   30.000   30.000   30.000  90.00  90.00  90.00 P 1           1\n" % f)
+            for a in range(n):
+                rec = "HETATM" if a % 4 == 0 else "ATOM  "
+                fh.write("%s%5d  C   MOL A   1    %8.3f%8.3f%8.3f  1.00  0.00           C\n" % ((rec, a + 1) + tuple(Xp[f, a])))
+            fh.write("TER\nEND\n")
+    p = PDB(ppath)
+    assert p.no_of_frames == F
+    native = p._decode_coordinates(list(range(F)))
+    np.testing.assert_array_equal(native, Trajectory._decode_coordinates(p, list(range(F))))
+    np.testing.assert_array_equal(native, Xp)
