@@ -238,10 +238,18 @@ class Trajectory:
         if not frames:
             return np.zeros((0, eng.rec_stride)), []
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
+        # the next batch is decoded on a helper thread (the C++ decoders and the GPU call both release the GIL)
+        # while the current one is on the GPU
+        from concurrent.futures import ThreadPoolExecutor
+        chunks = [frames[s:s + self.batch_frames] for s in range(0, len(frames), self.batch_frames)]
         recs = []
-        for s in range(0, len(frames), self.batch_frames):
-            chunk = frames[s:s + self.batch_frames]
-            recs.append(eng.analyse_frames(self._decode_coordinates(chunk), elements, **gpu_kwargs).host_records())
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(self._decode_coordinates, chunks[0])
+            for k in range(len(chunks)):
+                coords = pending.result()
+                if k + 1 < len(chunks):
+                    pending = pool.submit(self._decode_coordinates, chunks[k + 1])
+                recs.append(eng.analyse_frames(coords, elements, **gpu_kwargs).host_records())
         return np.concatenate(recs), [(f, "0") for f in frames]
 
     def _analyse_modular(self, frames, rebuild, swap_atoms, forcefield, gpu_kwargs):
