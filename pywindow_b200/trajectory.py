@@ -15,6 +15,7 @@ PDB trajectory frames decode, XYZ frames are delimited by their atom-count lines
 from __future__ import annotations
 
 import json
+import gc
 import mmap
 import pathlib
 import re
@@ -71,14 +72,16 @@ class LazyFrame(dict):
         super().__init__()
         self._pending = list(pending)
 
-    def _add(self, mol_key, rec):
-        self._pending.append((mol_key, rec))
+    def _add(self, mol_key, records, row):
+        # (key, record table, row): the row view is only taken when somebody looks (slicing 100 000 numpy rows
+        # costs more than analysing them)
+        self._pending.append((mol_key, records, row))
 
     def _load(self):
         if self._pending:
             pend, self._pending = self._pending, []
-            for k, rec in pend:
-                super().__setitem__(k, record_to_properties(rec))
+            for k, records, row in pend:
+                super().__setitem__(k, record_to_properties(records[row]))
         return self
 
     def __getitem__(self, k):
@@ -202,11 +205,19 @@ class Trajectory:
         if size > 1:
             records, keys = gather_records(records, keys)
         out = self.analysis_output
-        for (frame, mol_key), rec in zip(keys, records):
-            fr = out.get(frame)
-            if not isinstance(fr, LazyFrame):
-                fr = out[frame] = LazyFrame()
-            fr._add(mol_key, rec)
+        # 1e5 small containers: the cyclic collector would rescan the growing heap every few hundred allocations
+        # (8x the cost of the loop itself), and nothing allocated here can form a cycle
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            for row, (frame, mol_key) in enumerate(keys):
+                fr = out.get(frame)
+                if not isinstance(fr, LazyFrame):
+                    fr = out[frame] = LazyFrame()
+                fr._add(mol_key, records, row)
+        finally:
+            if gc_was_on:
+                gc.enable()
 
     def _elements_of(self, frame, swap_atoms, forcefield):
         ms = self._get_frame(self.trajectory_map[frame], frame, swap_atoms=swap_atoms, forcefield=forcefield)
