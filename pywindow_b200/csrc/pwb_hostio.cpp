@@ -103,16 +103,30 @@ extern "C" {
 // Byte offsets of every line that starts with "timestep" (DL_POLY frame records).  Returns the
 // number found (may exceed cap: call again with a larger array).
 int64_t pwb_history_index(const char* buf, int64_t len, int64_t* starts, int64_t cap) {
-  int64_t n = 0;
-  const char* end = buf + len;
-  const char* p = buf;
-  while (p < end) {
-    if ((size_t)(end - p) >= 8 && memcmp(p, "timestep", 8) == 0) {
-      if (n < cap) starts[n] = (int64_t)(p - buf);
-      n++;
+  // the file is cut into one range per host thread; a thread owns the lines that START inside its range
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if (len < (int64_t)(1 << 22)) nt = 1;
+  std::vector<std::vector<int64_t>> found((size_t)nt);
+  auto scan = [&](int t) {
+    const char* end = buf + len;
+    const char* lo = buf + len * t / nt;
+    const char* hi = buf + len * (t + 1) / nt;
+    const char* p = lo;
+    if (t > 0 && p[-1] != '\n') p = skip_line(p, end);         // first line start at or after lo
+    while (p < hi) {
+      if ((size_t)(end - p) >= 8 && memcmp(p, "timestep", 8) == 0) found[(size_t)t].push_back((int64_t)(p - buf));
+      p = skip_line(p, end);
     }
-    p = skip_line(p, end);
-  }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(scan, t);
+  scan(0);
+  for (auto& th : pool) th.join();
+  int64_t n = 0;
+  for (auto& v : found)
+    for (int64_t s : v) { if (n < cap) starts[n] = s; n++; }
   return n;
 }
 
