@@ -215,18 +215,12 @@ __device__ __forceinline__ void warp_min_clear_rs(const WarpAtoms& A, First firs
   for (int c0 = 0; c0 < A.ncls; c0 += CPG) {
     double mine = PWB_INF;
     const int cend = min(A.ncls, c0 + CPG);
-#ifdef RS_NOUNROLL
-#pragma unroll 1
-#endif
     for (int c = c0; c < cend; c++) {
       const int cb = first(c), ce = last(c);
       if (cb == ce) continue;
       double m[K];
 #pragma unroll
       for (int k = 0; k < K; k++) m[k] = PWB_INF;
-#ifdef RS_NOUNROLL_T
-#pragma unroll 1
-#endif
       for (int t = cb + A.lane; t < ce; t += 32) {
         const double4 q = A.p[atom(t)];
 #pragma unroll

@@ -1651,7 +1651,6 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   int ctas = (b->n_items + wpb - 1) / wpb;
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_opt_pore, wpb * 32, sm));
-  if (const char* e = getenv("PWB_OPT_CTAS_PER_SM")) { int v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }
   const int resident = c->num_sms * (per_sm > 0 ? per_sm : 1);
   if (ctas > resident) ctas = resident;
   k_opt_pore<<<ctas, wpb * 32, sm, s>>>(*b, w);
