@@ -149,7 +149,7 @@ def analyse_cells(coords, elements, lattice=None, rebuild=False, tol=0.4, engine
                           max_atoms=max_atoms, **kw)
         frame_idx = torch.arange(F, device=dev)[:, None].expand(F, mol_cap)[mmask].cpu().numpy()
         mol_idx = torch.arange(mol_cap, device=dev)[None, :].expand(F, mol_cap)[mmask].cpu().numpy()
-        keys = [(int(f), int(k)) for f, k in zip(frame_idx, mol_idx)]
+        keys = list(zip(frame_idx.tolist(), mol_idx.tolist()))      # python ints, without a numpy scalar per entry
         return out.host_records(), keys, sizes.cpu().numpy()
 
 
