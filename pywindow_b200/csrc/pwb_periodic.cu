@@ -39,6 +39,7 @@ struct DmArgs {
   unsigned* vis;     // [F][ceil(27N/32)]
   unsigned char* rem;  // [F][N]
   int* front;        // [F][2][out_cap]
+  double* seed_d;    // [F][N] distance of every atom to the pseudo origin (k_dm_fill)
   // outputs
   int* n_mol;        // [F]
   int* mol_off;      // [F][mol_cap+1]
@@ -355,23 +356,28 @@ k_dm_fill(DmArgs A) {
   const double yy = __dadd_rn(__dadd_rn(__dmul_rn(psx, psx), __dmul_rn(psy, psy)), __dmul_rn(psz, psz));
   int nout = 0, nmol = 0, st = 0;
   if (lane == 0) moff[0] = 0;
+  // distance of every atom to the pseudo origin, once, with sklearn's euclidean_distances operation order
+  // (utilities.py:944-953); the seed searches below only compare
+  double* sd = A.seed_d + (size_t)f * N;
+  for (int a = lane; a < N; a += 32) {
+    double x = xr[3 * a], y = xr[3 * a + 1], z = xr[3 * a + 2];
+    double dot = __dadd_rn(__dadd_rn(__dmul_rn(x, psx), __dmul_rn(y, psy)), __dmul_rn(z, psz));
+    double xx = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), xx), yy);
+    sd[a] = A.type_terminal[A.atom_type[a]] ? PWB_INF : sqrt(fmax(d2, 0.0));     // terminal atoms never seed
+  }
+  for (int w = lane; w < vis_words; w += 32) vis[w] = 0u;
+  __syncwarp();
   while (true) {
-    // ---- seed: remaining non-terminal atom closest to the pseudo origin, first arg-min, with
-    // sklearn's euclidean_distances operation order (utilities.py:944-953)
+    // ---- seed: remaining non-terminal atom closest to the pseudo origin, first arg-min
     ValIdx best; best.v = PWB_INF; best.i = 0x7fffffff;
     for (int a = lane; a < N; a += 32) {
-      if (!rem[a] || A.type_terminal[A.atom_type[a]]) continue;
-      double x = xr[3 * a], y = xr[3 * a + 1], z = xr[3 * a + 2];
-      double dot = __dadd_rn(__dadd_rn(__dmul_rn(x, psx), __dmul_rn(y, psy)), __dmul_rn(z, psz));
-      double xx = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
-      double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), xx), yy);
-      ValIdx c; c.v = sqrt(fmax(d2, 0.0)); c.i = a;
-      best = vi_min(best, c);
+      if (!rem[a]) continue;
+      ValIdx c; c.v = sd[a]; c.i = a;
+      if (c.v < PWB_INF) best = vi_min(best, c);
     }
     best = warp_vi_min(best);
     if (best.i == 0x7fffffff) break;
-    for (int w = lane; w < vis_words; w += 32) vis[w] = 0u;
-    __syncwarp();
     const int start = nout;
     int overflow = 0;
     if (lane == 0) {
@@ -429,6 +435,7 @@ k_dm_fill(DmArgs A) {
     double mx = 0, my = 0, mz = 0, mt = 0;
     for (int q = start + lane; q < nout; q += 32) {
       const int p = osrc[q];
+      vis[p >> 5] = 0u;                            // every set bit belongs to a node of this molecule
       const int a = p % N, img = p / N;
       double X, Y, Z;
       if (!A.rebuild || img == 13) { X = xr[3 * a]; Y = xr[3 * a + 1]; Z = xr[3 * a + 2]; }
@@ -481,8 +488,13 @@ int pwb_dm_workspace_layout(int F, int N, int out_cap, pwb_dm_layout* L) {
   L->vis = o; o = up256(o + sizeof(unsigned) * (size_t)F * ((27 * (size_t)N + 31) / 32));
   L->rem = o; o = up256(o + (size_t)F * N);
   L->front = o; o = up256(o + sizeof(int) * (size_t)F * 2 * out_cap);
+  o = up256(o + sizeof(double) * (size_t)F * N);      // seed distances, see dm_seed_offset
   L->total = o;
   return 0;
+}
+// the per-atom distances to the pseudo origin (k_dm_fill) live behind the frontier buffers
+static size_t dm_seed_offset(const pwb_dm_layout& L, int F, int out_cap) {
+  return up256(L.front + sizeof(int) * (size_t)F * 2 * out_cap);
 }
 size_t pwb_dm_workspace_bytes(int F, int N, int out_cap) {
   pwb_dm_layout L;
@@ -517,6 +529,7 @@ int pwb_discrete_molecules(int F, int N, int rebuild, double tol, double max_cov
   A.frame_d = (double*)(p + L.frame_d); A.frac = (double*)(p + L.frac); A.xr = (double*)(p + L.xr);
   A.adj = (unsigned*)(p + L.adj); A.deg = (int*)(p + L.deg); A.vis = (unsigned*)(p + L.vis);
   A.rem = (unsigned char*)(p + L.rem); A.front = (int*)(p + L.front);
+  A.seed_d = (double*)(p + dm_seed_offset(L, F, out_cap));
   A.n_mol = n_mol; A.mol_off = mol_off; A.out_src = out_src; A.out_xyz = out_xyz; A.status = status;
   k_dm_prepare<<<F, 128, 0, s>>>(A);
   const size_t cl_smem = DM_CL_SMEM(N);
