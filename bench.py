@@ -353,7 +353,7 @@ def run_ours(args):
         "arithmetic": "f64 kernels; FLOP counted by the SURVEY 8(d) per-frame work formula",
     }
     cores = os.cpu_count() or 1
-    n_cpu = 0 if args.skip_cpu else min(max(32 * cores, 64), 2048)
+    n_cpu = 0 if args.skip_cpu else min(max(128 * cores, 256), 4096)      # ~10-15 s of all-core CPU work
     cpu_fps, cpu_dt = cpu_baseline(elements, synth(seeds, 0, n_cpu), cores) if n_cpu else (None, 0.0)
     nwin = rec_h[:, L.REC_NWIN]
     line = {
