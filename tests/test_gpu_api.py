@@ -122,3 +122,23 @@ def test_host_buffer_entry_point_matches_device_path():
         streams[k].synchronize()
     np.testing.assert_array_equal(outs[0].numpy(), h)
     np.testing.assert_array_equal(outs[1].numpy(), h[::-1])
+
+
+def test_xyz_and_pdb_trajectory_analysis_matches_per_frame(tmp_path):
+    """XYZ / PDB trajectories through the native frame decoders (pwb_xyz_decode, pwb_pdb_decode) and one GPU
+    batch == Molecule.full_analysis of every frame decoded by the Python reader."""
+    import pywindow_b200 as pw
+    from pywindow_b200 import synthetic
+    gs = [load_golden(f"md_frame{i:02d}") for i in range(4)]
+    X = np.stack([g["coords"] for g in gs])
+    el = gs[0]["elements"]
+    synthetic.write_xyz_trajectory(tmp_path / "t.xyz", el, X)
+    synthetic.write_pdb_trajectory(tmp_path / "t.pdb", el, X)
+    for t in (pw.XYZ(tmp_path / "t.xyz"), pw.PDB(tmp_path / "t.pdb")):
+        assert t.no_of_frames == 4
+        t.analysis(frames="all")
+        assert sorted(t.analysis_output) == [0, 1, 2, 3]
+        for f in range(4):
+            p = t.get_frames(f)[f].system_to_molecule().full_analysis()
+            assert pw.compare_properties_dict(p, t.analysis_output[f]["0"]) == (True, "none"), (type(t).__name__, f)
+            assert len(p["windows"]["diameters"]) == 4
