@@ -73,3 +73,22 @@ def test_tables_are_the_reference_tables(ref):
     assert MT.atomic_mass == RT.atomic_mass and MT.atomic_vdw_radius == RT.atomic_vdw_radius
     assert MT.atomic_covalent_radius == RT.atomic_covalent_radius
     assert MT.opls_atom_keys == RT.opls_atom_keys and MT.periodic_table == RT.periodic_table
+
+
+def test_xyz_trajectory_decode_against_reference(ref, tmp_path):
+    """The native XYZ frame map / decoder against the reference's own XYZ trajectory reader
+    (trajectory.py:792-915) on a file it maps correctly (non-numeric comment lines)."""
+    pw, U = ref
+    import pywindow_b200 as mine
+    from pywindow_b200 import synthetic
+    gs = [load_golden(f"md_frame{i:02d}") for i in range(3)]
+    X = np.stack([g["coords"] for g in gs])
+    synthetic.write_xyz_trajectory(tmp_path / "t.xyz", gs[0]["elements"], X)
+    a, b = pw.XYZ(str(tmp_path / "t.xyz")), mine.XYZ(tmp_path / "t.xyz")
+    assert a.no_of_frames == b.no_of_frames == 3
+    native = b._decode_coordinates([0, 1, 2])
+    for f in range(3):
+        ra = a.get_frames(f)[f].system
+        np.testing.assert_array_equal(native[f], np.asarray(ra["coordinates"], dtype=np.float64))
+        rb = b.get_frames(f)[f].system
+        assert list(rb["atom_ids"]) == list(ra["atom_ids"])      # the reference keeps XYZ symbols as atom_ids
