@@ -24,6 +24,16 @@ inline const char* skip_line(const char* p, const char* end) {
   return q ? q + 1 : end;
 }
 
+// eight ASCII digits packed in a little-endian word: test and convert without a loop
+inline bool all_digits8(uint64_t w) {
+  return (((w & 0xF0F0F0F0F0F0F0F0ull) | (((w + 0x0606060606060606ull) & 0xF0F0F0F0F0F0F0F0ull) >> 4)) == 0x3333333333333333ull);
+}
+inline uint32_t parse_digits8(uint64_t w) {
+  w = (w & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;
+  w = (w & 0x00FF00FF00FF00FFull) * 6553601 >> 16;
+  return (uint32_t)((w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32);
+}
+
 // parse one floating point token starting at p (leading blanks skipped); returns pointer past it
 inline const char* parse_double(const char* p, const char* end, double* out, bool* ok) {
   while (p < end && (*p == ' ' || *p == '\t')) p++;
@@ -40,6 +50,14 @@ inline const char* parse_double(const char* p, const char* end, double* out, boo
   }
   if (p < end && *p == '.') {
     p++;
+    // eight fraction digits at a time (SWAR) once the mantissa is non-zero, i.e. every digit is significant
+    while (digits > 0 && digits <= 11 && end - p >= 8) {
+      uint64_t w;
+      memcpy(&w, p, 8);
+      if (!all_digits8(w)) break;
+      mant = mant * 100000000ull + parse_digits8(w);
+      digits += 8; exp10 -= 8; p += 8; any = true;
+    }
     while (p < end && *p >= '0' && *p <= '9') {
       if (digits < 19) { mant = mant * 10 + (uint64_t)(*p - '0'); digits += (mant != 0); exp10--; }
       else if (*p != '0') exact = false;
