@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PWB_ABI_VERSION 1
+#define PWB_ABI_VERSION 2
 #define PWB_MAX_TYPES 16
 
 /* ---- result record: `rec_stride` doubles per item (>= PWB_REC_WIN0 + 4*win_cap) --------------- */
@@ -100,6 +100,9 @@ typedef struct pwb_batch {
   const double* type_vdw;    /* [n_types]                                                         */
   const double* type_mass;   /* [n_types]                                                         */
   const double* centre_override; /* optional [F][3]: use instead of optimising (teacher forcing)  */
+  /* opt_pore_diameter(bounds=, com=) (utilities.py:400-426); both optional (NULL = reference defaults) */
+  const double* opt_start;   /* [F][3] start point x0 instead of the centre of mass                */
+  const double* opt_bounds;  /* [F][3][2] (lo, hi) per axis, +-inf = unbounded, instead of x0 +- pore radius */
   /* outputs / scratch */
   double* records;           /* [F][rec_stride]                                                   */
   void* workspace;           /* pwb_workspace_bytes() bytes                                       */

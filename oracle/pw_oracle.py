@@ -93,10 +93,12 @@ def pore_diameter(r, X, c):
     return float(a[i] * 2), i
 
 
-def opt_pore_diameter(r, X, com):
-    """U:400-426 -- L-BFGS-B (scipy defaults) on -pore_diameter inside the box COM +- pore_r."""
-    pore_r = pore_diameter(r, X, com)[0] / 2
-    bounds = tuple((com[k] - pore_r, com[k] + pore_r) for k in range(3))
+def opt_pore_diameter(r, X, com, bounds=None):
+    """U:400-426 -- L-BFGS-B (scipy defaults) on -pore_diameter from ``com`` inside ``bounds`` (default: the box
+    com +- pore_r, pore_r measured at ``com``)."""
+    if bounds is None:
+        pore_r = pore_diameter(r, X, com)[0] / 2
+        bounds = tuple((com[k] - pore_r, com[k] + pore_r) for k in range(3))
     res = minimize(lambda c: -pore_diameter(r, X, c)[0], x0=com, bounds=bounds)
     d, i = pore_diameter(r, X, res.x)
     return d, i, res.x

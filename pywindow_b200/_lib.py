@@ -40,6 +40,7 @@ class Batch(ctypes.Structure):
         ("pore_opt", ctypes.c_int32), ("total_atoms", ctypes.c_int32),
         ("coords", ctypes.c_void_p), ("item_off", ctypes.c_void_p), ("atom_type", ctypes.c_void_p),
         ("type_vdw", ctypes.c_void_p), ("type_mass", ctypes.c_void_p), ("centre_override", ctypes.c_void_p),
+        ("opt_start", ctypes.c_void_p), ("opt_bounds", ctypes.c_void_p),
         ("records", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
     ]
 
@@ -104,7 +105,7 @@ def load():
     L.pwb_fma_peak.restype = ci
     L.pwb_launch_count.argtypes = [vp]
     L.pwb_launch_count.restype = ctypes.c_longlong
-    if L.pwb_abi_version() != 1:
+    if L.pwb_abi_version() != 2:
         raise PwbLibraryError("libpwb.so ABI version mismatch")
     _lib = L
     return L

@@ -338,15 +338,17 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 // =================================================================================================
 constexpr int OPT_WARPS = 4;
 
+// NBD >= 0: every variable has that bound type (compile time); NBD < 0: per-variable types in `nbd`
+template <int NBD>
 struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-point differences
-  WarpAtoms A; const double* lo; const double* hi; int nfev;   // all three variables boxed (nbd = 2)
+  WarpAtoms A; const double* lo; const double* hi; const int* nbd; int nfev;
   __device__ void fg(const double* x, double& f, double* g) {
     nfev += 4;
     double px[4], py[4], pz[4], h[3], m[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
 #pragma unroll
-    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], 2, lo[i], hi[i]);
+    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], NBD >= 0 ? NBD : nbd[i], lo[i], hi[i]);
     px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
     warp_min_clear<4>(A, px, py, pz, m);
     f = -(m[0] * 2.0);
@@ -359,8 +361,9 @@ struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-p
 #define OPT_MINB 8
 #endif
 // doubles of shared memory per warp: double4[NA] atoms, the L-BFGS ring, class starts (17 ints, padded), bounds
-#define OPT_WARP_DOUBLES(NA) ((((NA) * 4 + LB_STORAGE(3) + 10 + 6) + 1) & ~(size_t)1)   // even: double4 tiles
+#define OPT_WARP_DOUBLES(NA) ((((NA) * 4 + LB_STORAGE(3) + 10 + 6 + 2) + 1) & ~(size_t)1)   // even: double4 tiles
 // one item on one warp; `smw` is the warp's private shared memory
+template <bool GENERAL>
 __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, const int item, const int lane, double* smw) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
@@ -386,18 +389,43 @@ __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, 
     st = -1;
   } else {
     double pore_r = rec[PWB_REC_PORE_D] / 2.0;
-    if (pore_r < 0) {   // scipy raises on inverted bounds; the reference has no handler
-      if (lane == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
-      return;
+    if (b.opt_start) {   // opt_pore_diameter(com=...): start there; the default box is built around it (:411-420)
+      const double* o = b.opt_start + (size_t)item * 3;
+      c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+      if (!b.opt_bounds) pore_r = warp_pore_argmin(A, orig, c[0], c[1], c[2]).v;
     }
     double* lo = (double*)(cls + 20);                          // [3], [3]: box bounds, one copy per warp
     double* hi = lo + 3;
+    int* nbd = (int*)(hi + 3);                                 // [3] (general path only)
+    bool bad = false;
+    if (b.opt_bounds) {
+      const double* ob = b.opt_bounds + (size_t)item * 6;
 #pragma unroll
-    for (int i = 0; i < 3; i++) if (lane == i) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
+      for (int i = 0; i < 3; i++) {
+        const double l = ob[2 * i], h = ob[2 * i + 1];
+        const bool fl = l > -PWB_INF, fh = h < PWB_INF;       // +-inf (or beyond 1e300) = no bound
+        bad |= fl && fh && l > h;
+        if (lane == i) { lo[i] = l; hi[i] = h; nbd[i] = fl ? (fh ? 2 : 1) : (fh ? 3 : 0); }
+      }
+    } else {
+      bad = pore_r < 0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (lane == i) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
+    }
+    if (bad) {   // scipy raises on inverted bounds; the reference has no handler
+      if (lane == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+      return;
+    }
     __syncwarp();
-    DevPoreObj3 obj{A, lo, hi, 0};
-    st = lbfgsb_minimize<3, DevPoreObj3, 2>(obj, c, lo, hi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
-    nfev = obj.nfev;
+    if (GENERAL) {
+      DevPoreObj3<-1> obj{A, lo, hi, nbd, 0};
+      st = lbfgsb_minimize<3, DevPoreObj3<-1>, -1>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
+      nfev = obj.nfev;
+    } else {
+      DevPoreObj3<2> obj{A, lo, hi, nullptr, 0};
+      st = lbfgsb_minimize<3, DevPoreObj3<2>, 2>(obj, c, lo, hi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
+      nfev = obj.nfev;
+    }
   }
   ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
   if (lane == 0) {
@@ -411,6 +439,9 @@ __device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, 
 // Warps pull items from a queue (one atomic per item): the iteration counts of the optimiser vary by
 // 10x between frames, so a static item -> warp map leaves CTAs waiting for their slowest warp and the
 // last wave mostly empty.
+// GENERAL: user-supplied, possibly one-sided or absent bounds (opt_pore_diameter(bounds=...)); the default
+// instantiation has every variable boxed at compile time.
+template <bool GENERAL>
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)
 k_opt_pore(pwb_batch b, Ws ws) {
   extern __shared__ __align__(16) double sm[];
@@ -422,7 +453,7 @@ k_opt_pore(pwb_batch b, Ws ws) {
     if (lane == 0) item = atomicAdd(queue, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= b.n_items) break;
-    opt_pore_item(b, ws, item, lane, smw);
+    opt_pore_item<GENERAL>(b, ws, item, lane, smw);
     __syncwarp();
   }
 }
@@ -613,7 +644,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       const int chunks = (int)py_floordiv(nr, b.increment);
       const double cxs = px / chunks, cys = py / chunks, czs = pz / chunks;
       const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
-      const int jmax = chunks > 0 ? chunks - 1 : 0;
+      const int jmax = chunks > 0 ? chunks : 0;     // steps 0..chunks inclusive (range(chunks + 1), :1112)
       double bestv = PWB_INF;
       int bestj = 0;
       for (int c = 0; c < b.n_types; c++) {
@@ -1646,14 +1677,15 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   int wpb = OPT_WARPS;
   while (wpb > 1 && per_warp * wpb > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb;
-  if (set_smem(k_opt_pore, sm, c->max_smem)) return 1;
+  auto kern = b->opt_bounds ? k_opt_pore<true> : k_opt_pore<false>;
+  if (set_smem(kern, sm, c->max_smem)) return 1;
   CK(cudaMemsetAsync(w.item_i + I_QUEUE, 0, sizeof(int), s));
   int ctas = (b->n_items + wpb - 1) / wpb;
   int per_sm = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_opt_pore, wpb * 32, sm));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, sm));
   const int resident = c->num_sms * (per_sm > 0 ? per_sm : 1);
   if (ctas > resident) ctas = resident;
-  k_opt_pore<<<ctas, wpb * 32, sm, s>>>(*b, w);
+  kern<<<ctas, wpb * 32, sm, s>>>(*b, w);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1763,6 +1795,8 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       t.item_off = b->item_off + first;
       t.records = b->records + (size_t)first * b->rec_stride;
       if (b->centre_override) t.centre_override = b->centre_override + (size_t)first * 3;
+      if (b->opt_start) t.opt_start = b->opt_start + (size_t)first * 3;
+      if (b->opt_bounds) t.opt_bounds = b->opt_bounds + (size_t)first * 6;
       Ws u = w;
       u.item_d += (size_t)first * ITEM_D; u.item_i += (size_t)first * ITEM_I;
       u.clear_k += (size_t)first * b->ray_cap; u.clear_pos += (size_t)first * b->ray_cap;

@@ -128,7 +128,8 @@ class Engine:
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
 
     def _make_batch(self, coords, item_off, atom_type, type_vdw, type_mass, shared_types, max_atoms,
-                    centre_override, stages, adjust, increment, increment2, pore_opt, ray_cap):
+                    centre_override, stages, adjust, increment, increment2, pore_opt, ray_cap,
+                    opt_start=None, opt_bounds=None):
         F = int(item_off.numel() - 1)
         total = int(coords.shape[0])
         b = _lib.Batch()
@@ -140,6 +141,8 @@ class Engine:
         b.coords, b.item_off, b.atom_type = coords.data_ptr(), item_off.data_ptr(), atom_type.data_ptr()
         b.type_vdw, b.type_mass = type_vdw.data_ptr(), type_mass.data_ptr()
         b.centre_override = centre_override.data_ptr() if centre_override is not None else None
+        b.opt_start = opt_start.data_ptr() if opt_start is not None else None
+        b.opt_bounds = opt_bounds.data_ptr() if opt_bounds is not None else None
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if ray_cap is None:
             cap = ctypes.c_int(0)
@@ -151,7 +154,7 @@ class Engine:
 
     def analyse(self, coords, item_off, atom_type, type_vdw, type_mass, *, shared_types, max_atoms,
                 centre_override=None, stages=_lib.STAGE_ALL, adjust=1.0, increment=1.0, increment2=0.1,
-                pore_opt=True, ray_cap=None):
+                pore_opt=True, ray_cap=None, opt_start=None, opt_bounds=None):
         """Run the stages on a batch whose inputs are (or are moved to) device tensors."""
         if int(item_off.shape[0] if hasattr(item_off, "shape") else len(item_off)) <= 1:      # empty batch
             empty = torch.zeros((0, self.rec_stride), dtype=torch.float64, device=self.device)
@@ -165,9 +168,17 @@ class Engine:
             type_mass = self._dev(type_mass, torch.float64)
             if centre_override is not None:
                 centre_override = self._dev(centre_override, torch.float64).view(-1, 3)
+            if opt_start is not None:
+                opt_start = self._dev(opt_start, torch.float64).view(-1, 3)
+            if opt_bounds is not None:
+                opt_bounds = self._dev(opt_bounds, torch.float64).view(-1, 6)
+            n_items = int(item_off.numel() - 1)
+            for name, t in (("centre_override", centre_override), ("opt_start", opt_start), ("opt_bounds", opt_bounds)):
+                if t is not None and t.shape[0] != n_items:
+                    raise ValueError(f"{name} needs one row per item ({n_items}), got {t.shape[0]}")
             b, stream, F, total = self._make_batch(coords, item_off, atom_type, type_vdw, type_mass,
                                                    shared_types, max_atoms, centre_override, stages, adjust,
-                                                   increment, increment2, pore_opt, ray_cap)
+                                                   increment, increment2, pore_opt, ray_cap, opt_start, opt_bounds)
             layout = _lib.WsLayout()
             self.lib.pwb_workspace_layout(F, total, b.ray_cap, self.win_cap, ctypes.byref(layout))
             ws = torch.empty(layout.total, dtype=torch.uint8, device=self.device)
@@ -175,7 +186,7 @@ class Engine:
             b.records, b.workspace, b.workspace_bytes = rec.data_ptr(), ws.data_ptr(), layout.total
             _lib.check(self.lib.pwb_full_analysis_batch(self._ctx, ctypes.byref(b), stream))
             res = BatchResult(rec, ws, layout, F, total, b.ray_cap, self.win_cap)
-            res._keep = (coords, item_off, atom_type, type_vdw, type_mass, centre_override)
+            res._keep = (coords, item_off, atom_type, type_vdw, type_mass, centre_override, opt_start, opt_bounds)
             return res
 
     def analyse_frames(self, coords, elements, **kw):
@@ -206,7 +217,7 @@ class Engine:
         F, N = int(coords_host.shape[0]), int(coords_host.shape[1])
         with torch.cuda.device(self.device):
             st = state if state is not None else {}
-            key = (F, N, ray_cap, tuple(str(e) for e in elements[:8]))
+            key = (F, N, ray_cap, self.win_cap, self.rec_stride, tuple(str(e) for e in elements))
             if st.get("key") != key:
                 types, vdw, mass = element_types(elements)
                 st.clear()

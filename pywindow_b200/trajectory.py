@@ -91,7 +91,7 @@ class LazyFrame(dict):
         return dict.__iter__(self._load())
 
     def __len__(self):
-        return dict.__len__(self) + len(self._pending)
+        return dict.__len__(self) + len({p[0] for p in self._pending if not dict.__contains__(self, p[0])})
 
     def __contains__(self, k):
         return dict.__contains__(self, k) or any(p[0] == k for p in self._pending)
@@ -210,11 +210,14 @@ class Trajectory:
         gc_was_on = gc.isenabled()
         gc.disable()
         try:
+            # every analysed frame REPLACES its entry (analysis_output[frame] = results, trajectory.py:483,
+            # :522): with override=True no stale molecule keys of an earlier run survive
+            fresh = set()
             for row, (frame, mol_key) in enumerate(keys):
-                fr = out.get(frame)
-                if not isinstance(fr, LazyFrame):
-                    fr = out[frame] = LazyFrame()
-                fr._add(mol_key, records, row)
+                if frame not in fresh:
+                    fresh.add(frame)
+                    out[frame] = LazyFrame()
+                out[frame]._add(mol_key, records, row)
         finally:
             if gc_was_on:
                 gc.enable()
@@ -489,12 +492,16 @@ class PDB(Trajectory):
         super().__init__(filepath)
         with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
             start, k, size = 0, 0, len(mm)
-            for m in re.finditer(rb"^END[^D\n]*\n?", mm, flags=re.MULTILINE):
-                if mm[start:m.start()].strip():
+            # whole-line END / ENDMDL records only (the reference splits on lines that are exactly "END",
+            # trajectory.py:960-975); a slice is a frame only if it holds an atom record, so the closing END
+            # after the last ENDMDL of a multi-model file does not become an empty frame
+            atom_rec = re.compile(rb"^(?:ATOM  |HETATM)", flags=re.MULTILINE)
+            for m in re.finditer(rb"^(?:ENDMDL|END)[ \t\r]*$\n?", mm, flags=re.MULTILINE):
+                if atom_rec.search(mm, start, m.start()):
                     self.trajectory_map[k] = [start, m.end()]
                     k += 1
                 start = m.end()
-            if start < size and b"ATOM" in mm[start:size] or (start < size and b"HETATM" in mm[start:size]):
+            if start < size and atom_rec.search(mm, start, size):
                 self.trajectory_map[k] = [start, size]
                 k += 1
         self.no_of_frames = k

@@ -110,11 +110,19 @@ def pore_diameter(elements, coordinates, com=None):
 
 
 def opt_pore_diameter(elements, coordinates, bounds=None, com=None):
-    """utilities.py:400-426 -> (diameter, closest atom, centre).  The GPU path implements the
-    reference's default call (box = COM +- pore radius, start at the COM)."""
-    if bounds is not None or com is not None:
-        raise NotImplementedError("custom bounds / start point are not on the accelerated path")
-    rec = _run(elements, coordinates, _lib.STAGE_SCALARS | _lib.STAGE_OPT)
+    """utilities.py:400-426 -> (diameter, closest atom, centre).  ``com`` is the optimiser's start point
+    (default: the centre of mass); ``bounds`` = ((lo, hi),) * 3 with ``None`` for a missing side (default: the box
+    start +- pore radius at the start point).  Inverted bounds raise scipy's ``ValueError`` like the reference."""
+    kw = {}
+    if com is not None:
+        kw["opt_start"] = np.asarray(com, dtype=np.float64).reshape(1, 3)
+    if bounds is not None:
+        bb = np.array([[-np.inf if lo is None else float(lo), np.inf if hi is None else float(hi)]
+                       for lo, hi in bounds], dtype=np.float64)
+        if bb.shape != (3, 2):
+            raise ValueError("bounds must be three (lower, upper) pairs")
+        kw["opt_bounds"] = bb.reshape(1, 6)
+    rec = _run(elements, coordinates, _lib.STAGE_SCALARS | _lib.STAGE_OPT, **kw)
     if int(rec[_lib.REC_STATUS]) & _lib.ST_OPT_BOUNDS:
         raise ValueError("An upper bound is less than the corresponding lower bound.")
     return (float(rec[_lib.REC_OPT_D]), int(rec[_lib.REC_OPT_ATOM]),
@@ -137,6 +145,10 @@ def find_windows(elements, coordinates, processes=None, adjust=1, pore_opt=True,
     kw = {"adjust": float(adjust), "increment": float(increment), "pore_opt": bool(pore_opt)}
     if pore_centre is not None:
         kw["centre_override"] = np.asarray(pore_centre, dtype=np.float64).reshape(1, 3)
+    elif not pore_opt:
+        # the reference never calls opt_pore_diameter here (utilities.py:1386-1393): a molecule whose COM lies
+        # inside an atom's vdW sphere must still return its windows instead of scipy's inverted-bounds error
+        stages &= ~_lib.STAGE_OPT
     rec = _run(elements, coordinates, stages, **kw)
     if int(rec[_lib.REC_STATUS]) & _lib.ST_OPT_BOUNDS:
         raise ValueError("An upper bound is less than the corresponding lower bound.")

@@ -266,3 +266,97 @@ def test_seeded_synthetic_frames_against_oracle(eng):
         np.testing.assert_allclose(g[0], w[0], atol=1e-3)
         np.testing.assert_allclose(g[1], w[1], atol=5e-3)
     assert near >= 0.6 * X.shape[0]        # free-running pore centre: the reference's own noise floor
+
+
+def test_path_scan_includes_the_ray_end_point(eng):
+    """vector_analysis evaluates steps 0..chunks INCLUSIVE (utilities.py:1112).  On sparse lopsided shells with an
+    off-centre ray origin the narrowest point of many clear rays IS the end point, so dropping it changes
+    2*min clearance, the arg-min step and sometimes the clear flag.  Clear-ray list, arg-min steps and
+    clearances must equal the oracle's stepped scan exactly."""
+    import pw_oracle as O
+    hit_last = 0
+    for seed in (1, 7, 11):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(20, 60))
+        u = rng.normal(size=(n, 3))
+        u /= np.linalg.norm(u, axis=1)[:, None]
+        X = u * (rng.uniform(5, 9, size=(n, 1)) * np.array([1 + 0.6 * (u[:, 0] > 0)]).T)
+        el = np.array(["C", "H", "N"])[rng.integers(0, 3, size=n)]
+        r, m = O.vdw_of(el), O.masses_of(el)
+        centre = O.center_of_mass(m, X) + rng.uniform(-2, 2, 3)
+        det = {}
+        O.find_windows(r, m, X, centre=centre, detail=det)
+        res = eng.analyse_molecules([(el, X)], centre_override=centre[None])
+        rec = res.host_records()[0]
+        S = int(rec[17])                                    # PWB_REC_NCLEAR
+        want = np.nonzero(det["clear"])[0]
+        assert S == len(want) and (res.clear_k.cpu().numpy()[0, :S] == want).all(), seed
+        recs = det["records"]
+        np.testing.assert_allclose(res.clear_a2.cpu().numpy()[0, :S], recs[:, 1], atol=1e-9)
+        Rn = np.linalg.norm(recs[:, 5:8], axis=1)
+        chunks = np.floor_divide(Rn, 1.0)
+        pos = np.rint(recs[:, 0] / (Rn / chunks)).astype(int)
+        assert (res.clear_pos.cpu().numpy()[0, :S] == pos).all(), seed
+        hit_last += int((pos == chunks).sum())
+    assert hit_last > 20, "the cases must exercise the last path step"
+
+
+def test_find_windows_without_pore_optimisation_ignores_inverted_bounds(eng):
+    """find_windows(pore_opt=False) never calls opt_pore_diameter in the reference (utilities.py:1386-1393): a
+    molecule whose COM sits inside an atom's vdW sphere still gets its ray analysis instead of scipy's
+    inverted-bounds ValueError."""
+    import pw_oracle as O
+    from pywindow_b200 import utilities as U
+    g = load_golden("md_frame00")
+    el = np.concatenate([g["elements"], np.array(["C"])])
+    r0, m0 = O.vdw_of(g["elements"]), O.masses_of(g["elements"])
+    X = np.concatenate([g["coords"], O.center_of_mass(m0, g["coords"])[None] + 0.05])   # an atom on the COM
+    with pytest.raises(ValueError):
+        U.find_windows(el, X)
+    got = U.find_windows(el, X, pore_opt=False)
+    want = O.find_windows(O.vdw_of(el), O.masses_of(el), X, pore_opt=False)
+    assert (got is None) == (want is None)
+    if want is not None:
+        assert len(got[0]) == len(want[0])
+        np.testing.assert_allclose(got[0], want[0], atol=1e-3)
+
+
+def test_opt_pore_diameter_bounds_and_start_point(eng):
+    """opt_pore_diameter(bounds=..., com=...) (utilities.py:400-426): custom start point, custom / one-sided /
+    absent bounds, degenerate and inverted boxes -- against the oracle (same scipy call as the reference)."""
+    import pw_oracle as O
+    from pywindow_b200 import utilities as U
+    g = load_golden("md_frame05")
+    el, X = g["elements"], g["coords"]
+    r, m = O.vdw_of(el), O.masses_of(el)
+    com = O.center_of_mass(m, X)
+    start = com + np.array([0.4, -0.3, 0.2])
+    cases = [
+        dict(com=start),                                                                   # box around the start point
+        dict(bounds=tuple((c - 1.0, c + 1.0) for c in com)),                               # custom box, default start
+        dict(bounds=tuple((c - 0.7, c + 1.2) for c in start), com=start),
+        dict(bounds=((com[0] - 0.5, None), (None, com[1] + 0.5), (None, None)), com=com),  # one-sided / unbounded
+    ]
+    close = 0
+    for kw in cases:
+        d, a, c = U.opt_pore_diameter(el, X, **kw)
+        x0 = kw.get("com", com)
+        od, oa, oc = O.opt_pore_diameter(r, X, np.asarray(x0), kw.get("bounds"))
+        # the returned diameter / atom are pore_diameter at the returned centre, and the optimiser did not lose
+        pd_, pa = O.pore_diameter(r, X, c)
+        assert abs(d - pd_) < 1e-9 and a == pa
+        assert d >= O.pore_diameter(r, X, np.asarray(x0))[0] - 1e-12
+        if "bounds" in kw:
+            for k, (lo, hi) in enumerate(kw["bounds"]):
+                assert (lo is None or c[k] >= lo) and (hi is None or c[k] <= hi)
+        else:
+            pr = O.pore_diameter(r, X, np.asarray(x0))[0] / 2
+            assert (np.abs(c - x0) <= pr + 1e-12).all()
+        assert abs(d - od) < 5e-2, (kw, d, od)       # chaotic stopping point: the reference's own noise floor
+        close += abs(d - od) <= 1e-3
+    assert close >= 2
+    # degenerate box: nothing to optimise, the answer is pore_diameter(start) exactly
+    d, a, c = U.opt_pore_diameter(el, X, bounds=tuple((v, v) for v in start), com=start)
+    assert np.array_equal(c, start) and abs(d - O.pore_diameter(r, X, start)[0]) < 1e-12
+    with pytest.raises(ValueError):
+        U.opt_pore_diameter(el, X, bounds=((1.0, -1.0), (0.0, 1.0), (0.0, 1.0)))

@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     lib.pwb_abi_version.restype = ctypes.c_int
-    assert lib.pwb_abi_version() == 1
+    assert lib.pwb_abi_version() == 2
     from pywindow_b200 import _lib
     assert set(_lib.EXPORTS) <= declared
 
@@ -223,3 +223,58 @@ def test_native_xyz_and_pdb_decoders_are_bit_exact(tmp_path):
     native = p._decode_coordinates(list(range(F)))
     np.testing.assert_array_equal(native, Trajectory._decode_coordinates(p, list(range(F))))
     np.testing.assert_array_equal(native, Xp)
+
+
+def test_pdb_model_endmdl_files_map_to_whole_frames(md):
+    """Multi-model PDB with MODEL/ENDMDL pairs and a closing END: frames are cut on whole-line END /
+    ENDMDL records only, the trailing END does not become an atom-less extra frame, and every frame decodes."""
+    tmp, el, X, syn = md
+    from pywindow_b200.trajectory import PDB
+    syn.write_pdb_trajectory(tmp / "plain.pdb", el, X)
+    frames = [f for f in re.split(r"^END[ \t]*\n", (tmp / "plain.pdb").read_text(), flags=re.M) if f.strip()]
+    assert len(frames) == 3
+    text = "".join(f"MODEL     {k + 1:4d}\n{body}ENDMDL\n" for k, body in enumerate(frames)) + "END\n"
+    (tmp / "models.pdb").write_text(text)
+    t = PDB(tmp / "models.pdb")
+    assert t.no_of_frames == 3 and sorted(k for k in t.trajectory_map) == [0, 1, 2]
+    got = t._decode_coordinates([0, 1, 2])
+    np.testing.assert_allclose(got, X, atol=6e-4)
+    # a residue / atom name that merely starts with END must not split a frame
+    weird = text.replace("MODEL        2\n", "MODEL        2\nREMARK ENDMDL is not a record here\n")
+    (tmp / "weird.pdb").write_text(weird)
+    assert PDB(tmp / "weird.pdb").no_of_frames == 3
+
+
+def test_lazyframe_len_and_override_semantics():
+    """LazyFrame counts a key once whether it is pending, loaded or both; analysis(override=True) replaces the
+    frame entry instead of merging into it (trajectory.py:483)."""
+    from pywindow_b200 import _lib
+    from pywindow_b200.trajectory import LazyFrame, Trajectory
+    rec = np.zeros((3, _lib.REC_WIN0 + 4 * 16))
+    rec[:, _lib.REC_STATUS] = _lib.ST_NO_CLEAR_RAY
+    rec[:, _lib.REC_NATOMS] = [5, 6, 7]
+    fr = LazyFrame()
+    fr._add(0, rec, 0)
+    fr._add(1, rec, 1)
+    assert len(fr) == 2
+    assert fr[1]["no_of_atoms"] == 6 and len(fr) == 2
+    fr._add(1, rec, 2)                       # same key pending again: still two keys
+    assert len(fr) == 2 and fr[1]["no_of_atoms"] == 7
+
+    class Fake(Trajectory):
+        def __init__(self):
+            self.analysis_output, self.no_of_frames, self.calls = {}, 2, 0
+
+        def _analyse_modular(self, frames, *a):
+            return rec[:2 * len(frames)], [(f, m) for f in frames for m in (0, 1)]
+
+        def _analyse_single(self, frames, *a):
+            return rec[:len(frames)], [(f, "0") for f in frames]
+
+    t = Fake()
+    t.analysis(frames=[0], modular=True)
+    assert sorted(t.analysis_output[0].keys()) == [0, 1]
+    t.analysis(frames=[0], modular=False, override=True)
+    assert list(t.analysis_output[0].keys()) == ["0"]          # no stale modular keys
+    t.analysis(frames=[0, 1], modular=False)                   # override=False keeps frame 0, adds frame 1
+    assert list(t.analysis_output[1].keys()) == ["0"]
