@@ -158,10 +158,12 @@ int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
  * the per-frame loop of Trajectory.analysis (trajectory.py:473-586) binds to.                      */
 int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream);
-/* Same without the final synchronisation (h_records must be pinned): the records are valid once
- * `stream` has been synchronised.  With two calls in flight on two streams -- each with its own staging
- * buffers and workspace -- the copies of one batch overlap the kernels of the other, which is how a
- * trajectory reader that decodes batch i+1 while batch i is analysed uses it.                       */
+/* Same without the final synchronisation (h_coords / h_records must be pinned): the records are valid once
+ * `stream` has been synchronised.  `d_coords` must be idle when the call is made (no earlier queued work still
+ * reads it): the input copies go to an internal copy stream and do NOT wait for work already queued on `stream`,
+ * so with two sets of staging buffers used alternately the copies of batch i+1 overlap the kernels of batch i --
+ * which is how a trajectory reader that decodes batch i+1 while batch i is analysed uses it
+ * (pywindow_b200.engine.FramePipeline).                                                              */
 int pwb_full_analysis_host_async(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                                  double* d_coords, double* d_records, int total_atoms, void* stream);
 
@@ -204,6 +206,14 @@ int64_t pwb_xyz_decode(const char* buf, int64_t len, const int64_t* starts, cons
                        int natoms, double* xyz, int threads);
 int64_t pwb_pdb_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
                        int natoms, double* xyz, int threads);
+
+/* Writer of the same HISTORY layout (keytrj 0; imcon 0 or 3): the synthetic trajectories of bench.py / tests that
+ * feed the reference's DLPOLY reader and pwb_history_decode alike.  keys: natoms x 8 blank-padded characters;
+ * lattice NULL | [9] | [n_frames][9] row-major (written transposed, as trajectory.py:723-726 reads it); coordinates
+ * as %20.10E, or DL_POLY's own %12.4E if compact.  Returns the file size, or -1.                                                                 */
+int64_t pwb_history_write(const char* path, const char* title, const char* keys, const double* masses,
+                          const double* xyz, int64_t n_frames, int natoms, const double* lattice,
+                          int lattice_per_frame, int compact, int threads);
 
 /* Measurement utility: sustained FMA throughput of the FP32 (fp64 = 0) or FP64 (fp64 = 1) pipe in
  * TFLOP/s, timed with CUDA events (the roofline denominator of this compute-bound path).          */

@@ -6,9 +6,12 @@
 // parallel by host threads straight into the [F, N, 3] float64 batch the GPU path consumes.
 // Numbers are converted with Clinger's exact fast path (mantissa < 2^53, |exp10| <= 22, one correctly
 // rounded multiply or divide), falling back to strtod -- bit-identical to Python's float().
+#include <fcntl.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <thread>
@@ -267,6 +270,63 @@ int64_t pwb_pdb_decode(const char* buf, int64_t len, const int64_t* starts, cons
     }
     return ok && a == natoms;
   });
+}
+
+// Write a DL_POLY HISTORY file (keytrj 0; imcon 0, or 3 with `lattice`) in the record layout the readers above
+// and the reference's DLPOLY class (trajectory.py:647-766) parse: fixed-width records, coordinates as %20.10E so a
+// float64 survives the round trip to 11 significant digits (compact != 0: DL_POLY's own %12.4E records, the
+// format of the reference's examples/data/input/HISTORY_singlemol_short).  Every frame has the same byte length, so host threads
+// format disjoint frame ranges and write them at their own offsets.  keys: natoms x 8 characters (blank padded);
+// lattice: NULL, [9] (lattice_per_frame = 0) or [n_frames][9], row-major, written transposed like the reference
+// reads it (trajectory.py:723-726).  Returns the file size in bytes, or -1.
+int64_t pwb_history_write(const char* path, const char* title, const char* keys, const double* masses,
+                          const double* xyz, int64_t n_frames, int natoms, const double* lattice,
+                          int lattice_per_frame, int compact, int threads) {
+  const int imcon = lattice ? 3 : 0;
+  const int cw = compact ? 12 : 20;                             // DL_POLY's own %12.4E records, or %20.10E
+  char head[512];
+  const int head_len = snprintf(head, sizeof head, "%.200s\n%10d%10d%10d\n", title, 0, imcon, natoms);
+  const int64_t frame_len = 61 + (lattice ? 3 * 61 : 0) + (int64_t)natoms * (43 + 3 * cw + 1);
+  const int fd = open(path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  if (fd < 0) return -1;
+  if (write(fd, head, (size_t)head_len) != head_len) { close(fd); return -1; }
+  std::atomic<int64_t> next(0);
+  std::atomic<int> failed(0);
+  const int64_t block = 64;                                     // frames per work item
+  auto work = [&]() {
+    std::vector<char> buf((size_t)(block * frame_len + 8));
+    while (!failed.load()) {
+      const int64_t f0 = next.fetch_add(block);
+      if (f0 >= n_frames) break;
+      const int64_t f1 = f0 + block < n_frames ? f0 + block : n_frames;
+      char* p = buf.data();
+      for (int64_t f = f0; f < f1; f++) {
+        p += sprintf(p, "timestep%10lld%10d%10d%10d%12.6f\n", (long long)(f + 1), natoms, 0, imcon, 0.0007);
+        if (lattice) {
+          const double* m = lattice + (lattice_per_frame ? f * 9 : 0);
+          for (int r = 0; r < 3; r++) p += sprintf(p, "%20.10f%20.10f%20.10f\n", m[r], m[3 + r], m[6 + r]);
+        }
+        const double* x = xyz + (size_t)f * natoms * 3;
+        for (int a = 0; a < natoms; a++) {
+          memcpy(p, keys + 8 * a, 8); p += 8;
+          p += sprintf(p, "%10d%12.6f%12.6f\n", a + 1, masses ? masses[a] : 1.0, 0.0);
+          p += compact ? sprintf(p, "%12.4E%12.4E%12.4E\n", x[3 * a], x[3 * a + 1], x[3 * a + 2])
+                       : sprintf(p, "%20.10E%20.10E%20.10E\n", x[3 * a], x[3 * a + 1], x[3 * a + 2]);
+        }
+      }
+      const int64_t want = (f1 - f0) * frame_len;
+      if (p - buf.data() != want ||        // a value wider than its field would shift every later frame
+          pwrite(fd, buf.data(), (size_t)want, (off_t)(head_len + f0 * frame_len)) != want) failed.store(1);
+    }
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; t++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  close(fd);
+  return failed.load() ? -1 : head_len + n_frames * frame_len;
 }
 
 }  // extern "C"

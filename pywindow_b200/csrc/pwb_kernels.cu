@@ -1768,7 +1768,8 @@ static int run_stages(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t 
 // Items are independent, so a large batch is cut into `chunks` contiguous sub-batches that run on
 // internal streams: the latency-bound optimiser kernels of one sub-batch overlap the FP-pipe-bound
 // ray / grid kernels of another, and the long tail of one kernel no longer idles the GPU.
-static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const double* h_coords, double* h_records) {
+static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const double* h_coords, double* h_records,
+                      bool staging_idle = false) {
   if (check(b)) return 1;
   Ws w;
   if (resolve(b, &w)) return 1;
@@ -1808,7 +1809,9 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       if (chunk_copies) {
         // The copies go to their own stream so that, with two calls in flight, the next batch's input
         // arrives while this batch's kernels still occupy the chunk streams.
-        if (g == 0) CK(cudaStreamWaitEvent(c->copy_stream, c->fork, 0));
+        // (`staging_idle`: the caller guarantees that nothing queued earlier still reads the staging buffer, so
+        // the copies need not wait for the work already on `s` -- the pipelined trajectory reader's case.)
+        if (g == 0 && !staging_idle) CK(cudaStreamWaitEvent(c->copy_stream, c->fork, 0));
         CK(cudaMemcpyAsync((double*)b->coords + 3 * apf * first, h_coords + 3 * apf * first,
                            sizeof(double) * 3 * apf * count, cudaMemcpyHostToDevice, c->copy_stream));
         CK(cudaEventRecord(c->h2d[g], c->copy_stream));
@@ -1892,7 +1895,7 @@ int pwb_full_analysis_host_async(pwb_ctx* c, const pwb_batch* b, const double* h
   t.coords = d_coords;
   t.records = d_records;
   t.total_atoms = total_atoms;
-  return batch_impl(c, &t, (cudaStream_t)stream, h_coords, h_records);
+  return batch_impl(c, &t, (cudaStream_t)stream, h_coords, h_records, true);
 }
 
 }  // extern "C"

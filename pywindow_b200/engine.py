@@ -206,6 +206,10 @@ class Engine:
         flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 3) for _, c in mols])
         return self.analyse(flat, off, types, vdw, mass, shared_types=False, max_atoms=max(sizes), **kw)
 
+    def frame_pipeline(self, elements, cap_frames, ray_cap, slots=2, **params):
+        """:class:`FramePipeline` bound to this engine (the trajectory front-ends' entry point)."""
+        return FramePipeline(self, elements, cap_frames, ray_cap, slots=slots, **params)
+
     # ------------------------------------------------------------------ host-buffer path (e2e)
     def analyse_frames_host(self, coords_host, elements, *, ray_cap, out=None, stages=_lib.STAGE_ALL,
                             adjust=1.0, increment=1.0, increment2=0.1, pore_opt=True, state=None, wait=True):
@@ -249,6 +253,85 @@ class Engine:
             _lib.check(entry(self._ctx, ctypes.byref(b), h_ptr, h_rec.data_ptr(),
                               st["d_coords"].data_ptr(), st["d_rec"].data_ptr(), F * N, stream))
             return h_rec
+
+
+def host_ray_capacity(coords, vdw_max, adjust=1.0, margin=64):
+    """Upper bound of the ray count any of the frames ``coords`` [F,N,3] can need, from each frame's bounding box
+    (the host-side twin of ``pwb_ray_capacity``; no device synchronisation).  ``int(log10(4 pi D^2) 250 adjust)``
+    grows by 22 rays per 10 % of D, so ``margin`` rays cover frames ~30 % larger than any seen here."""
+    c = np.asarray(coords)
+    if c.size == 0:
+        return 64 + margin
+    ext = c.max(axis=1) - c.min(axis=1)
+    D = float(np.sqrt((ext * ext).sum(axis=1)).max()) + 2.0 * float(vdw_max)
+    P = int(np.log10(4.0 * np.pi * D * D) * 250.0 * float(adjust)) + 1
+    return max(64, (P + margin + 63) // 64 * 64)
+
+
+class FramePipeline:
+    """Double-buffered host -> GPU -> host path for a trajectory of one molecule (the batched replacement of the
+    per-frame loop of trajectory.py:473-494): ``slots`` pinned input buffers [cap_frames, N, 3] that the trajectory
+    decoders fill directly, persistent device staging / workspace / record buffers per slot, and
+    ``pwb_full_analysis_host_async`` so that batch i runs on the GPU while the host decodes batch i+1.  Nothing is
+    allocated and nothing synchronises per batch except the wait for a slot's own records."""
+
+    def __init__(self, engine, elements, cap_frames, ray_cap, slots=2, stages=_lib.STAGE_ALL, adjust=1.0,
+                 increment=1.0, increment2=0.1, pore_opt=True):
+        self.eng, self.cap, self.N = engine, int(cap_frames), len(elements)
+        self.ray_cap = int(ray_cap)
+        self.params = dict(stages=stages, adjust=adjust, increment=increment, increment2=increment2, pore_opt=pore_opt)
+        eng, dev, F, N = engine, engine.device, self.cap, self.N
+        types, vdw, mass = element_types(elements)
+        with torch.cuda.device(dev):
+            self.types = eng._dev(types, torch.int32)
+            self.vdw, self.mass = eng._dev(vdw, torch.float64), eng._dev(mass, torch.float64)
+            self.off = torch.arange(0, (F + 1) * N, N, dtype=torch.int32, device=dev)
+            self.layout = _lib.WsLayout()
+            eng.lib.pwb_workspace_layout(F, F * N, self.ray_cap, eng.win_cap, ctypes.byref(self.layout))
+            self.slots = []
+            for _ in range(slots):
+                self.slots.append({
+                    "h_in": torch.empty((F, N, 3), dtype=torch.float64).pin_memory(),
+                    "h_rec": torch.empty((F, eng.rec_stride), dtype=torch.float64).pin_memory(),
+                    "d_in": torch.empty((F * N, 3), dtype=torch.float64, device=dev),
+                    "d_rec": torch.empty((F, eng.rec_stride), dtype=torch.float64, device=dev),
+                    "ws": torch.empty(self.layout.total, dtype=torch.uint8, device=dev),
+                    "done": torch.cuda.Event(), "n": 0})
+            for sl in self.slots:
+                sl["in_np"], sl["rec_np"] = sl["h_in"].numpy(), sl["h_rec"].numpy()
+
+    def buffer(self, k):
+        """numpy view [cap_frames, N, 3] of slot k's pinned input buffer (decode straight into it)."""
+        return self.slots[k]["in_np"]
+
+    def submit(self, k, n_frames, src=None):
+        """Queue the analysis of the first ``n_frames`` frames of slot k (H2D, kernels, D2H); returns at once.
+        ``src``: a pinned [>= n_frames, N, 3] float64 torch tensor to read instead of the slot's own buffer
+        (it must stay untouched until :meth:`collect` returns)."""
+        sl, eng = self.slots[k], self.eng
+        h_in = sl["h_in"] if src is None else src
+        n = int(n_frames)
+        if not 0 < n <= self.cap:
+            raise ValueError(f"n_frames {n} outside 1..{self.cap}")
+        with torch.cuda.device(eng.device):
+            p = self.params
+            b, stream, _, _ = eng._make_batch(sl["d_in"], self.off, self.types, self.vdw, self.mass, True, self.N,
+                                              None, p["stages"], p["adjust"], p["increment"], p["increment2"],
+                                              p["pore_opt"], self.ray_cap)
+            b.n_items, b.total_atoms = n, n * self.N
+            b.workspace, b.workspace_bytes = sl["ws"].data_ptr(), self.layout.total
+            _lib.check(eng.lib.pwb_full_analysis_host_async(
+                eng._ctx, ctypes.byref(b), h_in.data_ptr(), sl["h_rec"].data_ptr(), sl["d_in"].data_ptr(),
+                sl["d_rec"].data_ptr(), n * self.N, stream))
+            sl["done"].record(torch.cuda.current_stream(eng.device))
+            sl["n"], sl["src"] = n, src
+
+    def collect(self, k):
+        """Wait for slot k's batch; numpy view [n_frames, rec_stride] of its records (valid until the slot is
+        submitted again)."""
+        sl = self.slots[k]
+        sl["done"].synchronize()
+        return sl["rec_np"][:sl["n"]]
 
 
 _default_engine = None

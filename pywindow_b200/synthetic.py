@@ -37,6 +37,25 @@ def write_history(path, atom_keys, frames, lattice=None, masses=None, title="pyw
                 fh.write("".join(f"{v:20.10E}" for v in X[i]) + "\n")
 
 
+def write_history_native(path, atom_keys, frames, lattice=None, masses=None, title="pywindow_b200 synthetic HISTORY",
+                         threads=0, compact=False):
+    """Same file as :func:`write_history`, byte for byte, written by host threads (``pwb_history_write``):
+    a 100 000-frame trajectory (1.8 GB) takes about a second instead of minutes.  ``compact``: coordinates in
+    DL_POLY's own ``%12.4E`` records (the format of the reference's example HISTORY files) instead of ``%20.10E``."""
+    from . import _lib
+    frames = np.ascontiguousarray(frames, dtype=np.float64)
+    F, n = frames.shape[0], frames.shape[1]
+    keys = np.array([f"{str(k):<8}"[:8] for k in atom_keys], dtype="S8")
+    m = np.ones(n) if masses is None else np.ascontiguousarray(masses, dtype=np.float64)
+    lat = None if lattice is None else np.ascontiguousarray(lattice, dtype=np.float64)
+    size = _lib.load().pwb_history_write(str(path).encode(), title.encode(), keys.ctypes.data, m.ctypes.data,
+                                          frames.ctypes.data, F, n, lat.ctypes.data if lat is not None else None,
+                                          int(lat is not None and lat.ndim == 3), int(bool(compact)), threads)
+    if size < 0:
+        raise OSError(f"could not write {path}")
+    return int(size)
+
+
 def write_xyz_trajectory(path, elements, frames):
     with open(path, "w") as fh:
         for k, X in enumerate(frames):

@@ -29,6 +29,15 @@ from .engine import default_engine, record_to_properties
 from .molecular import MolecularSystem
 
 
+def _host_threads():
+    """Decoder threads for this process: all cores, shared evenly between the ranks of one node."""
+    import os
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+    if local <= 0:
+        _, local = world()
+    return max(1, (os.cpu_count() or 1) // max(1, local))
+
+
 class _ParallelAnalysisError(Exception):
     def __init__(self, message):
         self.message = message
@@ -121,6 +130,99 @@ class LazyFrame(dict):
         return dict(self._load())
 
 
+class AnalysisOutput(dict):
+    """``Trajectory.analysis_output``: ``{frame: {molecule_key: properties}}`` (trajectory.py:483, :516-522).  The
+    batched analysis hands over whole record tables; they are parked as blocks and only turned into per-frame
+    :class:`LazyFrame` entries when somebody first looks at the dictionary, so ``analysis()`` itself does no
+    per-frame Python work (100 000 small containers cost twice the GPU time of analysing the frames)."""
+
+    __slots__ = ("_blocks",)
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._blocks = []
+
+    def _add_block(self, records, keys):
+        self._blocks.append((records, keys))
+
+    def _load(self):
+        if self._blocks:
+            blocks, self._blocks = self._blocks, []
+            # small containers only: the cyclic collector would rescan the growing heap every few hundred
+            # allocations (8x the cost of the loop itself), and nothing allocated here can form a cycle
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                for records, keys in blocks:
+                    # every analysed frame REPLACES its entry (analysis_output[frame] = results): with
+                    # override=True no stale molecule keys of an earlier run survive
+                    fresh = set()
+                    for row, (frame, mol_key) in enumerate(keys):
+                        if frame not in fresh:
+                            fresh.add(frame)
+                            dict.__setitem__(self, frame, LazyFrame())
+                        dict.__getitem__(self, frame)._add(mol_key, records, row)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._load(), k)
+
+    def __setitem__(self, k, v):
+        dict.__setitem__(self._load(), k, v)
+
+    def __delitem__(self, k):
+        dict.__delitem__(self._load(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._load())
+
+    def __len__(self):
+        return dict.__len__(self._load())
+
+    def __contains__(self, k):
+        return dict.__contains__(self._load(), k)
+
+    def __eq__(self, other):
+        return dict.__eq__(self._load(), other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __repr__(self):
+        return dict.__repr__(self._load())
+
+    def __bool__(self):
+        return bool(self._blocks) or dict.__len__(self) > 0
+
+    def keys(self):
+        return dict.keys(self._load())
+
+    def values(self):
+        return dict.values(self._load())
+
+    def items(self):
+        return dict.items(self._load())
+
+    def get(self, k, default=None):
+        return dict.get(self._load(), k, default)
+
+    def pop(self, *a):
+        return dict.pop(self._load(), *a)
+
+    def copy(self):
+        return dict(self._load())
+
+    def record_table(self):
+        """(records [M, stride] float64, keys [(frame, molecule_key)]) of everything analysed by the batched path
+        and not yet looked at through the dictionary interface -- bulk post-processing without any dicts."""
+        if not self._blocks:
+            return np.zeros((0, 0)), []
+        return (np.concatenate([b[0] for b in self._blocks]), [k for b in self._blocks for k in b[1]])
+
+
 class Trajectory:
     """Shared machinery: frame selection, batched GPU analysis, result storage."""
 
@@ -130,7 +232,7 @@ class Trajectory:
         self.filepath = pathlib.Path(filepath)
         self.system_id = self.filepath.name.split(".")[0]
         self.frames = {}
-        self.analysis_output = {}
+        self.analysis_output = AnalysisOutput()
         self.trajectory_map = {}
         self.no_of_frames = 0
 
@@ -205,22 +307,9 @@ class Trajectory:
         if size > 1:
             records, keys = gather_records(records, keys)
         out = self.analysis_output
-        # 1e5 small containers: the cyclic collector would rescan the growing heap every few hundred allocations
-        # (8x the cost of the loop itself), and nothing allocated here can form a cycle
-        gc_was_on = gc.isenabled()
-        gc.disable()
-        try:
-            # every analysed frame REPLACES its entry (analysis_output[frame] = results, trajectory.py:483,
-            # :522): with override=True no stale molecule keys of an earlier run survive
-            fresh = set()
-            for row, (frame, mol_key) in enumerate(keys):
-                if frame not in fresh:
-                    fresh.add(frame)
-                    out[frame] = LazyFrame()
-                out[frame]._add(mol_key, records, row)
-        finally:
-            if gc_was_on:
-                gc.enable()
+        if not isinstance(out, AnalysisOutput):          # a plain dict assigned by the user: keep its contents
+            out = self.analysis_output = AnalysisOutput(out)
+        out._add_block(records, keys)
 
     def _elements_of(self, frame, swap_atoms, forcefield):
         ms = self._get_frame(self.trajectory_map[frame], frame, swap_atoms=swap_atoms, forcefield=forcefield)
@@ -247,24 +336,59 @@ class Trajectory:
     def _decode_xyz_only(self, raw):
         return np.asarray(self._decode_frame(raw)["coordinates"], dtype=np.float64)
 
+    def _decode_into(self, frames, out, threads=0):
+        """Decode ``frames`` into ``out[:len(frames)]`` ([cap, N, 3] float64, e.g. a pinned staging buffer).  The
+        format classes override this with their native multi-threaded decoders writing in place."""
+        out[:len(frames)] = self._decode_coordinates(frames)
+
     def _analyse_single(self, frames, swap_atoms, forcefield, gpu_kwargs):
+        """Frames -> records through :class:`engine.FramePipeline`: the native decoder fills the pinned buffer of one
+        slot on all host threads while the previous batch is on the GPU; one workspace / ray capacity for the whole
+        trajectory; the only synchronisation per batch is the wait for its own records."""
+        from .engine import host_ray_capacity
+        from .tables import atomic_vdw_radius
         eng = default_engine()
         if not frames:
             return np.zeros((0, eng.rec_stride)), []
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
-        # the next batch is decoded on a helper thread (the C++ decoders and the GPU call both release the GIL)
-        # while the current one is on the GPU
-        from concurrent.futures import ThreadPoolExecutor
-        chunks = [frames[s:s + self.batch_frames] for s in range(0, len(frames), self.batch_frames)]
-        recs = []
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(self._decode_coordinates, chunks[0])
-            for k in range(len(chunks)):
-                coords = pending.result()
-                if k + 1 < len(chunks):
-                    pending = pool.submit(self._decode_coordinates, chunks[k + 1])
-                recs.append(eng.analyse_frames(coords, elements, **gpu_kwargs).host_records())
-        return np.concatenate(recs), [(f, "0") for f in frames]
+        N = len(elements)
+        B = max(1, min(self.batch_frames, len(frames)))
+        chunks = [frames[s:s + B] for s in range(0, len(frames), B)]
+        threads = _host_threads()
+        first = np.empty((len(chunks[0]), N, 3), dtype=np.float64)
+        self._decode_into(chunks[0], first, threads)
+        adjust = float(gpu_kwargs.get("adjust", 1.0))
+        vmax = max(atomic_vdw_radius[str(e).upper()] for e in set(elements))
+        ray_cap = host_ray_capacity(first, vmax, adjust)
+        pipe = eng.frame_pipeline(elements, B, ray_cap, slots=min(2, len(chunks)), **gpu_kwargs)
+        records = np.empty((len(frames), eng.rec_stride), dtype=np.float64)
+        nslots = len(pipe.slots)
+        pipe.buffer(0)[:len(chunks[0])] = first
+        del first
+        done = 0
+        for k, chunk in enumerate(chunks):
+            if k:
+                self._decode_into(chunk, pipe.buffer(k % nslots), threads)
+            pipe.submit(k % nslots, len(chunk))
+            if k + 1 >= nslots:                      # the slot the next batch will be decoded into must be free
+                j = k + 1 - nslots
+                records[done:done + len(chunks[j])] = pipe.collect(j % nslots)
+                done += len(chunks[j])
+        for j in range(max(0, len(chunks) - nslots + 1), len(chunks)):
+            records[done:done + len(chunks[j])] = pipe.collect(j % nslots)
+            done += len(chunks[j])
+        records = self._redo_overflowed(records, frames, elements, gpu_kwargs)
+        return records, [(f, "0") for f in frames]
+
+    def _redo_overflowed(self, records, frames, elements, gpu_kwargs):
+        """Frames whose ray count exceeded the trajectory-wide capacity (a molecule that grew far beyond the first
+        batch's bounding boxes) are re-analysed on their own, with a capacity sized for them."""
+        over = np.nonzero(records[:, _lib.REC_STATUS].astype(np.int64) & _lib.ST_RAY_CAP)[0]
+        if over.size:
+            redo = [frames[i] for i in over]
+            coords = self._decode_coordinates(redo)
+            records[over] = default_engine().analyse_frames(coords, elements, **gpu_kwargs).host_records()
+        return records
 
     def _analyse_modular(self, frames, rebuild, swap_atoms, forcefield, gpu_kwargs):
         """modular=True: every frame is decomposed into discrete molecules on the GPU (rebuilt across
@@ -368,20 +492,26 @@ class DLPOLY(Trajectory):
         self.no_of_frames = len(starts)
         self.check_log = ""
 
-    def _native_decode(self, frames, want_lattice):
-        """[F,N,3] (and [F,3,3] lattices) through the multi-threaded C++ decoder (pwb_history_decode)."""
+    def _native_decode(self, frames, want_lattice, out=None, threads=0):
+        """[F,N,3] (and [F,3,3] lattices) through the multi-threaded C++ decoder (pwb_history_decode); ``out``:
+        write the coordinates into ``out[:F]`` (a pinned staging buffer) instead of a new array."""
         lib = _lib.load()
         n, N = len(frames), self.no_of_atoms
         starts = np.array([self.trajectory_map[f][0] for f in frames], dtype=np.int64)
         ends = np.array([self.trajectory_map[f][1] for f in frames], dtype=np.int64)
-        xyz = np.empty((n, N, 3), dtype=np.float64)
+        if out is None:
+            xyz = np.empty((n, N, 3), dtype=np.float64)
+        else:
+            if out.shape[1:] != (N, 3) or out.shape[0] < n or out.dtype != np.float64 or not out.flags.c_contiguous:
+                raise _TrajectoryError(f"decode buffer {out.shape} does not fit {n} frames of {N} atoms")
+            xyz = out
         periodic = self._frame_imcon in (1, 2, 3)
         lat = np.empty((n, 3, 3), dtype=np.float64) if (want_lattice and periodic) else None
         with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
             buf = np.frombuffer(mm, dtype=np.uint8)
             bad = int(lib.pwb_history_decode(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, N,
                                              self._frame_keytrj, self._frame_imcon, xyz.ctypes.data,
-                                             lat.ctypes.data if lat is not None else None, 0))
+                                             lat.ctypes.data if lat is not None else None, threads))
             del buf
         if bad:
             raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {N} atoms, keytrj "
@@ -390,6 +520,9 @@ class DLPOLY(Trajectory):
 
     def _decode_coordinates(self, frames):
         return self._native_decode(frames, False)[0]
+
+    def _decode_into(self, frames, out, threads=0):
+        self._native_decode(frames, False, out=out, threads=threads)
 
     def _decode_cells(self, frames):
         return self._native_decode(frames, True)
@@ -423,17 +556,22 @@ class DLPOLY(Trajectory):
         return _float_block(lines[first + 1::stride]).reshape(-1, 3)
 
 
-def _native_xyz_like(traj, entry, frames, natoms):
-    """Shared driver of pwb_xyz_decode / pwb_pdb_decode: frames -> [F, natoms, 3] float64."""
+def _native_xyz_like(traj, entry, frames, natoms, out=None, threads=0):
+    """Shared driver of pwb_xyz_decode / pwb_pdb_decode: frames -> [F, natoms, 3] float64 (into ``out[:F]`` if given)."""
     lib = _lib.load()
     n = len(frames)
     starts = np.array([traj.trajectory_map[f][0] for f in frames], dtype=np.int64)
     ends = np.array([traj.trajectory_map[f][1] for f in frames], dtype=np.int64)
-    xyz = np.empty((n, natoms, 3), dtype=np.float64)
+    if out is None:
+        xyz = np.empty((n, natoms, 3), dtype=np.float64)
+    else:
+        if out.shape[1:] != (natoms, 3) or out.shape[0] < n or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise _TrajectoryError(f"decode buffer {out.shape} does not fit {n} frames of {natoms} atoms")
+        xyz = out
     with traj.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
         buf = np.frombuffer(mm, dtype=np.uint8)
         bad = int(getattr(lib, entry)(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, natoms,
-                                      xyz.ctypes.data, 0))
+                                      xyz.ctypes.data, threads))
         del buf
     if bad:
         raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {natoms} atoms)")
@@ -476,6 +614,12 @@ class XYZ(Trajectory):
             return super()._decode_coordinates(frames)
         return _native_xyz_like(self, "pwb_xyz_decode", frames, counts.pop())
 
+    def _decode_into(self, frames, out, threads=0):
+        counts = {int(self._natoms[f]) for f in frames}
+        if len(counts) != 1:
+            return super()._decode_into(frames, out, threads)
+        _native_xyz_like(self, "pwb_xyz_decode", frames, counts.pop(), out=out, threads=threads)
+
     def _decode_frame(self, raw):
         lines = bytes(raw).decode("utf-8").split("\n")
         natoms = int(lines[0].split()[0])
@@ -514,6 +658,9 @@ class PDB(Trajectory):
             start, end = self.trajectory_map[frames[0]]
             natoms = len(self._decode_frame(mm[start:end])["coordinates"])
         return _native_xyz_like(self, "pwb_pdb_decode", frames, natoms)
+
+    def _decode_into(self, frames, out, threads=0):
+        _native_xyz_like(self, "pwb_pdb_decode", frames, out.shape[1], out=out, threads=threads)
 
     def _decode_frame(self, raw):
         lines = bytes(raw).decode("utf-8").split("\n")

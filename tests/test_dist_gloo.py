@@ -36,6 +36,30 @@ class _StubEngine:
         rec[:, L.REC_WIN0] = coords[:, 0, 0]
         return _StubResult(rec)
 
+    def frame_pipeline(self, elements, cap_frames, ray_cap, slots=2, **params):
+        return _StubPipeline(self, elements, cap_frames, slots)
+
+
+class _StubPipeline:
+    """Host-only stand-in for engine.FramePipeline: same buffer / submit / collect protocol."""
+
+    def __init__(self, eng, elements, cap, slots):
+        self.eng, self.elements = eng, elements
+        self.slots = [{"in": np.zeros((cap, len(elements), 3)), "rec": None} for _ in range(slots)]
+
+    def buffer(self, k):
+        return self.slots[k]["in"]
+
+    def submit(self, k, n, src=None):
+        sl = self.slots[k]
+        assert sl["rec"] is None, "slot submitted again before it was collected"
+        sl["rec"] = self.eng.analyse_frames(sl["in"][:n].copy(), self.elements).host_records()
+
+    def collect(self, k):
+        rec, self.slots[k]["rec"] = self.slots[k]["rec"], None
+        assert rec is not None, "collect without submit"
+        return rec
+
 
 def _worker(rank, world, port, path, out):
     import sys
@@ -46,6 +70,7 @@ def _worker(rank, world, port, path, out):
     from pywindow_b200 import trajectory as T
     T.default_engine = lambda: _StubEngine()
     t = T.DLPOLY(path)
+    t.batch_frames = 2                                  # 4 (3) frames per rank -> the two slots are reused
     t.analysis(frames="all", forcefield="DLF")
     keys = sorted(t.analysis_output)
     vals = np.array([t.analysis_output[k]["0"]["windows"]["diameters"][0] for k in keys])

@@ -278,3 +278,29 @@ def test_lazyframe_len_and_override_semantics():
     assert list(t.analysis_output[0].keys()) == ["0"]          # no stale modular keys
     t.analysis(frames=[0, 1], modular=False)                   # override=False keeps frame 0, adds frame 1
     assert list(t.analysis_output[1].keys()) == ["0"]
+
+
+def test_analysis_output_is_a_lazy_dict():
+    """AnalysisOutput parks whole record tables and behaves like the reference's plain
+    {frame: {molecule: properties}} dict on first access (len / in / iteration / dict() / json)."""
+    import json
+    from pywindow_b200 import _lib, utilities as U
+    from pywindow_b200.trajectory import AnalysisOutput
+    rec = np.zeros((4, _lib.REC_WIN0 + 4 * 16))
+    rec[:, _lib.REC_STATUS] = _lib.ST_NO_CLEAR_RAY
+    rec[:, _lib.REC_NATOMS] = [3, 4, 5, 6]
+    out = AnalysisOutput()
+    assert not out and len(out) == 0
+    out._add_block(rec[:2], [(7, "0"), (9, "0")])
+    assert bool(out)
+    tab, keys = out.record_table()
+    assert tab.shape == (2, rec.shape[1]) and keys == [(7, "0"), (9, "0")]
+    assert 7 in out and 8 not in out and len(out) == 2 and sorted(out) == [7, 9]
+    out._add_block(rec[2:], [(9, 0), (9, 1)])                    # frame 9 re-analysed (modular): replaced
+    assert sorted(out[9].keys()) == [0, 1] and out[9][1]["no_of_atoms"] == 6
+    plain = dict(out)
+    assert sorted(plain) == [7, 9] and plain[7]["0"]["no_of_atoms"] == 3
+    out[11] = {"0": {"no_of_atoms": 1}}
+    assert out.get(11)["0"]["no_of_atoms"] == 1 and out.get(12) is None
+    text = json.dumps({str(f): {str(k): v for k, v in dict(m.items()).items()} for f, m in out.items()}, default=U.to_list)
+    assert json.loads(text)["7"]["0"]["windows"]["diameters"] is None
