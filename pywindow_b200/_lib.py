@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpwb.so")
+# PWB_LIBRARY: an alternative build of the same sources (kernel-variant experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("PWB_LIBRARY") or os.path.join(_HERE, "csrc", "libpwb.so")
 
 MAX_TYPES = 16
 REC_STATUS, REC_NATOMS, REC_COM, REC_MAXD, REC_MAXD_A1, REC_MAXD_A2, REC_AVGD = 0, 1, 2, 5, 6, 7, 8

@@ -26,10 +26,31 @@
 
 namespace pwb {
 
+// On the device the optimiser kernels are bound by INSTRUCTION SUPPLY and by the latency of their dependent FP64 /
+// shared-memory chains (ncu: 65-78 % instruction-cache hit rate, 3-5 of 7 warps per scheduler waiting for
+// instructions, one instruction per ~10 cycles per warp).  Two measures keep the code small without lengthening
+// the executed path (profiles/r2_opt_pore_variants.md): the cold per-variable loops of the Cauchy / subspace /
+// projection steps stay ROLLED (arrays live in shared memory anyway), while divisions and square roots stay INLINE
+// -- one out-of-line copy of each (LB_NOINLINE_MATH) shrank one search from 80 KB to 58 KB of code and raised the
+// I-cache hit rate, but the extra calls and moves cost 24 % more executed instructions and the kernel got slower.
+// Same IEEE operations in the same order in every variant: results are unchanged bit for bit.
+#if defined(__CUDA_ARCH__) && defined(LB_NOINLINE_MATH)
+__device__ __noinline__ double lb_div(double a, double b) { return a / b; }
+__device__ __noinline__ double lb_sqrt(double a) { return sqrt(a); }
+#else
+PWB_HD double lb_div(double a, double b) { return a / b; }
+PWB_HD double lb_sqrt(double a) { return sqrt(a); }
+#endif
+#if defined(__CUDA_ARCH__) && !defined(LB_UNROLLED)
+#define LB_ROLLED _Pragma("unroll 1")
+#else
+#define LB_ROLLED
+#endif
+
 constexpr int LB_M = 10;
 // doubles of caller storage lbfgsb_minimize<N> needs: (s, y) ring, z / d / t / r, line-search record
 // and the small work arrays of the Cauchy / subspace steps (x, g, iwhere: 3N; B: N*N; scratch: 4N + 3N*N)
-#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20 + 7 * (N) + 4 * (N) * (N))
+#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20 + 10 * (N) + 4 * (N) * (N) + 8)   /* = LbSolver<N>::SIZE */
 constexpr double LB_EPSMCH = 2.220446049250313e-16;
 constexpr double LB_FD_STEP = 1e-8;
 
@@ -71,20 +92,21 @@ PWB_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& 
   const int cs = (fp > fx) ? 1 : (sgnd < 0.0) ? 2 : (fabs(dp) < fabs(dx)) ? 3 : 4;
   const bool far_end = cs == 4;                       // cubic through (sty, stp) instead of (stx, stp)
   const double fa = far_end ? fy : fx, sta = far_end ? sty : stx, da = far_end ? dy : dx;
-  const double theta = 3.0 * (fa - fp) / (stp - sta) + da + dp;
+  const double theta = lb_div(3.0 * (fa - fp), stp - sta) + da + dp;
   const double s = fmax(fabs(theta), fmax(fabs(da), fabs(dp)));
-  double rad = (theta / s) * (theta / s) - (da / s) * (dp / s);
+  const double ths = lb_div(theta, s);
+  double rad = ths * ths - lb_div(da, s) * lb_div(dp, s);
   if (cs == 3) rad = fmax(0.0, rad);
-  double gamma = s * sqrt(rad);
+  double gamma = s * lb_sqrt(rad);
   if (cs == 1 ? (stp < stx) : (stp > sta)) gamma = -gamma;
   const double e = cs == 1 ? dx : dp;
   const double p = (gamma - e) + theta;
   const double q = cs == 3 ? (gamma + (dx - dp)) + gamma : ((gamma - e) + gamma) + (cs == 1 ? dp : da);
-  const double r = p / q;
+  const double r = lb_div(p, q);
   double stpf;
   if (cs == 1) {
     const double stpc = stx + r * (stp - stx);
-    const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    const double stpq = stx + (lb_div(dx, lb_div(fx - fp, stp - stx) + dx) / 2.0) * (stp - stx);
     stpf = (fabs(stpc - stx) <= fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
     brackt = true;
   } else if (cs == 4) {
@@ -92,7 +114,7 @@ PWB_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& 
     else if (stp > stx) stpf = stpmax;
     else stpf = stpmin;
   } else {
-    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    const double stpq = stp + lb_div(dp, dp - dx) * (stx - stp);
     double stpc = stp + r * (stx - stp);
     if (cs == 2) {
       stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
@@ -129,7 +151,7 @@ struct LbLineSearch {
   PWB_HD int start(double& stp, double f, double g) {
     if (stp < stpmin || stp > stpmax || g >= 0 || stpmax < stpmin) return ERR;
     brackt = false; stage = 1; finit = f; ginit = g; gtest = ftol * ginit;
-    width = stpmax - stpmin; width1 = width / 0.5;
+    width = stpmax - stpmin; width1 = width * 2.0;
     stx = 0; fx = finit; gx = ginit; sty = 0; fy = finit; gy = ginit;
     stmin = 0; stmax = stp + 4.0 * stp;
     return FG;
@@ -192,7 +214,7 @@ PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double* Bm) {
       Bs[i] = a;
     }
     for (int i = 0; i < N; i++) { sBs += H.S[p][i] * Bs[i]; ys += H.Y[p][i] * H.S[p][i]; }
-    const double iys = 1.0 / ys, isBs = 1.0 / sBs;
+    const double iys = lb_div(1.0, ys), isBs = lb_div(1.0, sBs);
     for (int i = 0; i < N; i++)
       for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] * iys - Bs[i] * Bs[j] * isBs;
   }
@@ -203,37 +225,44 @@ PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double* Bm) {
 // Solve A d = b for the leading nf x nf SPD system by Cholesky; false if not positive definite.
 template <int N>
 PWB_HD bool lb_spd_solve(int nf, const double* A, double* b, double* Lm) {   // A, Lm: [N][N] row-major
+  LB_ROLLED
   for (int i = 0; i < nf; i++) {
+    LB_ROLLED
     for (int j = 0; j <= i; j++) {
       double s = A[i * N + j];
       for (int k = 0; k < j; k++) s -= Lm[i * N + k] * Lm[j * N + k];
       if (i == j) {
         if (!(s > 0)) return false;
-        Lm[i * N + i] = sqrt(s);
-      } else Lm[i * N + j] = s / Lm[j * N + j];
+        Lm[i * N + i] = lb_sqrt(s);
+      } else Lm[i * N + j] = lb_div(s, Lm[j * N + j]);
     }
   }
+  LB_ROLLED
   for (int i = 0; i < nf; i++) {
     double s = b[i];
     for (int k = 0; k < i; k++) s -= Lm[i * N + k] * b[k];
-    b[i] = s / Lm[i * N + i];
+    b[i] = lb_div(s, Lm[i * N + i]);
   }
+  LB_ROLLED
   for (int i = nf - 1; i >= 0; i--) {
     double s = b[i];
     for (int k = i + 1; k < nf; k++) s -= Lm[k * N + i] * b[k];
-    b[i] = s / Lm[i * N + i];
+    b[i] = lb_div(s, Lm[i * N + i]);
   }
   return true;
 }
 
-template <int N>
+// (NBD >= 0: every variable has that bound type and `nbd` is not read; else per-variable types in memory)
+template <int N, int NBD>
 PWB_HD double lb_projgr(const double* x, const double* g, const double* lo, const double* hi, const int* nbd) {
   double sb = 0;
+  LB_ROLLED
   for (int i = 0; i < N; i++) {
     double gi = g[i];
-    if (nbd[i] != 0) {
-      if (gi < 0) { if (nbd[i] >= 2) gi = fmax(x[i] - hi[i], gi); }
-      else { if (nbd[i] <= 2) gi = fmin(x[i] - lo[i], gi); }
+    const int nbi = NBD >= 0 ? NBD : nbd[i];
+    if (nbi != 0) {
+      if (gi < 0) { if (nbi >= 2) gi = fmax(x[i] - hi[i], gi); }
+      else { if (nbi <= 2) gi = fmin(x[i] - lo[i], gi); }
     }
     sb = fmax(sb, fabs(gi));
   }
@@ -241,7 +270,7 @@ PWB_HD double lb_projgr(const double* x, const double* g, const double* lo, cons
 }
 
 // Generalized Cauchy point along the projected steepest-descent path (cauchy in L-BFGS-B 3.0).
-template <int N>
+template <int N, int NBD>
 PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const int* nbd, const double* g,
                       int* iwhere, const double* B, double theta, double sbgnrm, double* z, double* scratch) {
   for (int i = 0; i < N; i++) z[i] = x[i];
@@ -252,13 +281,15 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
   double* d = scratch; double* tb = d + N; double* zz = tb + N; double* Bz = zz + N;
   int* isb = reinterpret_cast<int*>(Bz + N); int* fixed = isb + N;
   double f1 = 0;
+  LB_ROLLED
   for (int i = 0; i < N; i++) {
     double neggi = -g[i], tl = 0, tu = 0;
+    const int nbi = NBD >= 0 ? NBD : nbd[i];
     isb[i] = false; fixed[i] = false; tb[i] = 0;
     if (iwhere[i] != 3 && iwhere[i] != -1) {
-      if (nbd[i] <= 2) tl = x[i] - lo[i];
-      if (nbd[i] >= 2) tu = hi[i] - x[i];
-      bool xlower = nbd[i] <= 2 && tl <= 0, xupper = nbd[i] >= 2 && tu <= 0;
+      if (nbi <= 2) tl = x[i] - lo[i];
+      if (nbi >= 2) tu = hi[i] - x[i];
+      bool xlower = nbi <= 2 && tl <= 0, xupper = nbi >= 2 && tu <= 0;
       iwhere[i] = 0;
       if (xlower) { if (neggi <= 0) iwhere[i] = 1; }
       else if (xupper) { if (neggi >= 0) iwhere[i] = 2; }
@@ -268,23 +299,25 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
     else {
       d[i] = neggi;
       f1 -= neggi * neggi;
-      if (nbd[i] <= 2 && nbd[i] != 0 && neggi < 0) { isb[i] = true; tb[i] = tl / (-neggi); nbreak++; }
-      else if (nbd[i] >= 2 && neggi > 0) { isb[i] = true; tb[i] = tu / neggi; nbreak++; }
+      if (nbi <= 2 && nbi != 0 && neggi < 0) { isb[i] = true; tb[i] = lb_div(tl, -neggi); nbreak++; }
+      else if (nbi >= 2 && neggi > 0) { isb[i] = true; tb[i] = lb_div(tu, neggi); nbreak++; }
       else { nunb++; if (fabs(neggi) > 0) bnded = false; }
     }
   }
   if (nbreak == 0 && nunb == 0) return;
   double f2_org = -theta * f1;
   double f2 = 0;
+  LB_ROLLED
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) f2 += d[i] * B[i * N + j] * d[j];
-  double dtm = -f1 / f2, tsum = 0;
+  double dtm = lb_div(-f1, f2), tsum = 0;
   if (nbreak > 0) {
     int nleft = nbreak;
     double tj = 0;
     while (true) {
       double tj0 = tj;
       int ibp = -1;
+      LB_ROLLED
       for (int i = 0; i < N; i++)
         if (isb[i] && (ibp < 0 || tb[i] < tb[ibp])) ibp = i;
       tj = tb[ibp];
@@ -299,8 +332,10 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
       if (dibp > 0) { z[ibp] = hi[ibp]; iwhere[ibp] = 2; }
       else { z[ibp] = lo[ibp]; iwhere[ibp] = 1; }
       if (nleft == 0 && nbreak == N) return;   // every variable sits on a bound
+      LB_ROLLED
       for (int i = 0; i < N; i++) zz[i] = fixed[i] ? z[i] - x[i] : tsum * d[i];
       f1 = 0; f2 = 0;
+      LB_ROLLED
       for (int i = 0; i < N; i++) {
         double a = 0, b = 0;
         for (int j = 0; j < N; j++) { a += B[i * N + j] * zz[j]; b += B[i * N + j] * d[j]; }
@@ -309,21 +344,22 @@ PWB_HD void lb_cauchy(const double* x, const double* lo, const double* hi, const
         f2 += d[i] * b;
       }
       f2 = fmax(LB_EPSMCH * f2_org, f2);
-      if (nleft > 0) { dtm = -f1 / f2; continue; }
+      if (nleft > 0) { dtm = lb_div(-f1, f2); continue; }
       if (bnded) { f1 = 0; f2 = 0; dtm = 0; }
-      else dtm = -f1 / f2;
+      else dtm = lb_div(-f1, f2);
       break;
     }
   }
   if (dtm <= 0) dtm = 0;
   tsum += dtm;
+  LB_ROLLED
   for (int i = 0; i < N; i++)
     if (!fixed[i]) z[i] = x[i] + tsum * d[i];
 }
 
 // Subspace minimisation over the variables free at the Cauchy point (cmprlb + subsm, 3.0 projection).
 // Returns false if the reduced Hessian is not positive definite (caller refreshes the memory).
-template <int N>
+template <int N, int NBD>
 PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const double* hi, const int* nbd,
                      const int* iwhere, const double* B, double* z, double* scratch) {
   double* zx = scratch; double* rr = zx + N; double* xp = rr + N; double* A = xp + N; double* Lm = A + N * N;
@@ -332,6 +368,7 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
   for (int i = 0; i < N; i++) if (iwhere[i] <= 0) ind[nf++] = i;
   if (nf == 0) return true;
   for (int i = 0; i < N; i++) zx[i] = z[i] - x[i];
+  LB_ROLLED
   for (int a = 0; a < nf; a++) {
     int i = ind[a];
     double s = g[i];
@@ -342,12 +379,14 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
   if (!lb_spd_solve<N>(nf, A, rr, Lm)) return false;   // rr now holds d on the free set
   for (int i = 0; i < N; i++) xp[i] = z[i];
   bool iword = false;
+  LB_ROLLED
   for (int a = 0; a < nf; a++) {
     int k = ind[a];
     double dk = rr[a], xk = z[k];
-    if (nbd[k] != 0) {
-      if (nbd[k] == 1) { z[k] = fmax(lo[k], xk + dk); if (z[k] == lo[k]) iword = true; }
-      else if (nbd[k] == 2) {
+    const int nbk = NBD >= 0 ? NBD : nbd[k];
+    if (nbk != 0) {
+      if (nbk == 1) { z[k] = fmax(lo[k], xk + dk); if (z[k] == lo[k]) iword = true; }
+      else if (nbk == 2) {
         xk = fmax(lo[k], xk + dk); z[k] = fmin(hi[k], xk);
         if (z[k] == lo[k] || z[k] == hi[k]) iword = true;
       } else { z[k] = fmin(hi[k], xk + dk); if (z[k] == hi[k]) iword = true; }
@@ -360,16 +399,18 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
     for (int i = 0; i < N; i++) z[i] = xp[i];
     double alpha = 1, temp1 = 1;
     int ibd = -1;
+    LB_ROLLED
     for (int a = 0; a < nf; a++) {
       int k = ind[a];
       double dk = rr[a];
-      if (nbd[k] != 0) {
-        if (dk < 0 && nbd[k] <= 2) {
+      const int nbk = NBD >= 0 ? NBD : nbd[k];
+      if (nbk != 0) {
+        if (dk < 0 && nbk <= 2) {
           double t2 = lo[k] - z[k];
-          if (t2 >= 0) temp1 = 0; else if (dk * alpha < t2) temp1 = t2 / dk;
-        } else if (dk > 0 && nbd[k] >= 2) {
+          if (t2 >= 0) temp1 = 0; else if (dk * alpha < t2) temp1 = lb_div(t2, dk);
+        } else if (dk > 0 && nbk >= 2) {
           double t2 = hi[k] - z[k];
-          if (t2 <= 0) temp1 = 0; else if (dk * alpha > t2) temp1 = t2 / dk;
+          if (t2 <= 0) temp1 = 0; else if (dk * alpha > t2) temp1 = lb_div(t2, dk);
         }
         if (temp1 < alpha) { alpha = temp1; ibd = a; }
       }
@@ -385,143 +426,220 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
   return true;
 }
 
+// The solver as a RESUMABLE state machine: `init` projects the start point into the box, the caller evaluates
+// (f, g) at x -- the ONE objective call site of a kernel -- and calls `advance`, which runs the bookkeeping up to
+// the next point that needs an evaluation (a line-search trial point) or to termination.  Several solvers can
+// therefore be interleaved by one warp (one per lane group), each pulling new problems when it finishes, and the
+// objective code exists once.  Scalars live in the struct (registers); everything indexed by a run-time variable or
+// ring slot lives in caller storage (LB_STORAGE(N) doubles: shared memory on the device, one copy per problem).
+// NBD >= 0: every variable has that bound type, known at compile time (the bound-type tests fold away).
+template <int N, int NBD = -1>
+struct LbSolver {
+  double* st;     // caller storage, LB_STORAGE(N) doubles: the WHOLE state lives there (on the device: shared memory,
+                  // so a kernel that interleaves several searches keeps one pointer per search in registers)
+  // layout: (s, y) ring | z d t r | line-search record (20) | x g | B | iwhere (N ints in N doubles) | scratch |
+  //         lo hi | nbd (N ints in N doubles) | scalars
+  static constexpr int O_Z = 2 * LB_M * N, O_LS = O_Z + 4 * N, O_X = O_LS + 20, O_G = O_X + N, O_B = O_G + N,
+                       O_IW = O_B + N * N, O_SCR = O_IW + N, O_LO = O_SCR + 4 * N + 3 * N * N, O_HI = O_LO + N,
+                       O_NBD = O_HI + N, O_SC = O_NBD + N, SIZE = O_SC + 8;
+  // scalars: doubles theta, sbgnrm, fold, gdold, stp, f; ints (in two doubles) iter, ifun, col+head, flags
+  enum { F_CNSTND = 1, F_BOXED = 2, F_STARTED = 4, F_RUNNING = 8 };
+
+  PWB_HD double* xs() const { return st + O_X; }        // current point: evaluate (f, g) here ...
+  PWB_HD double* gs() const { return st + O_G; }        // ... store the gradient here and pass f to advance()
+  PWB_HD const double* lo() const { return st + O_LO; }
+  PWB_HD const double* hi() const { return st + O_HI; }
+  PWB_HD int nbd(int i) const { return NBD >= 0 ? NBD : reinterpret_cast<const int*>(st + O_NBD)[i]; }
+  PWB_HD double& theta() const { return st[O_SC]; }
+  PWB_HD double& sbgnrm() const { return st[O_SC + 1]; }
+  PWB_HD double& fold() const { return st[O_SC + 2]; }
+  PWB_HD double& gdold() const { return st[O_SC + 3]; }
+  PWB_HD double& stp() const { return st[O_SC + 4]; }
+  PWB_HD double& fval() const { return st[O_SC + 5]; }  // objective at x (final value after termination)
+  PWB_HD int* ints() const { return reinterpret_cast<int*>(st + O_SC + 6); }
+  PWB_HD int& iter() const { return ints()[0]; }
+  PWB_HD int& ifun() const { return ints()[1]; }
+  PWB_HD int& colhead() const { return ints()[2]; }      // col | head << 8
+  PWB_HD int& flags() const { return ints()[3]; }
+
+  // x0 is projected into the box; the caller then evaluates (f, g) at xs()
+  PWB_HD void init(double* storage, const double* x0, const double* lo_, const double* hi_, const int* nbd_in) {
+    st = storage;
+    double* const x = st + O_X;
+    double* const lo = st + O_LO; double* const hi = st + O_HI;
+    int* const nb = reinterpret_cast<int*>(st + O_NBD);
+    int* const iwhere = reinterpret_cast<int*>(st + O_IW);
+    for (int i = 0; i < N; i++) { x[i] = x0[i]; lo[i] = lo_[i]; hi[i] = hi_[i]; nb[i] = NBD >= 0 ? NBD : nbd_in[i]; }
+    bool cnstnd = false, boxed = true;
+    for (int i = 0; i < N; i++) {
+      const int nbi = nbd(i);
+      if (nbi > 0) {
+        if (nbi <= 2 && x[i] <= lo[i]) { if (x[i] < lo[i]) x[i] = lo[i]; }
+        else if (nbi >= 2 && x[i] >= hi[i]) { if (x[i] > hi[i]) x[i] = hi[i]; }
+      }
+    }
+    for (int i = 0; i < N; i++) {
+      const int nbi = nbd(i);
+      if (nbi != 2) boxed = false;
+      if (nbi == 0) iwhere[i] = -1;
+      else { cnstnd = true; iwhere[i] = (nbi == 2 && hi[i] - lo[i] <= 0) ? 3 : 0; }
+    }
+    theta() = 1.0; sbgnrm() = 0; fold() = 0; gdold() = 0; stp() = 0; fval() = 0;
+    iter() = 0; ifun() = 0; colhead() = 0;
+    flags() = (cnstnd ? F_CNSTND : 0) | (boxed ? F_BOXED : 0);
+  }
+
+  // `f` and gs() hold the objective at xs().  Returns -1 if xs() now holds the next point to evaluate, otherwise
+  // the termination status (LbStatus; xs(), fval(), iter() final).
+  PWB_HD int advance(double f, double ftol, double pgtol, int maxls, int maxiter) {
+    double* const x = st + O_X; double* const g = st + O_G; double* const B = st + O_B;
+    int* const iwhere = reinterpret_cast<int*>(st + O_IW);
+    double* const scratch = st + O_SCR;
+    double* const z = st + O_Z; double* const d = z + N; double* const t = d + N; double* const r = t + N;
+    const double* const lo = st + O_LO; const double* const hi = st + O_HI;
+    LbLineSearch* const ls = reinterpret_cast<LbLineSearch*>(st + O_LS);
+    const int* const nb = reinterpret_cast<const int*>(st + O_NBD);
+    LbHistory<N> H;
+    H.S = reinterpret_cast<double (*)[N]>(st);
+    H.Y = reinterpret_cast<double (*)[N]>(st + LB_M * N);
+    H.col = colhead() & 255; H.head = colhead() >> 8;
+    int fl = flags();
+    const bool cnstnd = fl & F_CNSTND, boxed = fl & F_BOXED;
+    int it = iter(), nfun = ifun();
+    double th = theta(), sb = sbgnrm(), step = stp();
+    int status = -1;
+    bool new_iter;
+    if (!(fl & F_RUNNING)) {
+      fl |= F_RUNNING;
+      sb = lb_projgr<N, NBD>(x, g, lo, hi, nb);
+      if (sb <= pgtol) status = LB_CONV_PGTOL;
+      new_iter = true;
+    } else new_iter = false;
+    while (status < 0) {
+      if (new_iter) {
+        lb_build_B<N>(H, th, B);
+        if (!cnstnd && H.col > 0) { for (int i = 0; i < N; i++) z[i] = x[i]; }
+        else lb_cauchy<N, NBD>(x, lo, hi, nb, g, iwhere, B, th, sb, z, scratch);
+        int nfree = 0;
+        for (int i = 0; i < N; i++) if (iwhere[i] <= 0) nfree++;
+        if (nfree != 0 && H.col != 0) {
+          if (!lb_subsm<N, NBD>(x, g, lo, hi, nb, iwhere, B, z, scratch)) { H.col = 0; H.head = 0; th = 1.0; continue; }
+        }
+        // ---- line search set-up (lnsrlb)
+        double dtd = 0;
+        for (int i = 0; i < N; i++) { d[i] = z[i] - x[i]; dtd += d[i] * d[i]; }
+        const double dnorm = lb_sqrt(dtd);
+        double stpmx = 1e10;
+        if (cnstnd) {
+          if (it == 0) stpmx = 1.0;
+          else {
+            LB_ROLLED
+            for (int i = 0; i < N; i++) {
+              double a1 = d[i];
+              const int nbi = nbd(i);
+              if (nbi != 0) {
+                if (a1 < 0 && nbi <= 2) {
+                  double a2 = lo[i] - x[i];
+                  if (a2 >= 0) stpmx = 0; else if (a1 * stpmx < a2) stpmx = lb_div(a2, a1);
+                } else if (a1 > 0 && nbi >= 2) {
+                  double a2 = hi[i] - x[i];
+                  if (a2 <= 0) stpmx = 0; else if (a1 * stpmx > a2) stpmx = lb_div(a2, a1);
+                }
+              }
+            }
+          }
+        }
+        step = (it == 0 && !boxed) ? fmin(lb_div(1.0, dnorm), stpmx) : 1.0;
+        for (int i = 0; i < N; i++) { t[i] = x[i]; r[i] = g[i]; }
+        fold() = f;
+        nfun = 0;
+        ls->ftol = 1e-3; ls->gtol = 0.9; ls->xtol = 0.1; ls->stpmin = 0; ls->stpmax = stpmx;
+        fl &= ~F_STARTED;
+        new_iter = false;
+      }
+      // ---- one line-search step
+      bool fail = false;
+      double gd = 0;
+      for (int i = 0; i < N; i++) gd += g[i] * d[i];
+      if (nfun == 0) {
+        gdold() = gd;
+        if (gd >= 0) fail = true;
+      }
+      if (!fail) {
+        int task;
+        if (!(fl & F_STARTED)) { task = ls->start(step, f, gd); fl |= F_STARTED; }
+        else task = ls->iterate(step, f, gd);
+        if (!(task == LbLineSearch::CONV || task == LbLineSearch::WARN)) {
+          nfun++;
+          if (step == 1.0) { for (int i = 0; i < N; i++) x[i] = z[i]; }
+          else { for (int i = 0; i < N; i++) x[i] = step * d[i] + t[i]; }
+          if (nfun - 1 >= maxls) fail = true;
+          else break;                                // evaluate (f, g) at x, then call advance() again
+        }
+      }
+      if (fail) {
+        for (int i = 0; i < N; i++) { x[i] = t[i]; g[i] = r[i]; }
+        f = fold();
+        if (H.col == 0) { status = LB_ABNORMAL; it++; break; }
+        H.col = 0; H.head = 0; th = 1.0;
+        new_iter = true;
+        continue;
+      }
+      it++;
+      sb = lb_projgr<N, NBD>(x, g, lo, hi, nb);
+      if (sb <= pgtol) { status = LB_CONV_PGTOL; break; }
+      const double fo = fold(), go = gdold();
+      double ddum = fmax(fmax(fabs(fo), fabs(f)), 1.0);
+      if ((fo - f) <= ftol * ddum) { status = LB_CONV_FTOL; break; }
+      if (it >= maxiter) { status = LB_MAXITER; break; }
+      double rr = 0, dr;
+      for (int i = 0; i < N; i++) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
+      if (step == 1.0) { dr = gd - go; ddum = -go; }
+      else {
+        dr = (gd - go) * step;
+        for (int i = 0; i < N; i++) d[i] *= step;
+        ddum = -go * step;
+      }
+      new_iter = true;
+      if (dr <= LB_EPSMCH * ddum) continue;       // skip the BFGS update
+      int slot;
+      if (H.col < LB_M) { slot = (H.head + H.col) % LB_M; H.col++; }
+      else { slot = H.head; H.head = (H.head + 1) % LB_M; }
+      for (int i = 0; i < N; i++) { H.S[slot][i] = d[i]; H.Y[slot][i] = r[i]; }
+      th = lb_div(rr, dr);
+    }
+    theta() = th; sbgnrm() = sb; stp() = step; fval() = f;
+    iter() = it; ifun() = nfun; colhead() = H.col | (H.head << 8); flags() = fl;
+    return status;
+  }
+};
+
+static_assert(LbSolver<3>::SIZE == LB_STORAGE(3) && LbSolver<1>::SIZE == LB_STORAGE(1), "LB_STORAGE out of step with LbSolver");
+
 // Obj must provide:  void fg(const double* x, double& f, double* g);
 // (f and the bound-aware forward-difference gradient; on device it is warp-cooperative and every
 // lane runs this routine redundantly with identical data, so control flow is warp-uniform.)
-// NBD >= 0: every variable has that bound type, known at compile time (the bound-type tests fold away)
 template <int N, class Obj, int NBD = -1>
 PWB_HDN int lbfgsb_minimize(Obj& obj, double* x, const double* lo, const double* hi, const int* nbd_in,
                             double ftol, double pgtol, int maxls, int maxiter, double* f_out, int* nit_out,
                             double* hist_storage) {
-  // x, g, iwhere and B are indexed by run-time variable numbers in the Cauchy / subspace steps; as
-  // thread-local arrays that forces them into local memory, so they live in caller storage too
-  double* const store = hist_storage + 2 * LB_M * N + 4 * N + 20;
-  double* const xs = store; double* g = xs + N; double* B = g + N;
-  int* iwhere = reinterpret_cast<int*>(B + N * N);
-  double* const scratch = B + N * N + N;                       // [4N + 3N*N]: cauchy / subsm work arrays
-  double* const x_out = x;
-  for (int i = 0; i < N; i++) xs[i] = x[i];
-  x = xs;
+  LbSolver<N, NBD> s;
+  s.init(hist_storage, x, lo, hi, nbd_in);
+  int status;
   double f;
-  int nbd[N];
-  for (int i = 0; i < N; i++) nbd[i] = NBD >= 0 ? NBD : nbd_in[i];
-  bool cnstnd = false, boxed = true;
-  for (int i = 0; i < N; i++) {
-    if (nbd[i] > 0) {
-      if (nbd[i] <= 2 && x[i] <= lo[i]) { if (x[i] < lo[i]) x[i] = lo[i]; }
-      else if (nbd[i] >= 2 && x[i] >= hi[i]) { if (x[i] > hi[i]) x[i] = hi[i]; }
-    }
-  }
-  for (int i = 0; i < N; i++) {
-    if (nbd[i] != 2) boxed = false;
-    if (nbd[i] == 0) iwhere[i] = -1;
-    else { cnstnd = true; iwhere[i] = (nbd[i] == 2 && hi[i] - lo[i] <= 0) ? 3 : 0; }
-  }
-  obj.fg(x, f, g);
-  double sbgnrm = lb_projgr<N>(x, g, lo, hi, nbd);
-  int iter = 0, status = LB_MAXITER;
-  LbHistory<N> H;
-  H.S = reinterpret_cast<double (*)[N]>(hist_storage);
-  H.Y = reinterpret_cast<double (*)[N]>(hist_storage + LB_M * N);
-  H.col = 0; H.head = 0;
-  double theta = 1.0;
-  if (sbgnrm <= pgtol) { for (int i = 0; i < N; i++) x_out[i] = x[i]; *f_out = f; *nit_out = 0; return LB_CONV_PGTOL; }
-
-  // Step vectors and the line-search record live in caller storage behind the (s, y) ring: on the
-  // device that is shared memory, ONE copy per warp.  As thread-local arrays they were spilled around
-  // every objective call, 32 copies per warp, and thrashed the small L1 left beside the atom tiles.
-  double* z = hist_storage + 2 * LB_M * N;
-  double* d = z + N; double* t = d + N; double* r = t + N;
-  LbLineSearch& ls = *reinterpret_cast<LbLineSearch*>(r + N);
-  while (true) {
-    lb_build_B<N>(H, theta, B);
-    if (!cnstnd && H.col > 0) { for (int i = 0; i < N; i++) z[i] = x[i]; }
-    else lb_cauchy<N>(x, lo, hi, nbd, g, iwhere, B, theta, sbgnrm, z, scratch);
-    int nfree = 0;
-    for (int i = 0; i < N; i++) if (iwhere[i] <= 0) nfree++;
-    if (nfree != 0 && H.col != 0) {
-      if (!lb_subsm<N>(x, g, lo, hi, nbd, iwhere, B, z, scratch)) { H.col = 0; H.head = 0; theta = 1.0; continue; }
-    }
-    // ---- line search (lnsrlb)
-    double dtd = 0;
-    for (int i = 0; i < N; i++) { d[i] = z[i] - x[i]; dtd += d[i] * d[i]; }
-    double dnorm = sqrt(dtd), stpmx = 1e10;
-    if (cnstnd) {
-      if (iter == 0) stpmx = 1.0;
-      else {
-        for (int i = 0; i < N; i++) {
-          double a1 = d[i];
-          if (nbd[i] != 0) {
-            if (a1 < 0 && nbd[i] <= 2) {
-              double a2 = lo[i] - x[i];
-              if (a2 >= 0) stpmx = 0; else if (a1 * stpmx < a2) stpmx = a2 / a1;
-            } else if (a1 > 0 && nbd[i] >= 2) {
-              double a2 = hi[i] - x[i];
-              if (a2 <= 0) stpmx = 0; else if (a1 * stpmx > a2) stpmx = a2 / a1;
-            }
-          }
-        }
-      }
-    }
-    double stp = (iter == 0 && !boxed) ? fmin(1.0 / dnorm, stpmx) : 1.0;
-    for (int i = 0; i < N; i++) { t[i] = x[i]; r[i] = g[i]; }
-    double fold = f, gd = 0, gdold = 0;
-    int ifun = 0, iback = 0, info = 0;
-    ls.ftol = 1e-3; ls.gtol = 0.9; ls.xtol = 0.1; ls.stpmin = 0; ls.stpmax = stpmx;
-    bool started = false, newx = false;
-    while (true) {
-      gd = 0;
-      for (int i = 0; i < N; i++) gd += g[i] * d[i];
-      if (ifun == 0) {
-        gdold = gd;
-        if (gd >= 0) { info = -4; break; }
-      }
-      int task;
-      if (!started) { task = ls.start(stp, f, gd); started = true; }
-      else task = ls.iterate(stp, f, gd);
-      if (task == LbLineSearch::CONV || task == LbLineSearch::WARN) { newx = true; break; }
-      ifun++;
-      iback = ifun - 1;
-      if (stp == 1.0) { for (int i = 0; i < N; i++) x[i] = z[i]; }
-      else { for (int i = 0; i < N; i++) x[i] = stp * d[i] + t[i]; }
-      if (iback >= maxls) break;
-      obj.fg(x, f, g);
+  do {
+    obj.fg(s.xs(), f, s.gs());
 #ifdef __CUDA_ARCH__
-      __syncwarp();
+    __syncwarp();
 #endif
-    }
-    if (!newx) {
-      for (int i = 0; i < N; i++) { x[i] = t[i]; g[i] = r[i]; }
-      f = fold;
-      if (H.col == 0) { status = LB_ABNORMAL; iter++; break; }
-      H.col = 0; H.head = 0; theta = 1.0;
-      (void)info;
-      continue;
-    }
-    iter++;
-    sbgnrm = lb_projgr<N>(x, g, lo, hi, nbd);
-    if (sbgnrm <= pgtol) { status = LB_CONV_PGTOL; break; }
-    double ddum = fmax(fmax(fabs(fold), fabs(f)), 1.0);
-    if ((fold - f) <= ftol * ddum) { status = LB_CONV_FTOL; break; }
-    if (iter >= maxiter) { status = LB_MAXITER; break; }
-    double rr = 0, dr;
-    for (int i = 0; i < N; i++) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
-    if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
-    else {
-      dr = (gd - gdold) * stp;
-      for (int i = 0; i < N; i++) d[i] *= stp;
-      ddum = -gdold * stp;
-    }
-    if (dr <= LB_EPSMCH * ddum) continue;       // skip the BFGS update
-    int slot;
-    if (H.col < LB_M) { slot = (H.head + H.col) % LB_M; H.col++; }
-    else { slot = H.head; H.head = (H.head + 1) % LB_M; }
-    for (int i = 0; i < N; i++) { H.S[slot][i] = d[i]; H.Y[slot][i] = r[i]; }
-    theta = rr / dr;
-  }
-  for (int i = 0; i < N; i++) x_out[i] = x[i];
-  *f_out = f;
-  *nit_out = iter;
+    status = s.advance(f, ftol, pgtol, maxls, maxiter);
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+  } while (status < 0);
+  for (int i = 0; i < N; i++) x[i] = s.xs()[i];
+  *f_out = s.fval();
+  *nit_out = s.iter();
   return status;
 }
 

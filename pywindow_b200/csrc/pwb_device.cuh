@@ -286,6 +286,98 @@ __device__ __forceinline__ void warp_min_clear(const WarpAtoms& A, const double*
   }
 }
 
+// ---- lane groups: G lanes (a power of two, aligned) of a warp work on one problem ---------------------------
+// k_opt_pore runs 32/G independent pore-centre searches per warp, one per group of G lanes.  Every group-wide
+// collective names the group's own lanes in its member mask, so groups may sit in different branches.
+template <int G> __device__ __forceinline__ unsigned group_mask(int lane) {
+  return G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+}
+template <int G> __device__ __forceinline__ double group_min_nonneg(unsigned mask, double v) {   // v >= 0 or +inf
+  const unsigned long long k = (unsigned long long)__double_as_longlong(v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(mask, hi);
+  const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+  return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+template <int G> __device__ __forceinline__ ValIdx group_vi_min(unsigned mask, ValIdx a) {   // smaller v, then smaller i
+  const unsigned long long k = dkey(a.v);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(mask, hi);
+  const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+  ValIdx r; r.v = dunkey(((unsigned long long)mh << 32) | ml);
+  r.i = (int)__reduce_min_sync(mask, a.v == r.v ? (unsigned)a.i : 0xffffffffu);
+  return r;
+}
+
+struct GroupAtoms {
+  const double4* p;      // [n] x, y, z, vdW radius of the type-bucketed atoms (shared or global memory)
+  int n, gl;             // atoms, lane index inside the group
+  const int* cls;        // [ncls+1] class starts
+  int ncls;
+  unsigned mask;         // member mask of the group
+};
+
+// min_i(|x_i - p_k| - r_i) for K points by the G lanes of one group; same arithmetic and the same reduce-before-
+// sqrt scheme as warp_min_clear_rs (bit-identical results for every G): the squared distances of (class c, point
+// k) are reduced over the group, parked in group lane (c - c0)*K + k, rooted once, and a stride-K butterfly
+// finishes the min over the G/K classes of a pass.
+template <int G, int K>
+__device__ __forceinline__ void group_min_clear(const GroupAtoms& A, const double* px, const double* py,
+                                                const double* pz, double* out) {
+  static_assert(G >= K && (G % K) == 0, "a pass must hold at least one class");
+  constexpr int CPG = G / K;
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = PWB_INF;
+  for (int c0 = 0; c0 < A.ncls; c0 += CPG) {
+    double mine = PWB_INF;
+    const int cend = min(A.ncls, c0 + CPG);
+    for (int c = c0; c < cend; c++) {
+      const int cb = A.cls[c], ce = A.cls[c + 1];
+      if (cb == ce) continue;
+      double m[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = PWB_INF;
+#ifdef OBJ_ROLLED
+#pragma unroll 1
+#endif
+      for (int t = cb + A.gl; t < ce; t += G) {
+        const double4 q = A.p[t];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+          m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
+        }
+      }
+      const int slot = (c - c0) * K;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const double red = group_min_nonneg<G>(A.mask, m[k]);
+        if (A.gl == slot + k) mine = red;
+      }
+    }
+    double v = PWB_INF;
+    if (mine < PWB_INF) v = sqrt(mine) - A.p[A.cls[c0 + A.gl / K]].w;
+#pragma unroll
+    for (int s = K; s < G; s <<= 1) v = dmin(v, __shfl_xor_sync(A.mask, v, s, G));
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = dmin(out[k], __shfl_sync(A.mask, v, k, G));
+  }
+}
+
+// pore_diameter with first-occurrence argmin over ORIGINAL atom indices (utilities.py:375-388), by one group
+template <int G>
+__device__ __forceinline__ ValIdx group_pore_argmin(const GroupAtoms& A, const int* orig, double cx, double cy, double cz) {
+  ValIdx b; b.v = PWB_INF; b.i = 0x7fffffff;
+#pragma unroll 1
+  for (int i = A.gl; i < A.n; i += G) {
+    const double4 q = A.p[i];
+    double dx = q.x - cx, dy = q.y - cy, dz = q.z - cz;
+    ValIdx c; c.v = sqrt(dx * dx + dy * dy + dz * dz) - q.w; c.i = orig[i];
+    b = vi_min(b, c);
+  }
+  return group_vi_min<G>(A.mask, b);
+}
+
 // ---- direction grid: which atoms can a ray from the centroid hit at all? ---------------------------
 // The pre-test of find_windows and the average-diameter sampling both ask, for ~1e3 rays from the
 // centroid o, which of the N vdW spheres the ray's LINE intersects.  Sphere i subtends a cap of angular

@@ -334,127 +334,170 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 }
 
 // =================================================================================================
-// k_opt_pore
+// k_opt_pore: opt_pore_diameter (utilities.py:400-426) -- 32/G concurrent L-BFGS-B searches per warp
 // =================================================================================================
-constexpr int OPT_WARPS = 4;
-
-// NBD >= 0: every variable has that bound type (compile time); NBD < 0: per-variable types in `nbd`
-template <int NBD>
-struct DevPoreObj3 {   // utilities.py:391-397 correct_pore_diameter + scipy 2-point differences
-  WarpAtoms A; const double* lo; const double* hi; const int* nbd; int nfev;
-  __device__ void fg(const double* x, double& f, double* g) {
-    nfev += 4;
-    double px[4], py[4], pz[4], h[3], m[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
-#pragma unroll
-    for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], NBD >= 0 ? NBD : nbd[i], lo[i], hi[i]);
-    px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
-    warp_min_clear<4>(A, px, py, pz, m);
-    f = -(m[0] * 2.0);
-#pragma unroll
-    for (int i = 0; i < 3; i++) g[i] = (-(m[i + 1] * 2.0) - f) / ((x[i] + h[i]) - x[i]);
-  }
-};
-
-#ifndef OPT_MINB
-#define OPT_MINB 8
+// One pore-centre search is a serial optimiser: ~100 objective evaluations separated by scalar bookkeeping
+// (Cauchy point, subspace step, dense-B update, More-Thuente step).  A group of G lanes owns one problem: the
+// lanes share the atom loop of the objective (group_min_clear) and run the bookkeeping redundantly, so a warp
+// spends its bookkeeping issue slots on 32/G problems at once instead of one.  The solver is the resumable
+// LbSolver: every trip of the loop below evaluates the objective of all groups of the warp at the SAME call site
+// (converged code), then each group advances its own state machine (groups in different branches serialise) and
+// pulls the next item from the work queue when it finishes -- iteration counts vary 10x between frames, so a
+// static item -> group map would leave lanes waiting for the slowest problem.
+// Measured on B200, 100 000 CC3 frames, ms per 10 000 frames (profiles/r2_opt_pore_variants.md): the kernel is
+// latency bound (one instruction per ~10 cycles per warp), so what counts is problems in flight per SM times
+// work shared per instruction.  G = 32 with atom tiles in shared memory (round 1: 32 problems per SM) 2.21;
+// G = 16 / 8 with shared tiles 2.56 / 3.28 (same 32 problems, fewer warps to hide latency); G = 8 with the tiles
+// read through L1 / L2 (1.3 KB of state per problem in shared memory, 96 problems per SM at 80 registers) 1.96.
+#ifndef OPT_G
+#define OPT_G 8                      // lanes per problem (4, 8, 16 or 32)
 #endif
-// doubles of shared memory per warp: double4[NA] atoms, the L-BFGS ring, class starts (17 ints, padded), bounds
-#define OPT_WARP_DOUBLES(NA) ((((NA) * 4 + LB_STORAGE(3) + 10 + 6 + 2) + 1) & ~(size_t)1)   // even: double4 tiles
-// one item on one warp; `smw` is the warp's private shared memory
-template <bool GENERAL>
-__device__ __forceinline__ void opt_pore_item(const pwb_batch& b, const Ws& ws, const int item, const int lane, double* smw) {
-  int* iiv = ws.item_i + (size_t)item * ITEM_I;
-  double* idv = ws.item_d + (size_t)item * ITEM_D;
-  double* rec = b.records + (size_t)item * b.rec_stride;
-  if (iiv[I_STATUS] & PWB_ST_BAD_ITEM) return;
-  const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double4* p4 = (double4*)smw;                                // x, y, z, radius
-  double* hist = (double*)(p4 + NA);                          // [LB_STORAGE(3)] L-BFGS state, one copy per warp
-  int* cls = (int*)(hist + LB_STORAGE(3));                     // [PWB_MAX_TYPES+1] class starts
-  if (lane <= PWB_MAX_TYPES) cls[lane] = iiv[I_CLS0 + lane];
-  for (int a = lane; a < n; a += 32) {
-    const double* q = ws.atoms + (size_t)(off + a) * 4;
-    p4[a] = make_double4(q[0], q[1], q[2], q[3]);
-  }
-  __syncwarp();
-  WarpAtoms A{p4, (const double*)p4 + 3, 4, n, lane, cls, b.n_types};
-  const int* orig = ws.atom_idx + off;
-  double c[3] = {idv[D_COM], idv[D_COM + 1], idv[D_COM + 2]};
-  double fopt = 0; int nit = 0, st = 0, nfev = 0;
-  if (b.centre_override) {
-    const double* o = b.centre_override + (size_t)item * 3;
-    c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
-    st = -1;
-  } else {
-    double pore_r = rec[PWB_REC_PORE_D] / 2.0;
-    if (b.opt_start) {   // opt_pore_diameter(com=...): start there; the default box is built around it (:411-420)
-      const double* o = b.opt_start + (size_t)item * 3;
-      c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
-      if (!b.opt_bounds) pore_r = warp_pore_argmin(A, orig, c[0], c[1], c[2]).v;
-    }
-    double* lo = (double*)(cls + 20);                          // [3], [3]: box bounds, one copy per warp
-    double* hi = lo + 3;
-    int* nbd = (int*)(hi + 3);                                 // [3] (general path only)
-    bool bad = false;
-    if (b.opt_bounds) {
-      const double* ob = b.opt_bounds + (size_t)item * 6;
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const double l = ob[2 * i], h = ob[2 * i + 1];
-        const bool fl = l > -PWB_INF, fh = h < PWB_INF;       // +-inf (or beyond 1e300) = no bound
-        bad |= fl && fh && l > h;
-        if (lane == i) { lo[i] = l; hi[i] = h; nbd[i] = fl ? (fh ? 2 : 1) : (fh ? 3 : 0); }
-      }
-    } else {
-      bad = pore_r < 0;
-#pragma unroll
-      for (int i = 0; i < 3; i++) if (lane == i) { lo[i] = c[i] - pore_r; hi[i] = c[i] + pore_r; }
-    }
-    if (bad) {   // scipy raises on inverted bounds; the reference has no handler
-      if (lane == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
-      return;
-    }
-    __syncwarp();
-    if (GENERAL) {
-      DevPoreObj3<-1> obj{A, lo, hi, nbd, 0};
-      st = lbfgsb_minimize<3, DevPoreObj3<-1>, -1>(obj, c, lo, hi, nbd, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
-      nfev = obj.nfev;
-    } else {
-      DevPoreObj3<2> obj{A, lo, hi, nullptr, 0};
-      st = lbfgsb_minimize<3, DevPoreObj3<2>, 2>(obj, c, lo, hi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fopt, &nit, hist);
-      nfev = obj.nfev;
-    }
-  }
-  ValIdx pa = warp_pore_argmin(A, orig, c[0], c[1], c[2]);
-  if (lane == 0) {
-    idv[D_CENTRE] = c[0]; idv[D_CENTRE + 1] = c[1]; idv[D_CENTRE + 2] = c[2];
-    rec[PWB_REC_OPT_D] = 2.0 * pa.v; rec[PWB_REC_OPT_ATOM] = pa.i;
-    rec[PWB_REC_OPT_C] = c[0]; rec[PWB_REC_OPT_C + 1] = c[1]; rec[PWB_REC_OPT_C + 2] = c[2];
-    rec[PWB_REC_OPT_NIT] = nit; rec[PWB_REC_OPT_STOP] = st; rec[PWB_REC_OPT_NFEV] = nfev;
-  }
-}
+#ifndef OPT_ATOMS_SMEM
+#define OPT_ATOMS_SMEM 0             // atom tile of each problem in shared memory (else read through L1 / L2)
+#endif
+constexpr int OPT_WARPS = 4;
+#ifndef OPT_MINB
+#define OPT_MINB 6                   // CTAs per SM the register budget must allow (80 registers per thread)
+#endif
+// doubles of shared memory per problem: double4[NA] atoms (optional), the solver state (incl. bounds), class
+// starts (17 ints, padded to 20); even, so that the double4 tiles stay 16-byte aligned
+#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) ((((SMEM_ATOMS) ? (NA) * 4 : 0) + LB_STORAGE(3) + 10 + 1) & ~(size_t)1)
 
-// Warps pull items from a queue (one atomic per item): the iteration counts of the optimiser vary by
-// 10x between frames, so a static item -> warp map leaves CTAs waiting for their slowest warp and the
-// last wave mostly empty.
-// GENERAL: user-supplied, possibly one-sided or absent bounds (opt_pore_diameter(bounds=...)); the default
-// instantiation has every variable boxed at compile time.
-template <bool GENERAL>
+template <int G, bool GENERAL, bool ATOMS_SMEM>
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)
 k_opt_pore(pwb_batch b, Ws ws) {
   extern __shared__ __align__(16) double sm[];
+  constexpr int PPW = 32 / G;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double* smw = sm + (size_t)w * OPT_WARP_DOUBLES(b.max_atoms);
-  int* queue = ws.item_i + I_QUEUE;                           // zeroed by run_opt before the launch
+  const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+  const unsigned mask = group_mask<G>(lane);
+  double* smp = sm + (size_t)(w * PPW + lane / G) * OPT_PROB_DOUBLES(b.max_atoms, ATOMS_SMEM);
+  double4* p4 = (double4*)smp;                                        // x, y, z, radius (if ATOMS_SMEM)
+  double* hist = smp + (ATOMS_SMEM ? (size_t)b.max_atoms * 4 : 0);    // [LB_STORAGE(3)] solver state
+  int* cls = (int*)(hist + LB_STORAGE(3));                            // [PWB_MAX_TYPES+1] class starts
+  int* queue = ws.item_i + I_QUEUE;                                   // zeroed by run_opt before the launch
+  LbSolver<3, GENERAL ? -1 : 2> S;
+  S.st = hist;
+  GroupAtoms A;
+  A.gl = gl; A.mask = mask; A.cls = cls; A.ncls = b.n_types; A.n = 0; A.p = p4;
+  const int* orig = nullptr;
+  int item = -1, nfev = 0, fstop = 0;
+  bool active = false, exhausted = false, fin = false;
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(queue, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= b.n_items) break;
-    opt_pore_item<GENERAL>(b, ws, item, lane, smw);
-    __syncwarp();
+#ifdef OPT_CTA_SYNC
+    // experiment: keep the warps of a CTA in step so that they share instruction-cache lines
+    if (!__syncthreads_or(active || fin || !exhausted)) break;
+#endif
+    if (!active && !exhausted) {
+      // ---- pull the next item; set its search up (or finish it at once when there is nothing to optimise)
+      int it = 0;
+      if (gl == 0) it = atomicAdd(queue, 1);
+      it = __shfl_sync(mask, it, gbase);
+      if (it >= b.n_items) exhausted = true;
+      else {
+        item = it;
+        int* iiv = ws.item_i + (size_t)item * ITEM_I;
+        double* idv = ws.item_d + (size_t)item * ITEM_D;
+        double* rec = b.records + (size_t)item * b.rec_stride;
+        if (!(iiv[I_STATUS] & PWB_ST_BAD_ITEM)) {
+          const int n = iiv[I_N], off = b.item_off[item];
+          __syncwarp(mask);                                           // the previous item's tile is no longer read
+          for (int c = gl; c <= PWB_MAX_TYPES; c += G) cls[c] = iiv[I_CLS0 + c];
+          const double4* src = (const double4*)(ws.atoms + (size_t)off * 4);
+          if (ATOMS_SMEM) { for (int a = gl; a < n; a += G) p4[a] = src[a]; A.p = p4; }
+          else A.p = src;
+          A.n = n;
+          orig = ws.atom_idx + off;
+          __syncwarp(mask);
+          double c[3] = {idv[D_COM], idv[D_COM + 1], idv[D_COM + 2]};
+          double lo3[3] = {0, 0, 0}, hi3[3] = {0, 0, 0};
+          int nb3[3] = {2, 2, 2};
+          bool search = true, bad = false;
+          nfev = 0;
+          if (b.centre_override) {
+            const double* o = b.centre_override + (size_t)item * 3;
+            c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+            search = false;
+          } else {
+            const bool has_start = b.opt_start != nullptr;
+            if (has_start) {   // opt_pore_diameter(com=...): start there; the default box is built around it (:411-420)
+              const double* o = b.opt_start + (size_t)item * 3;
+              c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
+            }
+            if (b.opt_bounds) {
+              const double* ob = b.opt_bounds + (size_t)item * 6;
+#pragma unroll
+              for (int i = 0; i < 3; i++) {
+                const double l = ob[2 * i], h = ob[2 * i + 1];
+                const bool fl = l > -PWB_INF, fh = h < PWB_INF;       // +-inf (or beyond 1e300) = no bound
+                bad |= fl && fh && l > h;
+                lo3[i] = l; hi3[i] = h; nb3[i] = fl ? (fh ? 2 : 1) : (fh ? 3 : 0);
+              }
+            } else {
+              const double pore_r = has_start ? group_pore_argmin<G>(A, orig, c[0], c[1], c[2]).v : rec[PWB_REC_PORE_D] / 2.0;
+              bad = pore_r < 0;
+#pragma unroll
+              for (int i = 0; i < 3; i++) { lo3[i] = c[i] - pore_r; hi3[i] = c[i] + pore_r; }
+            }
+          }
+          if (bad) {   // scipy raises on inverted bounds; the reference has no handler
+            if (gl == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+          } else if (search) {
+            S.init(hist, c, lo3, hi3, nb3);
+            __syncwarp(mask);
+            active = true;
+          } else {     // forced centre: parked where a finished search leaves its result
+            if (gl < 3) S.xs()[gl] = c[gl];
+            if (gl == 0) S.iter() = 0;
+            fin = true; fstop = -1;
+          }
+        }
+      }
+    }
+#ifndef OPT_CTA_SYNC
+    if (!__any_sync(0xffffffffu, active || fin)) {
+      if (__all_sync(0xffffffffu, exhausted)) break;
+      continue;
+    }
+#endif
+    if (active) {
+      // ---- the objective: -pore_diameter and its bound-aware forward differences (utilities.py:391-397 +
+      // scipy's 2-point scheme), 4 points per evaluation
+      const double* x = S.xs();
+      double px[4], py[4], pz[4], h[3], m[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { px[k] = x[0]; py[k] = x[1]; pz[k] = x[2]; }
+#pragma unroll
+      for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], S.nbd(i), S.lo()[i], S.hi()[i]);
+      px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
+      group_min_clear<G, 4>(A, px, py, pz, m);
+      nfev += 4;
+      const double f = -(m[0] * 2.0);
+      double* g = S.gs();
+      __syncwarp(mask);
+#pragma unroll
+      for (int i = 0; i < 3; i++) g[i] = lb_div(-(m[i + 1] * 2.0) - f, (x[i] + h[i]) - x[i]);
+      __syncwarp(mask);
+      const int st = S.advance(f, 2.220446049250313e-09, 1e-5, 20, 15000);
+      __syncwarp(mask);
+      if (st >= 0) { fin = true; fstop = st; active = false; }
+    }
+    if (fin) {   // one epilogue for searched and forced centres: pore_diameter at the final centre (:424-425)
+      fin = false;
+      __syncwarp(mask);
+      const double fc0 = S.xs()[0], fc1 = S.xs()[1], fc2 = S.xs()[2];
+      const int fnit = S.iter();
+      const ValIdx pa = group_pore_argmin<G>(A, orig, fc0, fc1, fc2);
+      if (gl == 0) {
+        double* idv = ws.item_d + (size_t)item * ITEM_D;
+        double* rec = b.records + (size_t)item * b.rec_stride;
+        idv[D_CENTRE] = fc0; idv[D_CENTRE + 1] = fc1; idv[D_CENTRE + 2] = fc2;
+        rec[PWB_REC_OPT_D] = 2.0 * pa.v; rec[PWB_REC_OPT_ATOM] = pa.i;
+        rec[PWB_REC_OPT_C] = fc0; rec[PWB_REC_OPT_C + 1] = fc1; rec[PWB_REC_OPT_C + 2] = fc2;
+        rec[PWB_REC_OPT_NIT] = fnit; rec[PWB_REC_OPT_STOP] = fstop; rec[PWB_REC_OPT_NFEV] = fstop < 0 ? 0 : nfev;
+      }
+      __syncwarp(mask);
+    }
   }
 }
 
@@ -1672,15 +1715,17 @@ static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  // fewer warps per CTA for very large molecules so the per-warp atom tiles still fit shared memory
-  const size_t per_warp = sizeof(double) * OPT_WARP_DOUBLES((size_t)b->max_atoms);
+  constexpr bool SA = OPT_ATOMS_SMEM != 0;
+  constexpr int PPW = 32 / OPT_G;
+  // fewer warps per CTA for very large molecules so the per-problem atom tiles still fit shared memory
+  const size_t per_warp = sizeof(double) * OPT_PROB_DOUBLES((size_t)b->max_atoms, SA) * PPW;
   int wpb = OPT_WARPS;
   while (wpb > 1 && per_warp * wpb > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb;
-  auto kern = b->opt_bounds ? k_opt_pore<true> : k_opt_pore<false>;
+  auto kern = b->opt_bounds ? k_opt_pore<OPT_G, true, SA> : k_opt_pore<OPT_G, false, SA>;
   if (set_smem(kern, sm, c->max_smem)) return 1;
   CK(cudaMemsetAsync(w.item_i + I_QUEUE, 0, sizeof(int), s));
-  int ctas = (b->n_items + wpb - 1) / wpb;
+  int ctas = (b->n_items + wpb * PPW - 1) / (wpb * PPW);
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, sm));
   const int resident = c->num_sms * (per_sm > 0 ? per_sm : 1);

@@ -206,9 +206,19 @@ class Engine:
         flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 3) for _, c in mols])
         return self.analyse(flat, off, types, vdw, mass, shared_types=False, max_atoms=max(sizes), **kw)
 
-    def frame_pipeline(self, elements, cap_frames, ray_cap, slots=2, **params):
-        """:class:`FramePipeline` bound to this engine (the trajectory front-ends' entry point)."""
-        return FramePipeline(self, elements, cap_frames, ray_cap, slots=slots, **params)
+    def frame_pipeline(self, elements, cap_frames, ray_cap=0, slots=2, **params):
+        """:class:`FramePipeline` bound to this engine (the trajectory front-ends' entry point).  Pipelines are
+        pooled: a later trajectory of the same molecule, batch size and parameters reuses the pinned / device buffers
+        (pinning a few hundred MB costs more than analysing 100 000 frames)."""
+        key = (tuple(str(e) for e in elements), int(cap_frames), int(slots), tuple(sorted(params.items())))
+        pipe = self._pinned.get(key)
+        if pipe is None or any(sl["busy"] for sl in pipe.slots):
+            if len(self._pinned) >= 4:
+                self._pinned.pop(next(iter(self._pinned)))
+            pipe = self._pinned[key] = FramePipeline(self, elements, cap_frames, 0, slots=slots, **params)
+        if ray_cap:
+            pipe.ensure_ray_capacity(ray_cap)
+        return pipe
 
     # ------------------------------------------------------------------ host-buffer path (e2e)
     def analyse_frames_host(self, coords_host, elements, *, ray_cap, out=None, stages=_lib.STAGE_ALL,
@@ -255,13 +265,16 @@ class Engine:
             return h_rec
 
 
-def host_ray_capacity(coords, vdw_max, adjust=1.0, margin=64):
-    """Upper bound of the ray count any of the frames ``coords`` [F,N,3] can need, from each frame's bounding box
-    (the host-side twin of ``pwb_ray_capacity``; no device synchronisation).  ``int(log10(4 pi D^2) 250 adjust)``
-    grows by 22 rays per 10 % of D, so ``margin`` rays cover frames ~30 % larger than any seen here."""
+def host_ray_capacity(coords, vdw_max, adjust=1.0, margin=64, sample=512):
+    """Upper bound of the ray count the frames ``coords`` [F,N,3] can need, from the bounding boxes of an evenly
+    spaced sample of them (the host-side twin of ``pwb_ray_capacity``; no device synchronisation).
+    ``int(log10(4 pi D^2) 250 adjust)`` grows by 22 rays per 10 % of D, so ``margin`` rays cover frames ~30 % larger
+    than any sampled; a frame that still overflows is flagged PWB_ST_RAY_CAP and re-analysed by the caller."""
     c = np.asarray(coords)
     if c.size == 0:
         return 64 + margin
+    if c.shape[0] > sample:
+        c = c[:: -(-c.shape[0] // sample)]
     ext = c.max(axis=1) - c.min(axis=1)
     D = float(np.sqrt((ext * ext).sum(axis=1)).max()) + 2.0 * float(vdw_max)
     P = int(np.log10(4.0 * np.pi * D * D) * 250.0 * float(adjust)) + 1
@@ -273,32 +286,50 @@ class FramePipeline:
     per-frame loop of trajectory.py:473-494): ``slots`` pinned input buffers [cap_frames, N, 3] that the trajectory
     decoders fill directly, persistent device staging / workspace / record buffers per slot, and
     ``pwb_full_analysis_host_async`` so that batch i runs on the GPU while the host decodes batch i+1.  Nothing is
-    allocated and nothing synchronises per batch except the wait for a slot's own records."""
+    allocated and nothing synchronises per batch except the wait for a slot's own records.  The ray-list workspace
+    is sized by :meth:`ensure_ray_capacity` once the first frames are known."""
 
-    def __init__(self, engine, elements, cap_frames, ray_cap, slots=2, stages=_lib.STAGE_ALL, adjust=1.0,
+    def __init__(self, engine, elements, cap_frames, ray_cap=0, slots=2, stages=_lib.STAGE_ALL, adjust=1.0,
                  increment=1.0, increment2=0.1, pore_opt=True):
         self.eng, self.cap, self.N = engine, int(cap_frames), len(elements)
-        self.ray_cap = int(ray_cap)
+        self.ray_cap = 0
         self.params = dict(stages=stages, adjust=adjust, increment=increment, increment2=increment2, pore_opt=pore_opt)
         eng, dev, F, N = engine, engine.device, self.cap, self.N
         types, vdw, mass = element_types(elements)
+        self.vdw_max = float(vdw.max())
         with torch.cuda.device(dev):
             self.types = eng._dev(types, torch.int32)
             self.vdw, self.mass = eng._dev(vdw, torch.float64), eng._dev(mass, torch.float64)
             self.off = torch.arange(0, (F + 1) * N, N, dtype=torch.int32, device=dev)
             self.layout = _lib.WsLayout()
-            eng.lib.pwb_workspace_layout(F, F * N, self.ray_cap, eng.win_cap, ctypes.byref(self.layout))
             self.slots = []
             for _ in range(slots):
                 self.slots.append({
-                    "h_in": torch.empty((F, N, 3), dtype=torch.float64).pin_memory(),
-                    "h_rec": torch.empty((F, eng.rec_stride), dtype=torch.float64).pin_memory(),
+                    "h_in": torch.empty((F, N, 3), dtype=torch.float64, pin_memory=True),
+                    "h_rec": torch.empty((F, eng.rec_stride), dtype=torch.float64, pin_memory=True),
                     "d_in": torch.empty((F * N, 3), dtype=torch.float64, device=dev),
                     "d_rec": torch.empty((F, eng.rec_stride), dtype=torch.float64, device=dev),
-                    "ws": torch.empty(self.layout.total, dtype=torch.uint8, device=dev),
-                    "done": torch.cuda.Event(), "n": 0})
+                    "ws": None, "done": torch.cuda.Event(), "n": 0, "busy": False})
             for sl in self.slots:
                 sl["in_np"], sl["rec_np"] = sl["h_in"].numpy(), sl["h_rec"].numpy()
+        if ray_cap:
+            self.ensure_ray_capacity(ray_cap)
+
+    def ensure_ray_capacity(self, ray_cap):
+        """(Re)allocate the per-slot workspaces for ray lists of ``ray_cap`` entries; no-op if already large enough.
+        Must not be called while a batch is in flight."""
+        if int(ray_cap) <= self.ray_cap:
+            return
+        if any(sl["busy"] for sl in self.slots):
+            raise RuntimeError("ensure_ray_capacity while a batch is in flight")
+        eng = self.eng
+        self.ray_cap = int(ray_cap)
+        with torch.cuda.device(eng.device):
+            eng.lib.pwb_workspace_layout(self.cap, self.cap * self.N, self.ray_cap, eng.win_cap, ctypes.byref(self.layout))
+            for sl in self.slots:
+                sl["ws"] = None
+            for sl in self.slots:
+                sl["ws"] = torch.empty(self.layout.total, dtype=torch.uint8, device=eng.device)
 
     def buffer(self, k):
         """numpy view [cap_frames, N, 3] of slot k's pinned input buffer (decode straight into it)."""
@@ -313,6 +344,10 @@ class FramePipeline:
         n = int(n_frames)
         if not 0 < n <= self.cap:
             raise ValueError(f"n_frames {n} outside 1..{self.cap}")
+        if sl["ws"] is None:
+            raise RuntimeError("ensure_ray_capacity() has not been called")
+        if sl["busy"]:
+            raise RuntimeError(f"slot {k} submitted again before it was collected")
         with torch.cuda.device(eng.device):
             p = self.params
             b, stream, _, _ = eng._make_batch(sl["d_in"], self.off, self.types, self.vdw, self.mass, True, self.N,
@@ -324,13 +359,16 @@ class FramePipeline:
                 eng._ctx, ctypes.byref(b), h_in.data_ptr(), sl["h_rec"].data_ptr(), sl["d_in"].data_ptr(),
                 sl["d_rec"].data_ptr(), n * self.N, stream))
             sl["done"].record(torch.cuda.current_stream(eng.device))
-            sl["n"], sl["src"] = n, src
+            sl["n"], sl["src"], sl["busy"] = n, src, True
 
     def collect(self, k):
         """Wait for slot k's batch; numpy view [n_frames, rec_stride] of its records (valid until the slot is
         submitted again)."""
         sl = self.slots[k]
+        if not sl["busy"]:
+            raise RuntimeError(f"collect on slot {k} without a submitted batch")
         sl["done"].synchronize()
+        sl["busy"] = False
         return sl["rec_np"][:sl["n"]]
 
 

@@ -226,7 +226,7 @@ class AnalysisOutput(dict):
 class Trajectory:
     """Shared machinery: frame selection, batched GPU analysis, result storage."""
 
-    batch_frames = 8192
+    batch_frames = 16384
 
     def __init__(self, filepath):
         self.filepath = pathlib.Path(filepath)
@@ -293,8 +293,10 @@ class Trajectory:
         """Analyse frames; results go to ``analysis_output`` exactly as in the reference.
         ``ncpus`` / ``ncpus_analysis`` are accepted and ignored (one GPU batch replaces the pools)."""
         todo = self._select(frames)
-        if override is False:
-            todo = [f for f in todo if f not in self.analysis_output]
+        if override is False and self.analysis_output:
+            have = self.analysis_output
+            have = dict.keys(have._load()) if isinstance(have, AnalysisOutput) else have.keys()
+            todo = [f for f in todo if f not in have]
         if not todo:
             return
         rank, size = world()
@@ -346,29 +348,22 @@ class Trajectory:
         slot on all host threads while the previous batch is on the GPU; one workspace / ray capacity for the whole
         trajectory; the only synchronisation per batch is the wait for its own records."""
         from .engine import host_ray_capacity
-        from .tables import atomic_vdw_radius
         eng = default_engine()
         if not frames:
             return np.zeros((0, eng.rec_stride)), []
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
-        N = len(elements)
-        B = max(1, min(self.batch_frames, len(frames)))
+        B = max(1, self.batch_frames)
         chunks = [frames[s:s + B] for s in range(0, len(frames), B)]
         threads = _host_threads()
-        first = np.empty((len(chunks[0]), N, 3), dtype=np.float64)
-        self._decode_into(chunks[0], first, threads)
-        adjust = float(gpu_kwargs.get("adjust", 1.0))
-        vmax = max(atomic_vdw_radius[str(e).upper()] for e in set(elements))
-        ray_cap = host_ray_capacity(first, vmax, adjust)
-        pipe = eng.frame_pipeline(elements, B, ray_cap, slots=min(2, len(chunks)), **gpu_kwargs)
-        records = np.empty((len(frames), eng.rec_stride), dtype=np.float64)
+        pipe = eng.frame_pipeline(elements, B, slots=2, **gpu_kwargs)
         nslots = len(pipe.slots)
-        pipe.buffer(0)[:len(chunks[0])] = first
-        del first
+        records = np.empty((len(frames), eng.rec_stride), dtype=np.float64)
         done = 0
         for k, chunk in enumerate(chunks):
-            if k:
-                self._decode_into(chunk, pipe.buffer(k % nslots), threads)
+            self._decode_into(chunk, pipe.buffer(k % nslots), threads)
+            if k == 0:      # ray-list capacity for the whole trajectory from the first batch's bounding boxes
+                pipe.ensure_ray_capacity(host_ray_capacity(pipe.buffer(0)[:len(chunk)], pipe.vdw_max,
+                                                           float(gpu_kwargs.get("adjust", 1.0))))
             pipe.submit(k % nslots, len(chunk))
             if k + 1 >= nslots:                      # the slot the next batch will be decoded into must be free
                 j = k + 1 - nslots

@@ -36,12 +36,17 @@ class _StubEngine:
         rec[:, L.REC_WIN0] = coords[:, 0, 0]
         return _StubResult(rec)
 
-    def frame_pipeline(self, elements, cap_frames, ray_cap, slots=2, **params):
+    def frame_pipeline(self, elements, cap_frames, ray_cap=0, slots=2, **params):
         return _StubPipeline(self, elements, cap_frames, slots)
 
 
 class _StubPipeline:
     """Host-only stand-in for engine.FramePipeline: same buffer / submit / collect protocol."""
+
+    vdw_max = 2.0
+
+    def ensure_ray_capacity(self, ray_cap):
+        assert ray_cap >= 64
 
     def __init__(self, eng, elements, cap, slots):
         self.eng, self.elements = eng, elements
