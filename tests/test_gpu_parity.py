@@ -140,28 +140,38 @@ def test_windows_teacher_forced(forced, goldens):
 
 
 def test_free_running(free, goldens):
-    """No forcing: window COUNT must equal the reference's on every molecule; the optimised pore
-    diameter sits within the reference's own noise floor."""
+    """No forcing: window COUNT must equal the reference's on every molecule.  The optimised pore diameter is held
+    to 1e-3 A where the reference's own tests pin it (the crystal structures of tests/test_validate_*.py, whose
+    optimiser starts at the optimum) and, on the 20 MD frames, to the reference's MEASURED self-agreement under
+    1e-12 A jitter (tests/golden/noise_floor.npz; the 220-frame version of this check, incl. free-running window
+    diameters, is tests/test_noise_floor.py)."""
     from pywindow_b200 import _lib as L
     from pywindow_b200.engine import record_windows
     _, rec = free
-    d = []
+    d = {}
     for i, n in enumerate(NAMES):
         g = goldens[n]
         if "opt_error" in g:
             assert int(rec[i][L.REC_STATUS]) & L.ST_OPT_BOUNDS, n
             continue
-        d.append(abs(rec[i][L.REC_OPT_D] - g["opt"][0]))
+        d[n] = abs(rec[i][L.REC_OPT_D] - g["opt"][0])
         if "has_windows" in g:
             w = record_windows(rec[i], warn=False)
             if not bool(g["has_windows"]):
                 assert w is None, n
             else:
                 assert w is not None and len(w[0]) == len(g["windows_diam"]), n
-    d = np.array(d)
-    print("free-running pore_opt: %d/%d within 1e-3, worst %.2e" % ((d <= 1e-3).sum(), len(d), d.max()))
-    assert (d > 1e-3).mean() <= 0.4
-    assert d.max() < 5e-2
+    pinned = {n: v for n, v in d.items() if n.startswith(("cc3", "win_", "avg_"))}
+    md = np.array([v for n, v in d.items() if n.startswith("md_")])
+    other = {n: v for n, v in d.items() if n.startswith("ex_")}
+    print("free-running pore_opt: pinned worst %.2e; md %d/%d within 1e-3, worst %.2e; examples worst %.2e (%s)" % (
+        max(pinned.values()), (md <= 1e-3).sum(), len(md), md.max(), max(other.values()), max(other, key=other.get)))
+    assert max(pinned.values()) <= 1e-3, pinned
+    floor = load_golden("noise_floor")
+    ref = np.abs(floor["jit_opt_d"] - floor["base_opt_d"])[:20]          # the same 20 MD frames, reference vs itself
+    assert (md > 1e-3).mean() <= (ref > 1e-3).mean() + 0.10
+    assert md.max() <= 1.5 * np.abs(floor["jit_opt_d"] - floor["base_opt_d"]).max()
+    assert max(other.values()) <= 1.5 * np.abs(floor["jit_opt_d"] - floor["base_opt_d"]).max()
 
 
 def test_batch_vs_single_and_shared_types(eng, goldens):
@@ -265,7 +275,9 @@ def test_seeded_synthetic_frames_against_oracle(eng):
         assert w is not None and g is not None and len(w[0]) == len(g[0]) == 4
         np.testing.assert_allclose(g[0], w[0], atol=1e-3)
         np.testing.assert_allclose(g[1], w[1], atol=5e-3)
-    assert near >= 0.6 * X.shape[0]        # free-running pore centre: the reference's own noise floor
+    # free-running pore centre, GPU vs ORACLE (two independent draws from the same chaotic optimiser; the
+    # reference-anchored version of this check is tests/test_noise_floor.py)
+    assert near >= 0.6 * X.shape[0]
 
 
 def test_path_scan_includes_the_ray_end_point(eng):
