@@ -37,9 +37,32 @@ inline uint32_t parse_digits8(uint64_t w) {
   return (uint32_t)((w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32);
 }
 
+inline bool is_digit(char c) { return (unsigned char)(c - '0') < 10; }
+
+// Fast path for DL_POLY's own records, "[-]d.ddddE[+-]dd" (%12.4E): five significant digits and a two-digit
+// exponent -> mantissa < 2^53 and |exp10| <= 22 + 4, i.e. Clinger's exact case, one correctly rounded multiply or
+// divide.  Returns nullptr if the token does not have exactly this shape (the generic parser takes over).
+inline const char* parse_e4(const char* p, const char* end, double* out) {
+  if (end - p < 11) return nullptr;
+  const bool neg = *p == '-';
+  if (neg || *p == '+') p++;
+  if (!(is_digit(p[0]) && p[1] == '.' && is_digit(p[2]) && is_digit(p[3]) && is_digit(p[4]) && is_digit(p[5]) &&
+        (p[6] == 'E' || p[6] == 'e') && (p[7] == '-' || p[7] == '+') && is_digit(p[8]) && is_digit(p[9]))) return nullptr;
+  if (p + 10 < end && !(p[10] == ' ' || p[10] == '\n' || p[10] == '\r' || p[10] == '\t')) return nullptr;
+  const uint64_t mant = (uint64_t)(p[0] - '0') * 10000 + (p[2] - '0') * 1000 + (p[3] - '0') * 100 + (p[4] - '0') * 10 + (p[5] - '0');
+  int e = (p[8] - '0') * 10 + (p[9] - '0');
+  e = (p[7] == '-' ? -e : e) - 4;
+  if (e < -22 || e > 22) return nullptr;
+  double v = (double)mant;
+  v = e < 0 ? v / kPow10[-e] : v * kPow10[e];
+  *out = neg ? -v : v;
+  return p + 10;
+}
+
 // parse one floating point token starting at p (leading blanks skipped); returns pointer past it
 inline const char* parse_double(const char* p, const char* end, double* out, bool* ok) {
   while (p < end && (*p == ' ' || *p == '\t')) p++;
+  if (const char* q = parse_e4(p, end, out)) return q;
   const char* start = p;
   bool neg = false;
   if (p < end && (*p == '-' || *p == '+')) { neg = *p == '-'; p++; }
@@ -124,6 +147,55 @@ extern "C" {
 // Byte offsets of every line that starts with "timestep" (DL_POLY frame records).  Returns the
 // number found (may exceed cap: call again with a larger array).
 int64_t pwb_history_index(const char* buf, int64_t len, int64_t* starts, int64_t cap) {
+  // Fixed-width files (every DL_POLY writer): all frames have the byte length of the first one.  If a "timestep"
+  // record really starts at every multiple of that length -- and the file ends on one -- the map is arithmetic and
+  // the 1.4 GB of a 100 000-frame file need not be scanned.  Anything else falls through to the full scan.
+  {
+    const char* end = buf + len;
+    const char* p = buf;
+    const char* first = nullptr;
+    const char* second = nullptr;
+    while (p < end && p - buf < (int64_t)1 << 20) {            // header is two short lines
+      if ((size_t)(end - p) >= 8 && memcmp(p, "timestep", 8) == 0) { first = p; break; }
+      p = skip_line(p, end);
+    }
+    if (first) {
+      p = skip_line(first, end);
+      while (p < end) {
+        if ((size_t)(end - p) >= 8 && memcmp(p, "timestep", 8) == 0) { second = p; break; }
+        p = skip_line(p, end);
+      }
+    }
+    if (first && second) {
+      const int64_t flen = second - first, body = len - (first - buf);
+      if (flen > 8 && body % flen == 0) {
+        const int64_t n = body / flen;
+        // (one touch per frame = one page fault per frame on a fresh mapping: spread over the host threads)
+        std::atomic<int> irregular(0);
+        int vt = (int)std::thread::hardware_concurrency();
+        vt = vt < 1 ? 1 : (vt > 32 ? 32 : vt);
+        if (n < 4096) vt = 1;
+        auto verify = [&](int t) {
+          for (int64_t k = n * t / vt; k < n * (t + 1) / vt && !irregular.load(std::memory_order_relaxed); k++) {
+            const char* q = first + k * flen;
+            if (!(memcmp(q, "timestep", 8) == 0 && q[-1] == '\n')) irregular.store(1);
+          }
+        };
+        {
+          std::vector<std::thread> pool;
+          for (int t = 1; t < vt; t++) pool.emplace_back(verify, t);
+          verify(0);
+          for (auto& th : pool) th.join();
+        }
+        const bool regular = irregular.load() == 0;
+        // a frame must not hide a second "timestep" line: the atom count of the record fixes the line count
+        if (regular) {
+          for (int64_t k = 0; k < n; k++) if (k < cap) starts[k] = (first - buf) + k * flen;
+          return n;
+        }
+      }
+    }
+  }
   // the file is cut into one range per host thread; a thread owns the lines that START inside its range
   int nt = (int)std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;

@@ -130,6 +130,80 @@ class LazyFrame(dict):
         return dict(self._load())
 
 
+class FrameMap(dict):
+    """``Trajectory.trajectory_map``: ``{frame: [start_byte, end_byte]}`` (plus ``"header"`` for HISTORY files,
+    trajectory.py:647-689) backed by one int64 ``[F, 2]`` array.  The dictionary entries are only created when
+    somebody looks at the dictionary; the analysis path reads the array (``bounds``) -- 1e5 two-element lists cost
+    as much as decoding 3e4 frames."""
+
+    __slots__ = ("pairs", "_loaded")
+
+    def __init__(self, pairs=None, **extra):
+        super().__init__(**extra)
+        self.pairs = np.zeros((0, 2), dtype=np.int64) if pairs is None else np.ascontiguousarray(pairs, dtype=np.int64)
+        self._loaded = self.pairs.shape[0] == 0
+
+    def bounds(self, frames):
+        """(starts, ends) int64 arrays of the given frames."""
+        idx = np.asarray(frames, dtype=np.int64)
+        if idx.size and (idx.min() < 0 or idx.max() >= self.pairs.shape[0]):
+            raise KeyError(int(idx.max() if idx.max() >= self.pairs.shape[0] else idx.min()))
+        sel = self.pairs[idx]
+        return np.ascontiguousarray(sel[:, 0]), np.ascontiguousarray(sel[:, 1])
+
+    def _load(self):
+        if not self._loaded:
+            self._loaded = True
+            dict.update(self, enumerate(self.pairs.tolist()))
+        return self
+
+    def __missing__(self, k):                       # single look-ups do not materialise the whole map
+        if isinstance(k, (int, np.integer)) and 0 <= k < self.pairs.shape[0]:
+            return self.pairs[k].tolist()
+        raise KeyError(k)
+
+    def __iter__(self):
+        return dict.__iter__(self._load())
+
+    def __len__(self):
+        return dict.__len__(self._load())
+
+    def __contains__(self, k):
+        return dict.__contains__(self._load(), k)
+
+    def __repr__(self):
+        return dict.__repr__(self._load())
+
+    def __eq__(self, other):
+        return dict.__eq__(self._load(), other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def keys(self):
+        return dict.keys(self._load())
+
+    def values(self):
+        return dict.values(self._load())
+
+    def items(self):
+        return dict.items(self._load())
+
+    def get(self, k, default=None):
+        return dict.get(self._load(), k, default)
+
+    def copy(self):
+        return dict(self._load())
+
+
+def _bounds(traj, frames):
+    """(starts, ends) of ``frames`` from a FrameMap or a plain dict map."""
+    tm = traj.trajectory_map
+    if isinstance(tm, FrameMap):
+        return tm.bounds(frames)
+    return (np.array([tm[f][0] for f in frames], dtype=np.int64), np.array([tm[f][1] for f in frames], dtype=np.int64))
+
+
 class AnalysisOutput(dict):
     """``Trajectory.analysis_output``: ``{frame: {molecule_key: properties}}`` (trajectory.py:483, :516-522).  The
     batched analysis hands over whole record tables; they are parked as blocks and only turned into per-frame
@@ -235,6 +309,33 @@ class Trajectory:
         self.analysis_output = AnalysisOutput()
         self.trajectory_map = {}
         self.no_of_frames = 0
+
+    # ---- the file stays mapped for the lifetime of the object: mapping and (above all) unmapping a multi-GB file
+    # once per decoded batch costs as much as decoding the batch
+    def _mapped(self):
+        """(mmap, uint8 numpy view) of the trajectory file, opened on first use."""
+        mm = self.__dict__.get("_mm")
+        if mm is None:
+            with self.filepath.open("rb") as fh:
+                mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            self._mm, self._mm_view = mm, np.frombuffer(mm, dtype=np.uint8)
+        return self._mm, self._mm_view
+
+    def close(self):
+        """Release the file mapping (it is re-opened on demand)."""
+        mm = self.__dict__.pop("_mm", None)
+        self.__dict__.pop("_mm_view", None)
+        if mm is not None:
+            try:
+                mm.close()
+            except BufferError:          # a numpy view handed out earlier is still alive: the GC will unmap
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ---- to be provided by the format classes
     def _decode_frame(self, frame_bytes):
@@ -459,32 +560,34 @@ class DLPOLY(Trajectory):
 
     def _map_history(self):
         lib = _lib.load()
-        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            size = len(mm)
-            buf = np.frombuffer(mm, dtype=np.uint8)
-            cap = max(1024, size // 2048)
-            while True:
-                starts = np.empty(cap, dtype=np.int64)
-                n = int(lib.pwb_history_index(buf.ctypes.data, size, starts.ctypes.data, cap))
-                if n <= cap:
-                    break
-                cap = n
-            starts = starts[:n].tolist()
-            if not starts:
-                raise _TrajectoryError("no 'timestep' record found: not a DL_POLY HISTORY file")
-            head = bytes(mm[:starts[0]]).decode("utf-8").split("\n")
-            first = bytes(mm[starts[0]:mm.find(b"\n", starts[0])]).split()
-            del buf
+        if self.filepath.stat().st_size == 0:
+            raise _TrajectoryError("no 'timestep' record found: not a DL_POLY HISTORY file")
+        mm, buf = self._mapped()
+        size = len(mm)
+        cap = max(1024, size // 2048)
+        while True:
+            starts = np.empty(cap, dtype=np.int64)
+            n = int(lib.pwb_history_index(buf.ctypes.data, size, starts.ctypes.data, cap))
+            if n <= cap:
+                break
+            cap = n
+        starts = starts[:n]
+        if not n:
+            raise _TrajectoryError("no 'timestep' record found: not a DL_POLY HISTORY file")
+        s0 = int(starts[0])
+        head = bytes(mm[:s0]).decode("utf-8").split("\n")
+        first = bytes(mm[s0:mm.find(b"\n", s0)]).split()
         header = [int(i) for i in head[1].split()]
-        self.trajectory_map = {"header": header}
+        pairs = np.empty((n, 2), dtype=np.int64)
+        pairs[:, 0] = starts
+        pairs[:-1, 1] = starts[1:]
+        pairs[-1, 1] = size
+        self.trajectory_map = FrameMap(pairs, header=header)
         self.content_type = self._keytrj[header[0]]
         self.periodic_boundary = self._imcon[header[1]]
         self.no_of_atoms = header[2]
         self._frame_keytrj, self._frame_imcon = int(first[3]), int(first[4])
-        bounds = starts + [size]
-        for k in range(len(starts)):
-            self.trajectory_map[k] = [bounds[k], bounds[k + 1]]
-        self.no_of_frames = len(starts)
+        self.no_of_frames = n
         self.check_log = ""
 
     def _native_decode(self, frames, want_lattice, out=None, threads=0):
@@ -492,8 +595,7 @@ class DLPOLY(Trajectory):
         write the coordinates into ``out[:F]`` (a pinned staging buffer) instead of a new array."""
         lib = _lib.load()
         n, N = len(frames), self.no_of_atoms
-        starts = np.array([self.trajectory_map[f][0] for f in frames], dtype=np.int64)
-        ends = np.array([self.trajectory_map[f][1] for f in frames], dtype=np.int64)
+        starts, ends = _bounds(self, frames)
         if out is None:
             xyz = np.empty((n, N, 3), dtype=np.float64)
         else:
@@ -502,12 +604,10 @@ class DLPOLY(Trajectory):
             xyz = out
         periodic = self._frame_imcon in (1, 2, 3)
         lat = np.empty((n, 3, 3), dtype=np.float64) if (want_lattice and periodic) else None
-        with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            buf = np.frombuffer(mm, dtype=np.uint8)
-            bad = int(lib.pwb_history_decode(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, N,
-                                             self._frame_keytrj, self._frame_imcon, xyz.ctypes.data,
-                                             lat.ctypes.data if lat is not None else None, threads))
-            del buf
+        mm, buf = self._mapped()
+        bad = int(lib.pwb_history_decode(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, N,
+                                         self._frame_keytrj, self._frame_imcon, xyz.ctypes.data,
+                                         lat.ctypes.data if lat is not None else None, threads))
         if bad:
             raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {N} atoms, keytrj "
                                    f"{self._frame_keytrj}, imcon {self._frame_imcon})")
@@ -555,19 +655,16 @@ def _native_xyz_like(traj, entry, frames, natoms, out=None, threads=0):
     """Shared driver of pwb_xyz_decode / pwb_pdb_decode: frames -> [F, natoms, 3] float64 (into ``out[:F]`` if given)."""
     lib = _lib.load()
     n = len(frames)
-    starts = np.array([traj.trajectory_map[f][0] for f in frames], dtype=np.int64)
-    ends = np.array([traj.trajectory_map[f][1] for f in frames], dtype=np.int64)
+    starts, ends = _bounds(traj, frames)
     if out is None:
         xyz = np.empty((n, natoms, 3), dtype=np.float64)
     else:
         if out.shape[1:] != (natoms, 3) or out.shape[0] < n or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise _TrajectoryError(f"decode buffer {out.shape} does not fit {n} frames of {natoms} atoms")
         xyz = out
-    with traj.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-        buf = np.frombuffer(mm, dtype=np.uint8)
-        bad = int(getattr(lib, entry)(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, natoms,
-                                      xyz.ctypes.data, threads))
-        del buf
+    mm, buf = traj._mapped()
+    bad = int(getattr(lib, entry)(buf.ctypes.data, len(mm), starts.ctypes.data, ends.ctypes.data, n, natoms,
+                                  xyz.ctypes.data, threads))
     if bad:
         raise _TrajectoryError(f"frame {frames[bad - 1]} is malformed (expected {natoms} atoms)")
     return xyz
