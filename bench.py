@@ -765,7 +765,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-api", action="store_true", help="omit the public-API legs (profiling runs)")
     ap.add_argument("--skip-secondary", action="store_true", help="omit the secondary configs (profiling runs)")
-    ap.add_argument("--chunks", type=int, default=4, help="sub-batches pipelined over internal streams per step")
+    ap.add_argument("--chunks", type=int, default=2, help="sub-batches pipelined over internal streams per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

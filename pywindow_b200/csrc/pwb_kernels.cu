@@ -557,6 +557,11 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   DG.cnt = spos + RAY_TILE;                 // [DG_BINS]
   DG.overflow = DG.cnt + DG_BINS;           // [1] (+1 pad)
   DG.list = (unsigned short*)(DG.overflow + 2);   // [DG_BINS][DG_CAP]
+#ifdef RAYS_FP32_FILTER
+  // experiment: FP32 copy (Lx, Ly, Lz, r^2 - |L|^2) for a filter in front of the exact FP64 pre-test
+  float4* lf = (float4*)(((uintptr_t)(DG.list + DG_BINS * DG_CAP) + 15) & ~(uintptr_t)15);
+  __shared__ float s_eps_u, s_eps_t;
+#endif
 
   // shift exactly as find_windows does (utilities.py:1379-1393)
   const double cmx = idv[D_COM], cmy = idv[D_COM + 1], cmz = idv[D_COM + 2];
@@ -597,6 +602,26 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
       dg_insert_cap(DG, a, x * il, y * il, z * il, sa);
       if (L - ra <= onorm + 1e-9) dg_insert_cap(DG, a, -x * il, -y * il, -z * il, sa);
     }
+#ifdef RAYS_FP32_FILTER
+    // Rigorous FP32 error bounds (u = 2^-24): |t32 - t| <= 5.1 u |L| and |under32 - under| <= 7.3e-7 (|L|^2 + r^2)
+    // (conversion of L, n and W, three rounded products / FMAs, one squared term); the margins below are larger.
+    double m2 = 0;
+    for (int a = tid; a < n; a += nt) {
+      const double x = lx[a], y = ly[a], z = lz[a], L2 = x * x + y * y + z * z;
+      lf[a] = make_float4((float)x, (float)y, (float)z, (float)lw[a]);
+      m2 = fmax(m2, 2.0 * L2 + lw[a]);                    // |L|^2 + r^2
+    }
+    m2 = warp_max(m2);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = m2;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int k = 0; k < (nt >> 5); k++) t = fmax(t, red[k]);
+      s_eps_u = (float)(1e-6 * t + 1e-30);
+      s_eps_t = (float)(5e-7 * (sqrt(t) + onorm) + 1e-30);
+    }
+#endif
   }
   const double R = idv[D_MAXD] / 2.0;     // max_dim is translation invariant: reuse (utilities.py:1398)
   const int P = n_sampling_points(R, b.adjust);
@@ -646,12 +671,31 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
         const int bin = dg_bin(nx[u], ny[u], nz[u]), m = DG.cnt[bin];
         const unsigned short* lst = DG.list + bin * DG_CAP;
         int hit = 0;
+#ifdef RAYS_FP32_FILTER
+        const float nxf = (float)nx[u], nyf = (float)ny[u], nzf = (float)nz[u], onf = (float)on[u];
+        const float eu = s_eps_u, et = s_eps_t;
+        for (int e = 0; e < m; e++) {
+          const int a = lst[e];
+          const float4 Lf = lf[a];
+          const float tf = fmaf(Lf.x, nxf, fmaf(Lf.y, nyf, Lf.z * nzf));
+          const float uf = fmaf(tf, tf, Lf.w);
+          const bool sure = uf > eu && tf > onf + et;           // a hit whatever the rounding
+          const bool maybe = uf > -eu && tf > onf - et;         // cannot be excluded in FP32
+          hit |= (int)sure;
+          if (maybe && !sure) {                                 // rare: decide exactly
+            const double t = fma(lx[a], nx[u], fma(ly[a], ny[u], lz[a] * nz[u]));
+            const double under = fma(t, t, lw[a]);
+            hit |= (int)(under > 0.0) & (int)(t > on[u]);
+          }
+        }
+#else
         for (int e = 0; e < m; e++) {
           const int a = lst[e];
           const double t = fma(lx[a], nx[u], fma(ly[a], ny[u], lz[a] * nz[u]));
           const double under = fma(t, t, lw[a]);
           hit |= (int)(under > 0.0) & (int)(t > on[u]);
         }
+#endif
         blk[u] = hit;
       }
     } else {
@@ -1738,6 +1782,9 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
 static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
   size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_ACAP) +
               sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE + DG_BINS + 2) + sizeof(unsigned short) * DG_BINS * DG_CAP;
+#ifdef RAYS_FP32_FILTER
+  sm += sizeof(float) * 4 * (size_t)b->max_atoms + 16;
+#endif
   if (set_smem(k_rays, sm, c->max_smem)) return 1;
   const dim3 grid((unsigned)b->n_items, (unsigned)tile_ctas(c, b, RAY_TILE));
   k_rays<<<grid, RAY_THREADS, sm, s>>>(*b, w, c->c);
@@ -1827,8 +1874,14 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
   if (h_coords && !chunk_copies)
     CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, s));
   if (G == 1) {
-    if (chunk_copies)
-      CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, s));
+    if (chunk_copies) {
+      if (staging_idle) {   // pipelined reader: the input copy runs under the kernels of the batch queued before
+        CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->h2d[0], c->copy_stream));
+        CK(cudaStreamWaitEvent(s, c->h2d[0], 0));
+      } else
+        CK(cudaMemcpyAsync((void*)b->coords, h_coords, sizeof(double) * 3 * (size_t)b->total_atoms, cudaMemcpyHostToDevice, s));
+    }
     if (run_stages(c, b, w, s)) return 1;
   } else {
     CK(cudaEventRecord(c->fork, s));

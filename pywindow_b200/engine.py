@@ -84,7 +84,7 @@ class BatchResult:
 
 
 class Engine:
-    def __init__(self, device=None, table_cap=4100, win_cap=DEFAULT_WIN_CAP, chunks=4):
+    def __init__(self, device=None, table_cap=4100, win_cap=DEFAULT_WIN_CAP, chunks=2):
         if not torch.cuda.is_available():
             raise PwbNoDeviceError("pywindow_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = _lib.load()
