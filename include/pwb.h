@@ -187,6 +187,15 @@ int pwb_discrete_molecules(int n_frames, int n_atoms, int rebuild, double tol, d
                            const double* type_mass, const int32_t* type_terminal, int out_cap, int mol_cap,
                            int32_t* n_mol, int32_t* mol_off, int32_t* out_src, double* out_xyz,
                            int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Pack those per-frame outputs into ONE dense batch for pwb_full_analysis_batch (make_modular + the per-molecule
+ * loop of trajectory.py:512-522 for a whole batch of frames): item_off [items+1], coords [atoms][3], per-atom types
+ * (shared_types = 0) and the (frame, molecule) key of every item.  Device pointers sized for the worst case the
+ * caller allows (items <= F*mol_cap, atoms <= F*out_cap); scratch: 2*F + 4 ints.  counts_host[4] (HOST) receives
+ * {items, atoms, largest molecule, OR of status}; synchronises `stream` once to deliver them.                */
+int pwb_dm_compact(int n_frames, int n_atoms, int out_cap, int mol_cap, const int32_t* n_mol, const int32_t* mol_off,
+                   const int32_t* out_src, const double* out_xyz, const int32_t* status, const int32_t* atom_type,
+                   int32_t* item_off, double* coords, int32_t* types, int32_t* item_frame, int32_t* item_mol,
+                   int32_t* scratch, int32_t* counts_host, void* stream);
 void pwb_set_error(const char* msg);
 
 /* ---- host side: DL_POLY HISTORY text -> [F][N][3] float64 (replaces the per-frame Python decode of

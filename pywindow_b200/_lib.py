@@ -27,7 +27,7 @@ EXPORTS = [
     "pwb_workspace_layout", "pwb_ray_capacity", "pwb_frame_scalars", "pwb_average_diameter",
     "pwb_opt_pore", "pwb_ray_search", "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch",
     "pwb_full_analysis_host", "pwb_full_analysis_host_async", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
-    "pwb_dm_workspace_layout", "pwb_discrete_molecules", "pwb_set_error", "pwb_history_index",
+    "pwb_dm_workspace_layout", "pwb_discrete_molecules", "pwb_dm_compact", "pwb_set_error", "pwb_history_index",
     "pwb_history_decode", "pwb_xyz_index", "pwb_xyz_decode", "pwb_pdb_decode", "pwb_history_write",
 ]
 
@@ -92,6 +92,8 @@ def load():
     L.pwb_discrete_molecules.argtypes = [ci, ci, ci, ctypes.c_double, ctypes.c_double, vp, vp, ci, vp, ci, vp, vp,
                                          vp, ci, ci, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     L.pwb_discrete_molecules.restype = ci
+    L.pwb_dm_compact.argtypes = [ci, ci, ci, ci] + [vp] * 14
+    L.pwb_dm_compact.restype = ci
     i64 = ctypes.c_int64
     L.pwb_history_index.argtypes = [vp, i64, vp, i64]
     L.pwb_history_index.restype = i64

@@ -470,6 +470,77 @@ k_dm_fill(DmArgs A) {
   if (lane == 0) { A.n_mol[f] = nmol; if (st) atomicOr(&A.status[f], st); }
 }
 
+// ---- compaction of the per-frame outputs into ONE dense batch for the analysis kernels -----------------------
+// k_dm_scan  one CTA: exclusive prefix sums over the frames of (molecules kept, atoms emitted) -> per-frame bases,
+//            totals and the OR of the status words
+// k_dm_emit  CTA per frame: item offsets, coordinates, atom types and (frame, molecule) keys at the frame's bases
+struct DmPack {
+  int F, N, out_cap, mol_cap;
+  const int* n_mol; const int* mol_off; const int* out_src; const double* out_xyz; const int* status;
+  const int* atom_type;
+  int* base;           // [F][2] item base, atom base (scratch)
+  int* item_off;       // [items + 1]
+  double* coords;      // [atoms][3]
+  int* types;          // [atoms]
+  int* item_frame;     // [items]
+  int* item_mol;       // [items]
+  int* counts;         // [4] items, atoms, largest molecule, status OR
+};
+
+__global__ void __launch_bounds__(1024)
+k_dm_scan(DmPack P) {
+  __shared__ int s_items[1024], s_atoms[1024], s_st[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (P.F + nt - 1) / nt, f0 = tid * per, f1 = min(P.F, f0 + per);
+  int items = 0, atoms = 0, st = 0;
+  for (int f = f0; f < f1; f++) {
+    const int nm = P.n_mol[f];
+    items += nm;
+    atoms += P.mol_off[(size_t)f * (P.mol_cap + 1) + nm];
+    st |= P.status[f];
+  }
+  s_items[tid] = items; s_atoms[tid] = atoms; s_st[tid] = st;
+  __syncthreads();
+  for (int d = 1; d < nt; d <<= 1) {                      // inclusive Hillis-Steele scan over the strips
+    const int a = tid >= d ? s_items[tid - d] : 0, b = tid >= d ? s_atoms[tid - d] : 0, c = tid >= d ? s_st[tid - d] : 0;
+    __syncthreads();
+    s_items[tid] += a; s_atoms[tid] += b; s_st[tid] |= c;
+    __syncthreads();
+  }
+  int ib = s_items[tid] - items, ab = s_atoms[tid] - atoms;
+  for (int f = f0; f < f1; f++) {
+    const int nm = P.n_mol[f];
+    P.base[2 * f] = ib; P.base[2 * f + 1] = ab;
+    ib += nm;
+    ab += P.mol_off[(size_t)f * (P.mol_cap + 1) + nm];
+  }
+  if (tid == nt - 1) {
+    P.counts[0] = s_items[tid]; P.counts[1] = s_atoms[tid]; P.counts[2] = 0; P.counts[3] = s_st[tid];
+    P.item_off[s_items[tid]] = s_atoms[tid];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_dm_emit(DmPack P) {
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int nm = P.n_mol[f];
+  const int* moff = P.mol_off + (size_t)f * (P.mol_cap + 1);
+  const int ib = P.base[2 * f], ab = P.base[2 * f + 1], na = moff[nm];
+  int big = 0;
+  for (int k = tid; k < nm; k += blockDim.x) {
+    P.item_off[ib + k] = ab + moff[k];
+    P.item_frame[ib + k] = f;
+    P.item_mol[ib + k] = k;
+    big = max(big, moff[k + 1] - moff[k]);
+  }
+  const int* src = P.out_src + (size_t)f * P.out_cap;
+  const double* xyz = P.out_xyz + (size_t)f * P.out_cap * 3;
+  for (int j = tid; j < na; j += blockDim.x) P.types[ab + j] = P.atom_type[src[j]];
+  for (int j = tid; j < 3 * na; j += blockDim.x) P.coords[(size_t)ab * 3 + j] = xyz[j];
+  big = __reduce_max_sync(0xffffffffu, big);
+  if ((tid & 31) == 0 && big > 0) atomicMax(&P.counts[2], big);
+}
+
 }  // namespace pwb
 
 using namespace pwb;
@@ -542,6 +613,32 @@ int pwb_discrete_molecules(int F, int N, int rebuild, double tol, double max_cov
   }
   k_dm_fill<<<(F + DM_FILL_WARPS - 1) / DM_FILL_WARPS, DM_FILL_WARPS * 32, 0, s>>>(A);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pwb_set_error(cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+// Pack the per-frame outputs of pwb_discrete_molecules into one dense batch for pwb_full_analysis_batch
+// (MolecularSystem.make_modular + the per-molecule loop of trajectory.py:512-522 for a whole batch of frames):
+// item_off [items+1], coords [atoms][3], types [atoms] (per-atom type, i.e. shared_types = 0), and the (frame,
+// molecule) key of every item.  Device pointers; the dense buffers must hold F*mol_cap + 1 / F*out_cap entries
+// (or whatever bound the caller can prove); `scratch` = 2*F + 4 ints.  counts_host[4] (host memory) receives
+// {items, atoms, largest molecule, OR of the status words}; the call synchronises `stream` once to deliver them --
+// the analysis launch needs the batch size on the host.
+int pwb_dm_compact(int F, int N, int out_cap, int mol_cap, const int* n_mol, const int* mol_off, const int* out_src,
+                   const double* out_xyz, const int* status, const int* atom_type, int* item_off, double* coords,
+                   int* types, int* item_frame, int* item_mol, int* scratch, int* counts_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (F <= 0) { counts_host[0] = counts_host[1] = counts_host[2] = counts_host[3] = 0; return 0; }
+  DmPack P;
+  P.F = F; P.N = N; P.out_cap = out_cap; P.mol_cap = mol_cap;
+  P.n_mol = n_mol; P.mol_off = mol_off; P.out_src = out_src; P.out_xyz = out_xyz; P.status = status;
+  P.atom_type = atom_type; P.base = scratch; P.counts = scratch + 2 * (size_t)F;
+  P.item_off = item_off; P.coords = coords; P.types = types; P.item_frame = item_frame; P.item_mol = item_mol;
+  k_dm_scan<<<1, 1024, 0, s>>>(P);
+  k_dm_emit<<<F, 128, 0, s>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts_host, P.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { pwb_set_error(cudaGetErrorString(e)); return 1; }
   return 0;
 }

@@ -30,13 +30,17 @@ def shard_range(n, rank, size):
 
 
 def gather_records(records, keys):
-    """All ranks contribute ``records`` [k_r, S] float64 and ``keys`` [(frame, molecule), ...];
-    every rank receives the concatenation in rank order."""
+    """All ranks contribute ``records`` [k_r, S] float64 and their keys (a ``trajectory.RecordKeys`` or a list of
+    ``(frame, molecule)`` pairs); every rank receives the concatenation in rank order.  One fixed-width payload row
+    per record (frame, molecule key, record) goes through a single ``all_gather_into_tensor``; no per-record Python."""
     import torch
     import torch.distributed as dist
+    from .trajectory import RecordKeys
     rank, size = world()
     if size == 1:
         return records, keys
+    if not isinstance(keys, RecordKeys):
+        keys = RecordKeys.from_pairs(keys)
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     stride = records.shape[1] if records.ndim == 2 else 0
@@ -47,19 +51,15 @@ def gather_records(records, keys):
     stride = max(int(m[1]) for m in metas)
     kmax = max(counts)
     # payload row: frame index, molecule key (numeric; -1 encodes the string key "0"), then the record
-    pay = torch.zeros((kmax, stride + 2), dtype=torch.float64, device=dev)
+    rows = np.zeros((kmax, stride + 2))
     if len(keys):
-        rows = np.zeros((len(keys), stride + 2))
-        rows[:, 0] = [k[0] for k in keys]
-        rows[:, 1] = [-1 if isinstance(k[1], str) else k[1] for k in keys]
-        rows[:, 2:] = records
-        pay[:len(keys)] = torch.from_numpy(rows).to(dev)
-    out = torch.zeros((size * kmax, stride + 2), dtype=torch.float64, device=dev)
+        rows[:len(keys), 0] = keys.frames
+        rows[:len(keys), 1] = keys.mols
+        rows[:len(keys), 2:] = records
+    pay = torch.from_numpy(rows).to(dev)
+    out = torch.empty((size * kmax, stride + 2), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, pay)
     out = out.cpu().numpy().reshape(size, kmax, stride + 2)
-    recs, allkeys = [], []
-    for r in range(size):
-        blk = out[r, :counts[r]]
-        recs.append(blk[:, 2:])
-        allkeys += [(int(a), "0" if b < 0 else int(b)) for a, b in blk[:, :2]]
-    return (np.concatenate(recs) if recs else np.zeros((0, stride))), allkeys
+    valid = np.concatenate([out[r, :counts[r]] for r in range(size)]) if sum(counts) else np.zeros((0, stride + 2))
+    return (np.ascontiguousarray(valid[:, 2:]),
+            RecordKeys(valid[:, 0].astype(np.int64), valid[:, 1].astype(np.int64)))

@@ -52,10 +52,19 @@ def _type_tables(elements):
 
 
 class DiscreteBatch:
-    """Device-side result of :func:`discrete_molecules_batch`."""
+    """Device-side result of :func:`discrete_molecules_batch` (views of the engine's pooled buffers: valid until
+    the next call with the same batch shape)."""
 
-    def __init__(self, n_mol, mol_off, out_src, out_xyz, status, N):
-        self.n_mol, self.mol_off, self.out_src, self.out_xyz, self.status, self.N = n_mol, mol_off, out_src, out_xyz, status, N
+    def __init__(self, n_mol, mol_off, out_src, out_xyz, status, N, bufs=None):
+        self.n_mol_dev, self.mol_off, self.out_src, self.out_xyz, self.status, self.N = n_mol, mol_off, out_src, out_xyz, status, N
+        self._bufs = bufs
+        self._n_mol = None
+
+    @property
+    def n_mol(self):
+        if self._n_mol is None:
+            self._n_mol = self.n_mol_dev.cpu().numpy()
+        return self._n_mol
 
     def molecules(self, frame, elements, atom_ids=None):
         """Frame's molecules as the reference's list of dicts (utilities.py:1046-1085)."""
@@ -73,84 +82,136 @@ class DiscreteBatch:
         return out
 
 
-def discrete_molecules_batch(coords, elements, lattice=None, rebuild=False, tol=0.4, out_factor=2.0, engine=None):
-    """``coords`` [F,N,3]; ``lattice`` None | [3,3] | [F,3,3].  Returns a :class:`DiscreteBatch`."""
-    eng = engine or default_engine()
-    lib, dev = eng.lib, eng.device
-    F, N = int(coords.shape[0]), int(coords.shape[1])
+def _dm_buffers(eng, F, N, out_cap, elements):
+    """Pooled device buffers of the periodic stage for (F, N, out_cap): nothing is allocated or zero-filled per
+    batch (every word that must start at zero is initialised by the kernels themselves)."""
+    key = ("dm", F, N, out_cap, tuple(str(e) for e in elements))
+    pool = eng._pinned
+    b = pool.get(key)
+    if b is not None:
+        return b
+    for k in [k for k in pool if isinstance(k, tuple) and k and k[0] == "dm"][2:]:
+        pool.pop(k)                                              # keep at most three shapes alive
+    dev, lib = eng.device, eng.lib
     types, cov, mass, term = _type_tables(elements)
-    max_cov = float(max(atomic_covalent_radius[str(e).upper()] for e in set(elements)))
-    with torch.cuda.device(dev):
-        d_coords = eng._dev(coords, torch.float64)
-        d_lat, shared = None, 1
-        if lattice is not None:
+    a_types, a_vdw, a_mass = _engine_types(elements)
+    mol_cap = N
+    e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)      # noqa: E731
+    nbytes = lib.pwb_dm_workspace_bytes(F, N, out_cap)
+    b = {"mol_cap": mol_cap, "n_types": len(cov),
+         "max_cov": float(max(atomic_covalent_radius[str(x).upper()] for x in set(elements))),
+         "types": eng._dev(types, torch.int32), "cov": eng._dev(cov, torch.float64), "mass": eng._dev(mass, torch.float64),
+         "term": eng._dev(term, torch.int32),
+         "a_types": eng._dev(a_types, torch.int32), "a_vdw": eng._dev(a_vdw, torch.float64), "a_mass": eng._dev(a_mass, torch.float64),
+         "n_mol": e(F, torch.int32), "mol_off": e((F, mol_cap + 1), torch.int32), "out_src": e((F, out_cap), torch.int32),
+         "out_xyz": e((F, out_cap, 3), torch.float64), "status": e(F, torch.int32),
+         "ws": e(nbytes, torch.uint8), "ws_bytes": nbytes,
+         # dense batch for the analysis kernels (worst case: every emitted atom its own molecule)
+         "item_off": e(F * out_cap + 1, torch.int32), "coords": e((F * out_cap, 3), torch.float64),
+         "dense_types": e(F * out_cap, torch.int32), "item_frame": e(F * out_cap, torch.int32),
+         "item_mol": e(F * out_cap, torch.int32), "scratch": e(2 * F + 4, torch.int32),
+         "counts": torch.zeros(4, dtype=torch.int32).pin_memory(), "d_coords": None}
+    pool[key] = b
+    return b
+
+
+def _run_dm(eng, b, d_coords, d_lat, shared, F, N, out_cap, rebuild, tol):
+    stream = ctypes.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+    _lib.check(eng.lib.pwb_discrete_molecules(
+        F, N, int(bool(rebuild)), float(tol), b["max_cov"], d_coords.data_ptr(),
+        d_lat.data_ptr() if d_lat is not None else None, shared, b["types"].data_ptr(), b["n_types"],
+        b["cov"].data_ptr(), b["mass"].data_ptr(), b["term"].data_ptr(), out_cap, b["mol_cap"], b["n_mol"].data_ptr(),
+        b["mol_off"].data_ptr(), b["out_src"].data_ptr(), b["out_xyz"].data_ptr(), b["status"].data_ptr(),
+        b["ws"].data_ptr(), b["ws_bytes"], stream))
+    return stream
+
+
+def _compact(eng, b, F, N, out_cap, stream):
+    """pwb_dm_compact: dense (item_off, coords, per-atom types, keys) + {items, atoms, largest molecule, status}."""
+    _lib.check(eng.lib.pwb_dm_compact(
+        F, N, out_cap, b["mol_cap"], b["n_mol"].data_ptr(), b["mol_off"].data_ptr(), b["out_src"].data_ptr(),
+        b["out_xyz"].data_ptr(), b["status"].data_ptr(), b["a_types"].data_ptr(), b["item_off"].data_ptr(),
+        b["coords"].data_ptr(), b["dense_types"].data_ptr(), b["item_frame"].data_ptr(), b["item_mol"].data_ptr(),
+        b["scratch"].data_ptr(), b["counts"].data_ptr(), stream))
+    return [int(v) for v in b["counts"].tolist()]
+
+
+def _check_dm_status(st):
+    if st & 1:
+        raise RuntimeError("discrete_molecules: an atom has more than 12 bonded neighbours")
+    if st & 6:
+        raise RuntimeError("discrete_molecules: output capacity exceeded")
+
+
+def _device_inputs(eng, coords, lattice):
+    d_coords = eng._dev(coords, torch.float64)
+    d_lat, shared = None, 1
+    if lattice is not None:
+        if isinstance(lattice, torch.Tensor):
+            shared = 1 if lattice.dim() == 2 else 0
+            d_lat = eng._dev(lattice.reshape(-1, 9), torch.float64)
+        else:
             lat = np.asarray(lattice, dtype=np.float64)
             shared = 1 if lat.ndim == 2 else 0
             d_lat = eng._dev(lat.reshape(-1, 9), torch.float64)
-        d_types, d_cov, d_mass, d_term = (eng._dev(types, torch.int32), eng._dev(cov, torch.float64),
-                                          eng._dev(mass, torch.float64), eng._dev(term, torch.int32))
+    return d_coords, d_lat, shared
+
+
+def discrete_molecules_batch(coords, elements, lattice=None, rebuild=False, tol=0.4, out_factor=2.0, engine=None):
+    """``coords`` [F,N,3]; ``lattice`` None | [3,3] | [F,3,3].  Returns a :class:`DiscreteBatch`."""
+    eng = engine or default_engine()
+    F, N = int(coords.shape[0]), int(coords.shape[1])
+    with torch.cuda.device(eng.device):
+        d_coords, d_lat, shared = _device_inputs(eng, coords, lattice)
         while True:
-            out_cap, mol_cap = int(max(64, out_factor * N)), N
-            n_mol = torch.zeros(F, dtype=torch.int32, device=dev)
-            mol_off = torch.zeros((F, mol_cap + 1), dtype=torch.int32, device=dev)
-            out_src = torch.zeros((F, out_cap), dtype=torch.int32, device=dev)
-            out_xyz = torch.zeros((F, out_cap, 3), dtype=torch.float64, device=dev)
-            status = torch.zeros(F, dtype=torch.int32, device=dev)
-            nbytes = lib.pwb_dm_workspace_bytes(F, N, out_cap)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(lib.pwb_discrete_molecules(
-                F, N, int(bool(rebuild)), float(tol), max_cov, d_coords.data_ptr(),
-                d_lat.data_ptr() if d_lat is not None else None, shared, d_types.data_ptr(), len(cov),
-                d_cov.data_ptr(), d_mass.data_ptr(), d_term.data_ptr(), out_cap, mol_cap, n_mol.data_ptr(),
-                mol_off.data_ptr(), out_src.data_ptr(), out_xyz.data_ptr(), status.data_ptr(), ws.data_ptr(),
-                nbytes, stream))
-            st = int(status.max().item())
-            if st & 2 and out_factor < 64:
+            out_cap = int(max(64, out_factor * N))
+            b = _dm_buffers(eng, F, N, out_cap, elements)
+            stream = _run_dm(eng, b, d_coords, d_lat, shared, F, N, out_cap, rebuild, tol)
+            counts = _compact(eng, b, F, N, out_cap, stream)
+            if counts[3] & 2 and out_factor < 64:
                 out_factor *= 2          # a flood fill outgrew the output buffer: retry larger
                 continue
-            if st & 1:
-                raise RuntimeError("discrete_molecules: an atom has more than 12 bonded neighbours")
-            if st & 6:
-                raise RuntimeError("discrete_molecules: output capacity exceeded")
-            return DiscreteBatch(n_mol.cpu().numpy(), mol_off, out_src, out_xyz, status, N)
+            _check_dm_status(counts[3])
+            return DiscreteBatch(b["n_mol"], b["mol_off"], b["out_src"], b["out_xyz"], b["status"], N, b)
 
 
-def analyse_cells(coords, elements, lattice=None, rebuild=False, tol=0.4, engine=None, **kw):
-    """Periodic pipeline kept on the device: ``discrete_molecules`` for every cell-frame, then
-    ``Molecule.full_analysis`` for every molecule found (MolecularSystem.make_modular + the per-molecule
-    loop of trajectory.py:512-522 for a whole batch of frames).
+def analyse_cells(coords, elements, lattice=None, rebuild=False, tol=0.4, engine=None, out_factor=2.0, key_arrays=False,
+                  **kw):
+    """Periodic pipeline kept on the device: ``discrete_molecules`` for every cell-frame, a native compaction of
+    the molecules found into one dense batch (``pwb_dm_compact``), then ``Molecule.full_analysis`` for every molecule
+    (MolecularSystem.make_modular + the per-molecule loop of trajectory.py:512-522 for a whole batch of frames).
+    Only ``pwb::`` kernels run between the input copy and the record copy; one 16-byte read-back tells the host how
+    many molecules there are.
 
     ``coords`` [F,N,3]; ``lattice`` None | [3,3] | [F,3,3].  Returns ``(records [M, stride] numpy,
-    keys [(frame_index, molecule_index)], sizes [M])`` in the reference's molecule order."""
+    keys [(frame_index, molecule_index)] (or the two index arrays if ``key_arrays``), sizes [M])`` in the reference's
+    molecule order."""
     eng = engine or default_engine()
-    dev = eng.device
-    res = discrete_molecules_batch(coords, elements, lattice=lattice, rebuild=rebuild, tol=tol, engine=eng)
-    F = int(coords.shape[0])
-    with torch.cuda.device(dev):
-        nm = torch.as_tensor(res.n_mol, device=dev, dtype=torch.int64)
-        mol_cap = res.mol_off.shape[1] - 1
-        out_cap = res.out_src.shape[1]
-        mmask = torch.arange(mol_cap, device=dev)[None, :] < nm[:, None]
-        starts = res.mol_off[:, :-1][mmask].to(torch.int64)
-        ends = res.mol_off[:, 1:][mmask].to(torch.int64)
-        sizes = ends - starts
-        if sizes.numel() == 0:
+    F, N = int(coords.shape[0]), int(coords.shape[1])
+    with torch.cuda.device(eng.device):
+        d_coords, d_lat, shared = _device_inputs(eng, coords, lattice)
+        while True:
+            out_cap = int(max(64, out_factor * N))
+            b = _dm_buffers(eng, F, N, out_cap, elements)
+            stream = _run_dm(eng, b, d_coords, d_lat, shared, F, N, out_cap, rebuild, tol)
+            items, atoms, biggest, st = _compact(eng, b, F, N, out_cap, stream)
+            if st & 2 and out_factor < 64:
+                out_factor *= 2
+                continue
+            _check_dm_status(st)
+            break
+        if items == 0:
             return np.zeros((0, eng.rec_stride)), [], np.zeros(0, dtype=np.int64)
-        tot = torch.gather(res.mol_off.to(torch.int64), 1, nm[:, None]).squeeze(1)
-        amask = torch.arange(out_cap, device=dev)[None, :] < tot[:, None]
-        dense_xyz = res.out_xyz[amask]
-        types, vdw, mass = _engine_types(elements)
-        dense_types = torch.as_tensor(types, device=dev)[res.out_src[amask].to(torch.int64)]
-        item_off = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=dev)
-        item_off[1:] = torch.cumsum(sizes, 0)
-        max_atoms = int(sizes.max().item())
-        out = eng.analyse(dense_xyz, item_off.to(torch.int32), dense_types, vdw, mass, shared_types=False,
-                          max_atoms=max_atoms, **kw)
-        frame_idx = torch.arange(F, device=dev)[:, None].expand(F, mol_cap)[mmask].cpu().numpy()
-        mol_idx = torch.arange(mol_cap, device=dev)[None, :].expand(F, mol_cap)[mmask].cpu().numpy()
+        out = eng.analyse(b["coords"][:atoms], b["item_off"][:items + 1], b["dense_types"][:atoms], b["a_vdw"], b["a_mass"],
+                          shared_types=False, max_atoms=biggest, **kw)
+        rec = out.host_records()
+        frame_idx = b["item_frame"][:items].cpu().numpy()
+        mol_idx = b["item_mol"][:items].cpu().numpy()
+        sizes = np.diff(b["item_off"][:items + 1].cpu().numpy())
+        if key_arrays:               # (frame index, molecule index) as two int arrays: no per-item Python objects
+            return rec, (frame_idx.astype(np.int64), mol_idx.astype(np.int64)), sizes
         keys = list(zip(frame_idx.tolist(), mol_idx.tolist()))      # python ints, without a numpy scalar per entry
-        return out.host_records(), keys, sizes.cpu().numpy()
+        return rec, keys, sizes
 
 
 def _engine_types(elements):

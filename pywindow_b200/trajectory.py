@@ -204,6 +204,50 @@ def _bounds(traj, frames):
     return (np.array([tm[f][0] for f in frames], dtype=np.int64), np.array([tm[f][1] for f in frames], dtype=np.int64))
 
 
+class RecordKeys:
+    """(frame, molecule key) of every row of a record table as two int64 arrays -- molecule key -1 stands for the
+    string key ``"0"`` of a non-modular analysis (trajectory.py:483).  Behaves like the list of tuples it replaces
+    (``len``, iteration, indexing, ``==``) without creating 1e5 tuples unless somebody iterates."""
+
+    __slots__ = ("frames", "mols")
+
+    def __init__(self, frames, mols):
+        self.frames = np.ascontiguousarray(frames, dtype=np.int64)
+        self.mols = np.ascontiguousarray(mols, dtype=np.int64)
+
+    @classmethod
+    def single(cls, frames):
+        f = np.asarray(frames, dtype=np.int64)
+        return cls(f, np.full(f.shape, -1, dtype=np.int64))
+
+    @classmethod
+    def concat(cls, parts):
+        parts = [p if isinstance(p, RecordKeys) else cls.from_pairs(p) for p in parts]
+        if not parts:
+            return cls(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+        return cls(np.concatenate([p.frames for p in parts]), np.concatenate([p.mols for p in parts]))
+
+    @classmethod
+    def from_pairs(cls, pairs):
+        pairs = list(pairs)
+        return cls([p[0] for p in pairs], [-1 if isinstance(p[1], str) else p[1] for p in pairs])
+
+    def __len__(self):
+        return int(self.frames.shape[0])
+
+    def __iter__(self):
+        return iter(zip(self.frames.tolist(), ["0" if m < 0 else m for m in self.mols.tolist()]))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return RecordKeys(self.frames[i], self.mols[i])
+        m = int(self.mols[i])
+        return (int(self.frames[i]), "0" if m < 0 else m)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 class AnalysisOutput(dict):
     """``Trajectory.analysis_output``: ``{frame: {molecule_key: properties}}`` (trajectory.py:483, :516-522).  The
     batched analysis hands over whole record tables; they are parked as blocks and only turned into per-frame
@@ -293,8 +337,8 @@ class AnalysisOutput(dict):
         """(records [M, stride] float64, keys [(frame, molecule_key)]) of everything analysed by the batched path
         and not yet looked at through the dictionary interface -- bulk post-processing without any dicts."""
         if not self._blocks:
-            return np.zeros((0, 0)), []
-        return (np.concatenate([b[0] for b in self._blocks]), [k for b in self._blocks for k in b[1]])
+            return np.zeros((0, 0)), RecordKeys.concat([])
+        return (np.concatenate([b[0] for b in self._blocks]), RecordKeys.concat([b[1] for b in self._blocks]))
 
 
 class Trajectory:
@@ -451,7 +495,7 @@ class Trajectory:
         from .engine import host_ray_capacity
         eng = default_engine()
         if not frames:
-            return np.zeros((0, eng.rec_stride)), []
+            return np.zeros((0, eng.rec_stride)), RecordKeys.single([])
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
         B = max(1, self.batch_frames)
         chunks = [frames[s:s + B] for s in range(0, len(frames), B)]
@@ -474,7 +518,7 @@ class Trajectory:
             records[done:done + len(chunks[j])] = pipe.collect(j % nslots)
             done += len(chunks[j])
         records = self._redo_overflowed(records, frames, elements, gpu_kwargs)
-        return records, [(f, "0") for f in frames]
+        return records, RecordKeys.single(frames)
 
     def _redo_overflowed(self, records, frames, elements, gpu_kwargs):
         """Frames whose ray count exceeded the trajectory-wide capacity (a molecule that grew far beyond the first
@@ -492,19 +536,21 @@ class Trajectory:
         from .periodic import analyse_cells
         eng = default_engine()
         if not frames:
-            return np.zeros((0, eng.rec_stride)), []
+            return np.zeros((0, eng.rec_stride)), RecordKeys.single([])
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
-        recs, keys = [], []
+        recs, kf, km = [], [], []
         step = max(1, min(self.batch_frames, (1 << 21) // max(1, len(elements))))
         for s in range(0, len(frames), step):
             chunk = frames[s:s + step]
             coords, lattice = self._decode_cells(chunk)
             if rebuild and lattice is None:
                 raise _TrajectoryError("rebuild=True needs periodic frames (no lattice / CRYST1 record found)")
-            r, k, _ = analyse_cells(coords, elements, lattice=lattice, rebuild=rebuild, engine=eng, **gpu_kwargs)
+            r, (fi, mi), _ = analyse_cells(coords, elements, lattice=lattice, rebuild=rebuild, engine=eng, key_arrays=True,
+                                           **gpu_kwargs)
             recs.append(r)
-            keys += [(chunk[f], m) for f, m in k]
-        return np.concatenate(recs), keys
+            kf.append(np.asarray(chunk, dtype=np.int64)[fi])
+            km.append(mi)
+        return np.concatenate(recs), RecordKeys(np.concatenate(kf), np.concatenate(km))
 
     def _decode_cells(self, frames):
         """([F,N,3] coordinates, [F,3,3] lattices | None) for the requested frames."""
