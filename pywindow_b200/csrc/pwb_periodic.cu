@@ -329,13 +329,29 @@ k_dm_bonds(DmArgs A, double max_dist) {
   dm_store_bonds(A, f, a, list, n, overflow);
 }
 
-// flood fill: one warp per frame; lane 0 walks the graph, all lanes do the O(N) steps
+// Flood fill: one warp per frame, FRONTIER-PARALLEL and order preserving.  The reference grows a molecule level by
+// level; inside a level the parents are taken in frontier order and each parent appends, first, its bonded cell
+// atoms that are still unassigned (ascending index) and then its other bonded images (ascending supercell index),
+// the first occurrence of a node winning (utilities.py:985-1044, restated in oracle/pw_periodic_oracle.py).  Every
+// candidate therefore has the order key (parent rank, pass, adjacency slot) and a node goes to the candidate with
+// the SMALLEST key.  Parents are processed 32 at a time, one per lane: the lanes enter their candidates into a small
+// shared-memory hash table node -> min key (atomicMin), the winners are compacted in key order by a warp scan and
+// marked visited before the next 32 parents run, so later parents (larger keys) see them as taken.
 constexpr int DM_FILL_WARPS = 4;
+constexpr int DM_HASH = 1024;                    // >= 32 parents x 24 candidate slots, power of two
+constexpr unsigned DM_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ unsigned dm_hash_slot(unsigned node) { return (node * 2654435761u) >> 22; }   // 10 bits
+
 __global__ void __launch_bounds__(DM_FILL_WARPS * 32)
 k_dm_fill(DmArgs A) {
-  const int lane = threadIdx.x & 31;
-  const int f = blockIdx.x * DM_FILL_WARPS + (threadIdx.x >> 5);
+  __shared__ __align__(16) unsigned h_node[DM_FILL_WARPS][DM_HASH];
+  __shared__ __align__(16) unsigned h_key[DM_FILL_WARPS][DM_HASH];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.x * DM_FILL_WARPS + wid;
   if (f >= A.F) return;
+  unsigned* hn = h_node[wid];
+  unsigned* hk = h_key[wid];
   const int N = A.N;
   const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
   const double* xr = A.xr + (size_t)f * N * 3;
@@ -367,7 +383,26 @@ k_dm_fill(DmArgs A) {
     sd[a] = A.type_terminal[A.atom_type[a]] ? PWB_INF : sqrt(fmax(d2, 0.0));     // terminal atoms never seed
   }
   for (int w = lane; w < vis_words; w += 32) vis[w] = 0u;
+  const uint4 empty4 = make_uint4(DM_EMPTY, DM_EMPTY, DM_EMPTY, DM_EMPTY);
+  for (int t = lane; t < DM_HASH / 4; t += 32) { ((uint4*)hn)[t] = empty4; ((uint4*)hk)[t] = empty4; }
   __syncwarp();
+  // candidate (pass, slot e) of parent node p -> node id, or -1
+  auto candidate = [&](int a, int sa, int sb, int sc, unsigned k, int pass) -> int {
+    const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
+    int node;
+    bool central;
+    if (A.rebuild) {
+      const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
+      if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) return -1;
+      const int im = (ma + 1) * 9 + (mb + 1) * 3 + (mc + 1);
+      node = im * N + b;
+      central = im == 13;
+    } else { node = b; central = true; }
+    const bool cellpath = central && rem[b];
+    if ((pass == 0) != cellpath) return -1;          // pass 0: remaining cell atoms; pass 1: the rest
+    if (vis[node >> 5] & (1u << (node & 31))) return -1;
+    return node;
+  };
   while (true) {
     // ---- seed: remaining non-terminal atom closest to the pseudo origin, first arg-min
     ValIdx best; best.v = PWB_INF; best.i = 0x7fffffff;
@@ -380,56 +415,103 @@ k_dm_fill(DmArgs A) {
     if (best.i == 0x7fffffff) break;
     const int start = nout;
     int overflow = 0;
-    if (lane == 0) {
-      int* cur = fr0; int* nxt = fr1;
-      int ncur = 1, seed = cimg * N + best.i;
-      cur[0] = seed;
-      vis[seed >> 5] |= 1u << (seed & 31);
-      while (ncur > 0) {
-        int nn = 0;
-        for (int q = 0; q < ncur; q++) {
+    int* cur = fr0; int* nxt = fr1;
+    int ncur = 1;
+    {
+      const int seed = cimg * N + best.i;
+      if (lane == 0) { cur[0] = seed; vis[seed >> 5] |= 1u << (seed & 31); }
+    }
+    __syncwarp();
+    while (ncur > 0) {
+      // the level's nodes leave the frontier in order
+      for (int q = lane; q < ncur; q += 32) { if (nout + q < A.out_cap) osrc[nout + q] = cur[q]; else overflow = 1; }
+      nout += ncur;
+      int nn = 0;
+      const int npass = A.rebuild ? 2 : 1;
+      for (int q0 = 0; q0 < ncur; q0 += 32) {
+        const int q = q0 + lane;
+        int a = 0, sa = 0, sb = 0, sc = 0, dg = 0;
+        if (q < ncur) {
           const int p = cur[q];
-          const int a = p % N, img = p / N;
-          if (nout < A.out_cap) osrc[nout] = p; else overflow = 1;   // node id for now; resolved below
-          nout++;
-          if (A.type_terminal[A.atom_type[a]]) continue;
-          int sa = 0, sb = 0, sc = 0;
+          a = p % N;
+          const int img = p / N;
           if (A.rebuild) { sa = img / 9 - 1; sb = (img / 3) % 3 - 1; sc = img % 3 - 1; }
-          const int dg = deg[a];
-          for (int pass = 0; pass < (A.rebuild ? 2 : 1); pass++) {
-            for (int e = 0; e < dg; e++) {
-              const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
-              const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
-              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
-              int node;
-              bool central;
-              if (A.rebuild) {
-                if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) continue;
-                const int im = (ma + 1) * 9 + (mb + 1) * 3 + (mc + 1);
-                node = im * N + b;
-                central = im == 13;
-              } else { node = b; central = true; }
-              const bool cellpath = central && rem[b];
-              if ((pass == 0) != cellpath) continue;     // pass 0: remaining cell atoms; pass 1: the rest
-              const unsigned bit = 1u << (node & 31);
-              if (vis[node >> 5] & bit) continue;
-              vis[node >> 5] |= bit;
-              if (nn < A.out_cap) nxt[nn] = node; else overflow = 1;
-              nn++;
+          dg = A.type_terminal[A.atom_type[a]] ? 0 : deg[a];
+        }
+        // 1. enter the candidates: node -> smallest key (lane, pass, slot)
+        for (int pass = 0; pass < npass; pass++)
+          for (int e = 0; e < dg; e++) {
+            const int node = candidate(a, sa, sb, sc, adj[(size_t)a * DM_ADJ_CAP + e], pass);
+            if (node < 0) continue;
+            const unsigned key = (unsigned)(lane * 24 + pass * 12 + e);
+            unsigned h = dm_hash_slot((unsigned)node);
+            while (true) {
+              const unsigned old = atomicCAS(&hn[h], DM_EMPTY, (unsigned)node);
+              if (old == DM_EMPTY || old == (unsigned)node) { atomicMin(&hk[h], key); break; }
+              h = (h + 1) & (DM_HASH - 1);
             }
           }
-        }
-        for (int q = 0; q < ncur; q++) {
-          const int p = cur[q];
-          if (p / N == cimg) rem[p % N] = 0;
-        }
-        int* t = cur; cur = nxt; nxt = t;
-        ncur = min(nn, A.out_cap);
+        __syncwarp();
+        // 2. winners per lane, in slot order
+        unsigned keep = 0;
+        for (int pass = 0; pass < npass; pass++)
+          for (int e = 0; e < dg; e++) {
+            const int node = candidate(a, sa, sb, sc, adj[(size_t)a * DM_ADJ_CAP + e], pass);
+            if (node < 0) continue;
+            const unsigned key = (unsigned)(lane * 24 + pass * 12 + e);
+            unsigned h = dm_hash_slot((unsigned)node);
+            while (hn[h] != (unsigned)node) h = (h + 1) & (DM_HASH - 1);
+            if (hk[h] == key) keep |= 1u << (pass * 12 + e);
+          }
+        // 3. ordered compaction into the next frontier
+        int cnt = __popc(keep), inc = cnt;
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        int pos = nn + inc - cnt;
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        __syncwarp();
+        for (int pass = 0; pass < npass; pass++)
+          for (int e = 0; e < dg; e++) {
+            if (!(keep & (1u << (pass * 12 + e)))) continue;
+            const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
+            const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
+            int node = b;
+            if (A.rebuild) {
+              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
+              node = ((ma + 1) * 9 + (mb + 1) * 3 + (mc + 1)) * N + b;
+            }
+            if (pos < A.out_cap) nxt[pos] = node; else overflow = 1;
+            pos++;
+          }
+        __syncwarp();
+        // 4. mark the winners visited and wipe the table entries this chunk used
+        for (int pass = 0; pass < npass; pass++)
+          for (int e = 0; e < dg; e++) {
+            const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
+            const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
+            int node = b;
+            if (A.rebuild) {
+              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
+              if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) continue;
+              node = ((ma + 1) * 9 + (mb + 1) * 3 + (mc + 1)) * N + b;
+            }
+            if (keep & (1u << (pass * 12 + e))) atomicOr(&vis[node >> 5], 1u << (node & 31));
+          }
+        nn += total;
+        __syncwarp();
+        if (total) for (int t = lane; t < DM_HASH / 4; t += 32) { ((uint4*)hn)[t] = empty4; ((uint4*)hk)[t] = empty4; }
+        __syncwarp();
       }
+      // the level is done: its cell atoms are assigned now (utilities.py:1040-1044)
+      for (int q = lane; q < ncur; q += 32) {
+        const int p = cur[q];
+        if (p / N == cimg) rem[p % N] = 0;
+      }
+      __syncwarp();
+      int* t = cur; cur = nxt; nxt = t;
+      ncur = min(nn, A.out_cap);
+      if (nn > A.out_cap) overflow = 1;
     }
-    nout = __shfl_sync(0xffffffffu, nout, 0);
-    overflow = __shfl_sync(0xffffffffu, overflow, 0);
-    __syncwarp();
+    overflow = __any_sync(0xffffffffu, overflow);
     if (overflow || nout > A.out_cap) { st |= 2; break; }
     // ---- resolve nodes to (source atom, coordinates); centre of mass for the filter
     double mx = 0, my = 0, mz = 0, mt = 0;
@@ -451,16 +533,16 @@ k_dm_fill(DmArgs A) {
       mx += X * m; my += Y * m; mz += Z * m; mt += m;
     }
     mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz); mt = warp_sum(mt);
-    bool keep = true;
+    bool keepmol = true;
     if (A.rebuild) {   // utilities.py:1062-1077
       double cx = mx / mt, cy = my / mt, cz = mz / mt;
       double f0 = round8(fd[9] * cx + fd[10] * cy + fd[11] * cz);
       double f1 = round8(fd[12] * cx + fd[13] * cy + fd[14] * cz);
       double f2 = round8(fd[15] * cx + fd[16] * cy + fd[17] * cz);
       const double lo = fd[24], hi = fd[25];
-      keep = f0 >= lo && f0 < hi && f1 >= lo && f1 < hi && f2 >= lo && f2 < hi;
+      keepmol = f0 >= lo && f0 < hi && f1 >= lo && f1 < hi && f2 >= lo && f2 < hi;
     }
-    if (keep) {
+    if (keepmol) {
       if (nmol >= A.mol_cap) { st |= 4; break; }
       nmol++;
       if (lane == 0) moff[nmol] = nout;
