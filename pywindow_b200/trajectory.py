@@ -539,7 +539,9 @@ class Trajectory:
             return np.zeros((0, eng.rec_stride)), RecordKeys.single([])
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
         recs, kf, km = [], [], []
-        step = max(1, min(self.batch_frames, (1 << 21) // max(1, len(elements))))
+        # cells per batch: the flood fill runs one warp per cell and is bound by memory latency, so it wants
+        # thousands of cells in flight (8 192 PUDXES cells: 264 MB of coordinates, ~3 GB of pooled workspace)
+        step = max(1, min(8192, (1 << 24) // max(1, len(elements))))
         for s in range(0, len(frames), step):
             chunk = frames[s:s + step]
             coords, lattice = self._decode_cells(chunk)
