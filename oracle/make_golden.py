@@ -24,6 +24,13 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 NAN8 = np.full(8, np.nan)
 
 
+def writer_system(g):
+    """The system both writers are given in the writer fixtures / tests."""
+    keys = np.array([e + str(i % 7) for i, e in enumerate(g["elements"])])
+    return {"elements": g["elements"].copy(), "atom_ids": keys, "coordinates": g["coords"] * 3.7 - 11.0,
+            "unit_cell": np.array([24.8, 25.1, 26.0, 90.0, 95.5, 101.25])}
+
+
 def versions():
     import scipy
     import sklearn
@@ -181,6 +188,16 @@ def main():
     for nm, fn, sd in (("pudxes_noise1", "PUDXES_no_solvent.pdb", 20261017), ("pudxes_noise2", "PUDXES_no_solvent.pdb", 20261018),
                        ("epirur_noise", "EPIRUR_no_solvent.pdb", 20261019)):
         jobs.append(("per_" + nm, lambda nm=nm, fn=fn, sd=sd: periodic(pw, "per_" + nm, os.path.join(inp, fn), noise_seed=sd)))
+
+    def writers():
+        """Files written by the reference's Output (io_tools.py:349-493) for a fixed system: tests/golden/writer_ref.*"""
+        from pywindow._internal.io_tools import Output
+        g = np.load(os.path.join(OUT, "md_frame00.npz"))
+        system = writer_system(g)
+        for ext, kw in (("pdb", dict(atom_ids_key="atom_ids", remarks=["first", "second"], space_group="P21")),
+                        ("xyz", dict(atom_ids_key="elements", remarks=["a", "b"]))):
+            Output().dump2file(system, os.path.join(OUT, "writer_ref." + ext), override=True, **kw)
+    jobs.append(("writers", writers))
 
     for name, job in jobs:
         if a.only is None or a.only in name:

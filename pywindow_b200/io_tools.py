@@ -115,7 +115,6 @@ class Output:
 
     def __init__(self):
         self.cwd = pathlib.Path.cwd()
-        self._writers = {".xyz": self._save_xyz, ".pdb": self._save_pdb}
 
     def dump2json(self, obj, filepath, default=None, override=False, **kwargs):  # noqa: FBT002
         if not isinstance(obj, dict):
@@ -129,29 +128,68 @@ class Output:
         with filepath.open("w+") as fh:
             json.dump(obj, fh, default=default, **kwargs)
 
-    def dump2file(self, obj, filepath, override=False, **kwargs):  # noqa: FBT002
+    def dump2file(self, obj, filepath, atom_ids_key="elements", override=False, **kwargs):  # noqa: FBT002
+        """io_tools.py:267-347: XYZ or PDB by extension; kwargs as in the reference (elements_key, coordinates_key,
+        remarks, cryst, space_group, forcefield, decipher, resname, chainid, resseq)."""
         filepath = pathlib.Path(filepath)
         if not override and filepath.is_file():
             raise FileExistsError(f"The file {filepath} already exists. Use a different filepath, or set "
                                   "the 'override' kwarg to True.")
-        if filepath.suffix not in self._writers:
-            raise _FileTypeError(f"The {filepath.suffix!r} file extension is not supported for dumping (xyz, pdb).")
-        self._writers[filepath.suffix](obj, filepath, **kwargs)
+        if filepath.suffix == ".pdb":
+            self._save_pdb(obj, filepath, atom_ids_key=atom_ids_key, **kwargs)
+        elif filepath.suffix == ".xyz":
+            for k in ("cryst", "space_group", "resname", "chainid", "resseq"):
+                kwargs.pop(k, None)
+            self._save_xyz(obj, filepath, **kwargs)
+        else:
+            raise _FileTypeError(f"The {filepath.suffix} file extension is not supported for dumping a MolecularSystem "
+                                 "or a Molecule. Please use XYZ or PDB.")
 
-    def _save_xyz(self, system, filepath, atom_ids_key="elements", remark=None, **kwargs):  # noqa: ARG002
-        ids, xyz = system[atom_ids_key], system["coordinates"]
-        lines = [f"{len(ids)}", "" if remark is None else str(remark)]
-        lines += [f"{a:<5}{c[0]:>10.4f}{c[1]:>10.4f}{c[2]:>10.4f}" for a, c in zip(ids, xyz)]
-        filepath.write_text("\n".join(lines) + "\n")
+    @staticmethod
+    def _elements(system, key, forcefield, decipher):
+        el = system[key]
+        if decipher is True:
+            if forcefield is None:
+                raise ValueError("forcefield must be provided when decipher is True")
+            from .utilities import decipher_atom_key
+            el = np.array([decipher_atom_key(k, forcefield=forcefield) for k in el])
+        return el
 
-    def _save_pdb(self, system, filepath, atom_ids_key="elements", forcefield=None, **kwargs):  # noqa: ARG002
-        out = []
-        if "unit_cell" in system and len(system["unit_cell"]) == 6:
-            c = system["unit_cell"]
-            out.append(f"CRYST1{c[0]:9.3f}{c[1]:9.3f}{c[2]:9.3f}{c[3]:7.2f}{c[4]:7.2f}{c[5]:7.2f}")
+    def _save_xyz(self, system, filepath, elements_key="elements", coordinates_key="coordinates", remarks=None,
+                  forcefield=None, decipher=False):  # noqa: FBT002
+        """Byte-for-byte the file of io_tools.py:349-383: count, remark line, ``El x y z`` with two decimals."""
+        if isinstance(remarks, (list, tuple)):
+            remarks = ";".join(remarks)
+        elif remarks is None:
+            remarks = ""
+        el = self._elements(system, elements_key, forcefield, decipher)
+        body = "".join("{} {:.2f} {:.2f} {:.2f}\n".format(e, *c) for e, c in zip(el, system[coordinates_key]))
+        pathlib.Path(filepath).write_text(f"{len(el):0d}\n{remarks!s}\n" + body)
+
+    def _save_pdb(self, system, filepath, atom_ids_key="elements", elements_key="elements", coordinates_key="coordinates",
+                  remarks=None, cryst="unit_cell", space_group=None, forcefield=None, decipher=False, resname="MOL",  # noqa: FBT002
+                  chainid="A", resseq=1):
+        """Byte-for-byte the file of io_tools.py:385-493: generator remark, optional remarks, CRYST1 (P1 unless a
+        space group is given), one ATOM record per atom (serial, centred 4-character name, residue, chain, sequence
+        number, 8.3f coordinates, right-justified element), END without a trailing newline."""
+        filepath = pathlib.Path(filepath)
+        lines = ["REMARK File generated using pyWINDOW."]
+        if isinstance(remarks, (list, tuple)):
+            lines += [f"REMARK {r}" for r in remarks]
+        elif isinstance(remarks, (str, int, float)):
+            lines.append(f"REMARK {remarks}")
+        if cryst in system and np.asarray(system[cryst]).any():
+            c = system[cryst]
+            lines.append("CRYST1" + "".join(f"{v:9.3f}" for v in c[:3]) + "".join(f"{v:7.2f}" for v in c[3:])
+                         + " " + ("P1" if space_group is None else space_group))
         ids = system[atom_ids_key]
-        for i, (a, e, c) in enumerate(zip(ids, system["elements"], system["coordinates"]), start=1):
-            out.append(f"{'HETATM':<6}{i % 100000:>5} {str(a):<4} {'MOL':<3} {'A'}{1:>4}    "
-                       f"{c[0]:>8.3f}{c[1]:>8.3f}{c[2]:>8.3f}{1.0:>6.2f}{0.0:>6.2f}          {str(e):>2}")
-        out.append("END")
-        filepath.write_text("\n".join(out) + "\n")
+        el = self._elements(system, elements_key, forcefield, decipher)
+        xyz = system[coordinates_key]
+        seq = str(resseq).rjust(4)
+        for i in range(len(list(ids))):
+            lines.append(f"ATOM  {i + 1:5d} {ids[i].center(4):4} {resname:3} {chainid}{seq}    "
+                         f"{xyz[i][0]:8.3f}{xyz[i][1]:8.3f}{xyz[i][2]:8.3f}{' ' * 22}{el[i].rjust(2):2}  ")
+        lines.append("END")
+        if filepath.suffix != ".pdb":
+            filepath = pathlib.Path(f"{filepath}.pdb")
+        filepath.write_text("\n".join(lines))

@@ -92,3 +92,51 @@ def test_xyz_trajectory_decode_against_reference(ref, tmp_path):
         np.testing.assert_array_equal(native[f], np.asarray(ra["coordinates"], dtype=np.float64))
         rb = b.get_frames(f)[f].system
         assert list(rb["atom_ids"]) == list(ra["atom_ids"])      # the reference keeps XYZ symbols as atom_ids
+
+
+def test_writers_are_byte_identical(ref, tmp_path):
+    """Output._save_pdb / _save_xyz / dump2file and Molecule.dump_molecule(include_coms=True) against the
+    reference's writers (io_tools.py:267-493, molecular.py:419-545): same bytes for the same system."""
+    pw, U = ref
+    import pywindow_b200 as mine
+    from pywindow._internal.io_tools import Output as RefOutput
+    from pywindow_b200.io_tools import Output
+    g = load_golden("md_frame00")
+    rng = np.random.default_rng(4)
+    keys = np.array([e + str(i % 7) for i, e in enumerate(g["elements"])])
+    system = {"elements": g["elements"].copy(), "atom_ids": keys, "coordinates": g["coords"] * 3.7 - 11.0,
+              "unit_cell": np.array([24.8, 25.1, 26.0, 90.0, 95.5, 101.25])}
+    cases = [dict(atom_ids_key="elements"), dict(atom_ids_key="atom_ids", remarks=["first", "second"], space_group="P21"),
+             dict(atom_ids_key="atom_ids", remarks="one line", resname="CC3", chainid="B", resseq=12, cryst="nothing"),
+             dict(atom_ids_key="elements", elements_key="atom_ids", decipher=True, forcefield="DLF", remarks=3.5)]
+    for k, kw in enumerate(cases):
+        a, b = tmp_path / f"ref{k}.pdb", tmp_path / f"mine{k}.pdb"
+        RefOutput().dump2file(copy.deepcopy(system), a, **kw)
+        Output().dump2file(copy.deepcopy(system), b, **kw)
+        assert a.read_bytes() == b.read_bytes(), kw
+    for k, kw in enumerate([dict(), dict(remarks=["a", "b"]), dict(remarks="r", elements_key="atom_ids", decipher=True, forcefield="DLF")]):
+        a, b = tmp_path / f"ref{k}.xyz", tmp_path / f"mine{k}.xyz"
+        RefOutput().dump2file(copy.deepcopy(system), a, atom_ids_key="elements", **kw)
+        Output().dump2file(copy.deepcopy(system), b, atom_ids_key="elements", **kw)
+        assert a.read_bytes() == b.read_bytes(), kw
+    with pytest.raises(FileExistsError):
+        Output().dump2file(system, tmp_path / "mine0.pdb", atom_ids_key="elements")
+    # overlay of COM (He), optimised pore centre (Ne) and window centres (Ar1..) -- properties injected, no GPU
+    props = {"centre_of_mass": rng.normal(size=3), "pore_diameter_opt": {"centre_of_mass": rng.normal(size=3)},
+             "windows": {"centre_of_mass": rng.normal(size=(4, 3)) * 5}}
+    for with_ids in (True, False):
+        mol = {"elements": system["elements"].copy(), "coordinates": system["coordinates"].copy()}
+        if with_ids:
+            mol["atom_ids"] = keys.copy()
+        ra = pw.Molecule(copy.deepcopy(mol), "sys", 0)
+        rb = mine.Molecule(copy.deepcopy(mol), "sys", 0)
+        ra.properties.update(copy.deepcopy(props))
+        rb.properties.update(copy.deepcopy(props))
+        a, b = tmp_path / f"ref_coms{with_ids}.pdb", tmp_path / f"mine_coms{with_ids}.pdb"
+        ra.dump_molecule(a, include_coms=True)
+        rb.dump_molecule(b, include_coms=True)
+        assert a.read_bytes() == b.read_bytes()
+        a2, b2 = tmp_path / f"ref_plain{with_ids}.pdb", tmp_path / f"mine_plain{with_ids}.pdb"
+        ra.dump_molecule(a2)
+        rb.dump_molecule(b2)
+        assert a2.read_bytes() == b2.read_bytes()

@@ -304,3 +304,18 @@ def test_analysis_output_is_a_lazy_dict():
     assert out.get(11)["0"]["no_of_atoms"] == 1 and out.get(12) is None
     text = json.dumps({str(f): {str(k): v for k, v in dict(m.items()).items()} for f, m in out.items()}, default=U.to_list)
     assert json.loads(text)["7"]["0"]["windows"]["diameters"] is None
+
+
+def test_writers_reproduce_the_reference_files(tmp_path):
+    """Output.dump2file against files written by the reference's Output for the same system (tests/golden/writer_ref.*,
+    oracle/make_golden.py --only writers): byte identical (io_tools.py:349-493)."""
+    from pywindow_b200.io_tools import Output
+    g = load_golden("md_frame00")
+    keys = np.array([e + str(i % 7) for i, e in enumerate(g["elements"])])
+    system = {"elements": g["elements"].copy(), "atom_ids": keys, "coordinates": g["coords"] * 3.7 - 11.0,
+              "unit_cell": np.array([24.8, 25.1, 26.0, 90.0, 95.5, 101.25])}
+    gold = os.path.join(ROOT, "tests", "golden")
+    Output().dump2file(system, tmp_path / "w.pdb", atom_ids_key="atom_ids", remarks=["first", "second"], space_group="P21")
+    assert (tmp_path / "w.pdb").read_bytes() == open(os.path.join(gold, "writer_ref.pdb"), "rb").read()
+    Output().dump2file(system, tmp_path / "w.xyz", atom_ids_key="elements", remarks=["a", "b"])
+    assert (tmp_path / "w.xyz").read_bytes() == open(os.path.join(gold, "writer_ref.xyz"), "rb").read()
