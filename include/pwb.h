@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PWB_ABI_VERSION 2
+#define PWB_ABI_VERSION 3
 #define PWB_MAX_TYPES 16
 
 /* ---- result record: `rec_stride` doubles per item (>= PWB_REC_WIN0 + 4*win_cap) --------------- */
@@ -107,7 +107,14 @@ typedef struct pwb_batch {
   double* records;           /* [F][rec_stride]                                                   */
   void* workspace;           /* pwb_workspace_bytes() bytes                                       */
   size_t workspace_bytes;
+  /* Ray sharding of ONE huge item over several GPUs (BASELINE config 5, >= 1e5 rays): pwb_ray_search only
+   * analyses the ray tiles [ray_tile_begin, ray_tile_end) (tiles of PWB_RAY_TILE = 1024 consecutive rays of the
+   * golden spiral, utilities.py:1441-1470) and leaves that range's clear rays packed at the front of the lists;
+   * the caller gathers the ranges of all GPUs in rank order, writes the merged lists and counts back and runs
+   * pwb_cluster / pwb_window_refine on them.  0, 0 = every tile (single GPU).                               */
+  int32_t ray_tile_begin, ray_tile_end;
 } pwb_batch;
+#define PWB_RAY_TILE 1024
 
 /* layout of the per-item lists inside the workspace, for stage-wise tests */
 typedef struct pwb_ws_layout {

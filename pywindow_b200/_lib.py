@@ -20,6 +20,7 @@ REC_NRAYS, REC_NCLEAR, REC_NWIN, REC_EPS, REC_OPT_NIT, REC_OPT_STOP, REC_RADIUS,
 REC_OPT_NFEV = 24
 REC_WIN0 = 28
 ST_OPT_BOUNDS, ST_NO_CLEAR_RAY, ST_RAY_CAP, ST_WIN_CAP, ST_WIN_DROPPED, ST_WIN_NEGATIVE, ST_BAD_ITEM = 1, 2, 4, 8, 16, 32, 64
+RAY_TILE = 1024
 STAGE_SCALARS, STAGE_AVGD, STAGE_OPT, STAGE_RAYS, STAGE_CLUSTER, STAGE_WINDOWS, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
 
 EXPORTS = [
@@ -43,6 +44,7 @@ class Batch(ctypes.Structure):
         ("type_vdw", ctypes.c_void_p), ("type_mass", ctypes.c_void_p), ("centre_override", ctypes.c_void_p),
         ("opt_start", ctypes.c_void_p), ("opt_bounds", ctypes.c_void_p),
         ("records", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("ray_tile_begin", ctypes.c_int32), ("ray_tile_end", ctypes.c_int32),
     ]
 
 
@@ -110,7 +112,7 @@ def load():
     L.pwb_fma_peak.restype = ci
     L.pwb_launch_count.argtypes = [vp]
     L.pwb_launch_count.restype = ctypes.c_longlong
-    if L.pwb_abi_version() != 2:
+    if L.pwb_abi_version() != 3:
         raise PwbLibraryError("libpwb.so ABI version mismatch")
     _lib = L
     return L

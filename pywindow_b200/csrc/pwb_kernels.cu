@@ -505,7 +505,7 @@ k_opt_pore(pwb_batch b, Ws ws) {
 // k_rays
 // =================================================================================================
 constexpr int RAY_THREADS = 256;
-constexpr int RAY_TILE = 1024;   // rays per pass (4 per thread, register tiled)
+constexpr int RAY_TILE = PWB_RAY_TILE;   // rays per pass (4 per thread, register tiled)
 constexpr int RAY_RPT = RAY_TILE / RAY_THREADS;
 constexpr int RAY_ACAP = RAY_TILE;   // 2*min clearance of the survivors of one tile
 
@@ -645,10 +645,14 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   // RAY_TILE of them) and, when an item has more than one tile, packed in tile order afterwards -- by
   // whichever CTA of the item finishes last -- so the lists stay sorted by ray index whatever gridDim.y is.
   const int ntiles = (P + RAY_TILE - 1) / RAY_TILE;
-  const bool solo = gridDim.y == 1 && ntiles == 1;
+  // ray sharding over GPUs (pwb_batch.ray_tile_begin/end): only the tiles [tb, te) of this item are analysed here
+  const bool sharded = b.ray_tile_end > 0;
+  const int tb = sharded ? min(b.ray_tile_begin, ntiles) : 0, te = sharded ? min(b.ray_tile_end, ntiles) : ntiles;
+  const int Pend = min(P, te * RAY_TILE);
+  const bool solo = gridDim.y == 1 && ntiles == 1 && !sharded;
   int* tile_cnt = ws.labels + (size_t)item * b.ray_cap;      // [ntiles] clear rays, [ntiles] survivors (free until k_cluster)
   int n_clear = 0, n_surv_total = 0;
-  for (int base = blockIdx.y * RAY_TILE; base < P; base += gridDim.y * RAY_TILE) {
+  for (int base = (tb + blockIdx.y) * RAY_TILE; base < Pend; base += gridDim.y * RAY_TILE) {
     n_clear = 0;
     // ---- pre-test (utilities.py:1132-1161), RAY_RPT consecutive rays per thread, branch free:
     // atom i counts iff r_i^2 - d_i^2 > 0 (d_i about the line through the centroid o) and
@@ -785,7 +789,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     if (!s_last) return;
     __threadfence();
     n_clear = 0; n_surv_total = 0;
-    for (int t = 0; t < ntiles; t++) {
+    for (int t = tb; t < te; t++) {
       const int c = __ldcg(&tile_cnt[t]), src = t * RAY_TILE;
       n_surv_total += __ldcg(&tile_cnt[ntiles + t]);
       if (src != n_clear) {
@@ -804,7 +808,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   if (tid == 0) {
     iiv[I_NCLEAR] = n_clear; iiv[I_NSURV] = n_surv_total;
     rec[PWB_REC_NCLEAR] = n_clear; rec[PWB_REC_NSURV] = n_surv_total;
-    if (n_clear == 0) { iiv[I_STATUS] |= PWB_ST_NO_CLEAR_RAY; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
+    if (n_clear == 0 && !sharded) { iiv[I_STATUS] |= PWB_ST_NO_CLEAR_RAY; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
   }
 }
 
@@ -1729,6 +1733,9 @@ static int resolve(const pwb_batch* b, Ws* w) {
 
 static int check(const pwb_batch* b) {
   if (b->n_items <= 0) { snprintf(g_err, sizeof g_err, "n_items must be positive"); return 1; }
+  if (b->ray_tile_end < 0 || b->ray_tile_begin < 0 || (b->ray_tile_end > 0 && b->ray_tile_begin > b->ray_tile_end)) {
+    snprintf(g_err, sizeof g_err, "bad ray tile range"); return 1;
+  }
   if (b->n_types < 1 || b->n_types > PWB_MAX_TYPES) { snprintf(g_err, sizeof g_err, "n_types out of range"); return 1; }
   if (b->rec_stride < PWB_REC_WIN0 + 4 * b->win_cap) { snprintf(g_err, sizeof g_err, "rec_stride too small"); return 1; }
   if (b->ray_cap > (1 << 22)) { snprintf(g_err, sizeof g_err, "ray_cap > 4M rays not supported"); return 1; }

@@ -79,6 +79,10 @@ class BatchResult:
     def item_d(self):
         return self._view(self._layout.item_d, torch.float64, (self.n_items, 16))
 
+    @property
+    def item_i(self):
+        return self._view(self._layout.item_i, torch.int32, (self.n_items, 32))
+
     def host_records(self):
         return self.records.cpu().numpy()
 
@@ -187,7 +191,76 @@ class Engine:
             _lib.check(self.lib.pwb_full_analysis_batch(self._ctx, ctypes.byref(b), stream))
             res = BatchResult(rec, ws, layout, F, total, b.ray_cap, self.win_cap)
             res._keep = (coords, item_off, atom_type, type_vdw, type_mass, centre_override, opt_start, opt_bounds)
+            res._batch, res._stream = b, stream          # the descriptor, for stage-wise re-runs on the same workspace
             return res
+
+    def analyse_ray_sharded(self, elements, coords, *, adjust=1.0, increment=1.0, increment2=0.1, pore_opt=True,
+                            centre_override=None, stages=_lib.STAGE_ALL):
+        """ONE molecule with a dense ray set (BASELINE config 5: adjust ~ 100 -> ~1e5 rays), its rays sharded over
+        the ranks of the initialised ``torch.distributed`` group: every rank runs the cheap scalar /
+        pore-centre stages on the replicated molecule, analyses only its own contiguous range of ray tiles
+        (pre-test + path clearance are independent per ray, utilities.py:1441-1470), the clear-ray lists are
+        all-gathered in rank order (= ascending ray index: 16 B per clear ray over NCCL / NVLink), and DBSCAN + window
+        refinement run on the merged list on every rank, so all ranks return the same record.  Collective: every
+        rank must call it with the same arguments.  With one rank it is ``analyse_molecules`` on one item."""
+        import torch.distributed as dist
+        from .distributed import world
+        rank, size = world()
+        el = list(elements)
+        X = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, 3)
+        kw = dict(adjust=adjust, increment=increment, increment2=increment2, pore_opt=pore_opt)
+        if centre_override is not None:
+            kw["centre_override"] = np.asarray(centre_override, dtype=np.float64).reshape(1, 3)
+        if size == 1:
+            return self.analyse_molecules([(el, X)], stages=stages, **kw)
+        pre = stages & (_lib.STAGE_SCALARS | _lib.STAGE_AVGD | _lib.STAGE_OPT)
+        res = self.analyse_molecules([(el, X)], stages=pre | _lib.STAGE_SCALARS, **kw)
+        if not stages & _lib.STAGE_RAYS:
+            return res
+        b, stream = res._batch, res._stream
+        with torch.cuda.device(self.device):
+            # window rays: P = int(log10(4 pi R^2) 250 adjust), R = max_dim / 2 (utilities.py:1398-1409); the tile
+            # ranges only have to PARTITION the tiles (the kernel clamps them to its own P), so a host-side P that is
+            # off by one at an integer boundary is harmless: the last rank's range is open ended
+            D = float(res.records[0, _lib.REC_MAXD].item())
+            P = max(2, int(np.log10(4.0 * np.pi * (D / 2) ** 2) * 250.0 * float(adjust)))
+            tiles = -(-P // _lib.RAY_TILE)
+            per = -(-tiles // size)
+            b.stages = _lib.STAGE_RAYS
+            b.ray_tile_begin = rank * per
+            b.ray_tile_end = (rank + 1) * per if rank + 1 < size else (1 << 20)
+            _lib.check(self.lib.pwb_full_analysis_batch(self._ctx, ctypes.byref(b), stream))
+            ii = res.item_i
+            mine = ii[0, 2:4].clone()                                   # I_NSURV, I_NCLEAR of this rank's range
+            counts = [torch.zeros_like(mine) for _ in range(size)]
+            dist.all_gather(counts, mine)
+            counts = torch.stack(counts).cpu().numpy()
+            n_each, n_clear, n_surv = counts[:, 1], int(counts[:, 1].sum()), int(counts[:, 0].sum())
+            kmax = int(n_each.max())
+            if kmax:
+                # one payload row per clear ray: ray index, arg-min step, 2*min clearance
+                pay = torch.zeros((kmax, 3), dtype=torch.float64, device=self.device)
+                n = int(n_each[rank])
+                pay[:n, 0] = res.clear_k[0, :n].to(torch.float64)
+                pay[:n, 1] = res.clear_pos[0, :n].to(torch.float64)
+                pay[:n, 2] = res.clear_a2[0, :n]
+                out = torch.empty((size * kmax, 3), dtype=torch.float64, device=self.device)
+                dist.all_gather_into_tensor(out, pay)
+                out = out.view(size, kmax, 3)
+                merged = torch.cat([out[r, :int(n_each[r])] for r in range(size)])
+                res.clear_k[0, :n_clear] = merged[:, 0].to(torch.int32)
+                res.clear_pos[0, :n_clear] = merged[:, 1].to(torch.int32)
+                res.clear_a2[0, :n_clear] = merged[:, 2]
+            ii[0, 2], ii[0, 3] = n_surv, n_clear
+            res.records[0, _lib.REC_NCLEAR], res.records[0, _lib.REC_NSURV] = float(n_clear), float(n_surv)
+            if n_clear == 0:
+                ii[0, 0] |= _lib.ST_NO_CLEAR_RAY
+                res.records[0, _lib.REC_STATUS] = float(int(ii[0, 0]))
+            b.ray_tile_begin = b.ray_tile_end = 0
+            b.stages = stages & (_lib.STAGE_CLUSTER | _lib.STAGE_WINDOWS)
+            if b.stages:
+                _lib.check(self.lib.pwb_full_analysis_batch(self._ctx, ctypes.byref(b), stream))
+        return res
 
     def analyse_frames(self, coords, elements, **kw):
         """``coords``: [F, N, 3] (numpy or torch), one molecule with atom order ``elements``."""

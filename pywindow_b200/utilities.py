@@ -136,11 +136,14 @@ def find_average_diameter(elements, coordinates, adjust=1, processes=None):  # n
 
 
 def find_windows(elements, coordinates, processes=None, adjust=1, pore_opt=True, increment=1.0,  # noqa: ARG001
-                 pore_centre=None):
+                 pore_centre=None, shard_rays=None):
     """utilities.py:1364-1553 -> None | (diameters[W], centres[W,3]).
 
     ``processes`` is accepted and ignored (the GPU analyses all rays / windows at once).
-    ``pore_centre`` (extension) forces the ray origin instead of optimising it."""
+    ``pore_centre`` (extension) forces the ray origin instead of optimising it.
+    ``shard_rays``: spread the rays of this ONE molecule over the ranks of the initialised ``torch.distributed``
+    group (a collective call; default: when a group of more than one rank exists and ``adjust >= 32``, i.e. dense
+    sampling with >= ~3e4 rays, BASELINE config 5)."""
     stages = _lib.STAGE_ALL & ~_lib.STAGE_AVGD
     kw = {"adjust": float(adjust), "increment": float(increment), "pore_opt": bool(pore_opt)}
     if pore_centre is not None:
@@ -149,7 +152,14 @@ def find_windows(elements, coordinates, processes=None, adjust=1, pore_opt=True,
         # the reference never calls opt_pore_diameter here (utilities.py:1386-1393): a molecule whose COM lies
         # inside an atom's vdW sphere must still return its windows instead of scipy's inverted-bounds error
         stages &= ~_lib.STAGE_OPT
-    rec = _run(elements, coordinates, stages, **kw)
+    from .distributed import world
+    if shard_rays is None:
+        shard_rays = world()[1] > 1 and float(adjust) >= 32
+    if shard_rays and world()[1] > 1:
+        res = default_engine().analyse_ray_sharded(elements, coordinates, stages=stages, **kw)
+        rec = res.host_records()[0]
+    else:
+        rec = _run(elements, coordinates, stages, **kw)
     if int(rec[_lib.REC_STATUS]) & _lib.ST_OPT_BOUNDS:
         raise ValueError("An upper bound is less than the corresponding lower bound.")
     return record_windows(rec)

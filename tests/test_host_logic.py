@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     lib.pwb_abi_version.restype = ctypes.c_int
-    assert lib.pwb_abi_version() == 2
+    assert lib.pwb_abi_version() == 3
     from pywindow_b200 import _lib
     assert set(_lib.EXPORTS) <= declared
 
