@@ -449,7 +449,7 @@ def run_ours(args):
     # ray-list capacity from the frames' bounding boxes (host side, as Trajectory.analysis does)
     ray_cap = host_ray_capacity(host_batches[0].numpy()[:4096], float(vdw.max()))
     layout = L.WsLayout()
-    eng.lib.pwb_workspace_layout(F, F * N, ray_cap, eng.win_cap, ctypes.byref(layout))
+    eng.lib.pwb_workspace_layout(F, F * N, N, ray_cap, eng.win_cap, ctypes.byref(layout))
     ws = torch.empty(layout.total, dtype=torch.uint8, device=dev)
     rec = torch.empty((F, eng.rec_stride), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)

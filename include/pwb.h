@@ -129,6 +129,8 @@ typedef struct pwb_ws_layout {
   size_t win_k;      /* int32[F][win_cap]: arg-max ray of each cluster                            */
   size_t big_pts;    /* double[F][ray_cap][4]: unit ray points, only if ray_cap > 4096 (config 5) */
   size_t big_i;      /* int32[F][2][ray_cap]: union-find scratch of the large-ray-count path      */
+  size_t atom_scratch; /* per-CTA / per-warp atom arrays of molecules too large for shared memory
+                          (> ~2 900 atoms; empty otherwise)                                        */
   size_t total;
 } pwb_ws_layout;
 
@@ -140,9 +142,9 @@ int pwb_ctx_destroy(pwb_ctx* ctx);
 /* Cut batches into `chunks` (1..8) sub-batches pipelined over internal streams (default 1).      */
 int pwb_ctx_set_chunks(pwb_ctx* ctx, int chunks);
 
-/* bytes of workspace for a batch of n_items with total_atoms atoms */
-size_t pwb_workspace_bytes(int n_items, int total_atoms, int ray_cap, int win_cap);
-int pwb_workspace_layout(int n_items, int total_atoms, int ray_cap, int win_cap, pwb_ws_layout* out);
+/* bytes of workspace for a batch of n_items with total_atoms atoms, the largest item having max_atoms */
+size_t pwb_workspace_bytes(int n_items, int total_atoms, int max_atoms, int ray_cap, int win_cap);
+int pwb_workspace_layout(int n_items, int total_atoms, int max_atoms, int ray_cap, int win_cap, pwb_ws_layout* out);
 
 /* upper bound of the ray count any item of the batch can need (bounding-box bound on max_dim);
  * synchronises `stream`.  Replaces nothing in the reference: it sizes `ray_cap`.                  */

@@ -51,7 +51,7 @@ class Batch(ctypes.Structure):
 class WsLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
                 ("atoms", "atom_idx", "item_d", "item_i", "clear_k", "clear_pos", "clear_a2", "labels",
-                 "win_k", "big_pts", "big_i", "total")]
+                 "win_k", "big_pts", "big_i", "atom_scratch", "total")]
 
 
 class PwbLibraryError(RuntimeError):
@@ -77,9 +77,9 @@ def load():
     L.pwb_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     L.pwb_ctx_destroy.argtypes = [vp]
     L.pwb_ctx_set_chunks.argtypes = [vp, ci]
-    L.pwb_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    L.pwb_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
     L.pwb_workspace_bytes.restype = ctypes.c_size_t
-    L.pwb_workspace_layout.argtypes = [ci, ci, ci, ci, ctypes.POINTER(WsLayout)]
+    L.pwb_workspace_layout.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(WsLayout)]
     L.pwb_ray_capacity.argtypes = [vp, ctypes.POINTER(Batch), vp, ctypes.POINTER(ci)]
     for name in ("pwb_frame_scalars", "pwb_average_diameter", "pwb_opt_pore", "pwb_ray_search",
                  "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch"):

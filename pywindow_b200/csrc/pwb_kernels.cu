@@ -27,7 +27,15 @@ struct Ws {   // resolved workspace pointers
   int* win_k;      // [F][win_cap]
   double* big_pts; // [F][ray_cap][4] unit-sphere ray points (only if ray_cap > KNN_SMEM_CAP)
   int* big_i;      // [F][2][ray_cap] union-find / flag scratch of the large-ray-count path
+  // Molecules whose atom tiles do not fit the 227 KB of shared memory (> ~2 900 atoms): the per-CTA / per-warp
+  // atom arrays of k_prepare, k_rays and k_windows live here instead (read through L1 / L2); nullptr otherwise.
+  double* atom_scratch;
+  long long scratch_item;   // doubles of scratch per item
 };
+
+// shared-memory need of k_rays, the largest of the three, decides: host and layout code agree through these
+constexpr size_t PWB_SMEM_LIMIT = 232448;              // 227 KB opt-in maximum per CTA on sm_100
+constexpr int PWB_MAX_SMS = 160;                       // bound on the SM count for sizing (B200: 148)
 
 constexpr int KNN_SMEM_CAP = 4096;   // ray counts served by the shared-memory eps table / DBSCAN paths
 constexpr int BIG_SLICES = 64;      // CTAs per item in the large-ray-count k-NN kernel
@@ -45,6 +53,10 @@ struct Ctx {
 // =================================================================================================
 constexpr int PREP_THREADS = 256;
 constexpr int AVG_TILE = 1024;       // average-diameter rays per tile (4 per thread)
+// doubles of k_prepare's fixed shared-memory part (reductions, class counters, direction grid) and of its
+// per-atom arrays (x, y, z, r, w + int type)
+constexpr size_t PREP_FIXED_DOUBLES = (64 * 8 + (64 + PWB_MAX_TYPES + 1 + DG_BINS + 2) * 4 + DG_BINS * DG_CAP * 2 + 15) / 16 * 2;
+#define PREP_ATOM_DOUBLES(NA) ((size_t)(NA) * 5 + ((size_t)(NA) + 1) / 2)
 
 // Rarely taken paths kept out of line so the compiler does not if-convert a double-precision sqrt
 // (~40 instructions) into the hot loops.
@@ -69,19 +81,23 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   double* idv = ws.item_d + (size_t)item * ITEM_D;
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   const int NA = b.max_atoms;
-  double* sx = sm;            // original order
-  double* sy = sx + NA;
-  double* sz = sy + NA;
-  double* sr = sz + NA;
-  double* sw = sr + NA;       // mass, later scratch
-  double* red = sw + NA;      // 64 doubles
+  // fixed-size part in shared memory, then the per-atom arrays -- in shared memory too, or (huge molecules) in
+  // this CTA's slot of the global scratch
+  double* red = sm;                 // 64 doubles
   int* redi = (int*)(red + 64);     // 64 ints
-  int* stype = redi + 64;           // [NA]
-  int* cnt = stype + NA;            // [PWB_MAX_TYPES + 1]
+  int* cnt = redi + 64;             // [PWB_MAX_TYPES + 1]
   DirGrid DG;
   DG.cnt = cnt + PWB_MAX_TYPES + 1;                      // [DG_BINS]
   DG.overflow = DG.cnt + DG_BINS;                        // [1] (+1 pad)
   DG.list = (unsigned short*)(DG.overflow + 2);          // [DG_BINS][DG_CAP]
+  double* abase = ws.atom_scratch ? ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * PREP_ATOM_DOUBLES(NA)
+                                  : sm + PREP_FIXED_DOUBLES;
+  double* sx = abase;         // original order
+  double* sy = sx + NA;
+  double* sz = sy + NA;
+  double* sr = sz + NA;
+  double* sw = sr + NA;       // mass, later scratch
+  int* stype = (int*)(sw + NA);     // [NA]
   __shared__ int s_bad;
   if (tid == 0) s_bad = 0;
   for (int c = tid; c <= PWB_MAX_TYPES; c += nt) cnt[c] = 0;
@@ -508,6 +524,11 @@ constexpr int RAY_THREADS = 256;
 constexpr int RAY_TILE = PWB_RAY_TILE;   // rays per pass (4 per thread, register tiled)
 constexpr int RAY_RPT = RAY_TILE / RAY_THREADS;
 constexpr int RAY_ACAP = RAY_TILE;   // 2*min clearance of the survivors of one tile
+// doubles of k_rays' fixed shared-memory part (a multiple of 4: the double4 atom tile behind it stays 32-byte
+// aligned) and of its per-atom arrays
+constexpr size_t RAY_FIXED_DOUBLES = ((64 + PWB_MAX_TYPES + RAY_ACAP) * 8 + (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE + DG_BINS + 2) * 4 +
+                                      DG_BINS * DG_CAP * 2 + 31) / 32 * 4;
+#define RAY_ATOM_DOUBLES(NA) ((size_t)(NA) * 8)
 
 // Exclusive block scan of one int per thread; returns this thread's offset, `total` for all.
 __device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
@@ -544,9 +565,7 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   // blockIdx.y > 0: extra CTAs sharing the ray tiles of a huge item (config 5: 1e5 rays on one molecule)
   const bool lead = blockIdx.y == 0;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double4* ap = (double4*)sm;                 // [NA] shifted, bucketed atoms: x, y, z, |x|^2
-  double* lx = (double*)(ap + NA); double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
-  double* red = lw + NA;                    // 64
+  double* red = sm;                         // 64
   double* cr = red + 64;                    // [PWB_MAX_TYPES]
   double* sa = cr + PWB_MAX_TYPES;          // [RAY_ACAP] path clearances of the current sub-pass
   int* cls = (int*)(sa + RAY_ACAP);         // [PWB_MAX_TYPES+1]
@@ -557,9 +576,14 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   DG.cnt = spos + RAY_TILE;                 // [DG_BINS]
   DG.overflow = DG.cnt + DG_BINS;           // [1] (+1 pad)
   DG.list = (unsigned short*)(DG.overflow + 2);   // [DG_BINS][DG_CAP]
+  // per-atom arrays: shared memory behind the fixed part, or this CTA's slot of the global scratch (huge molecules)
+  double* abase = ws.atom_scratch ? ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * RAY_ATOM_DOUBLES(NA)
+                                  : sm + RAY_FIXED_DOUBLES;
+  double4* ap = (double4*)abase;              // [NA] shifted, bucketed atoms: x, y, z, |x|^2
+  double* lx = (double*)(ap + NA); double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
 #ifdef RAYS_FP32_FILTER
   // experiment: FP32 copy (Lx, Ly, Lz, r^2 - |L|^2) for a filter in front of the exact FP64 pre-test
-  float4* lf = (float4*)(((uintptr_t)(DG.list + DG_BINS * DG_CAP) + 15) & ~(uintptr_t)15);
+  float4* lf = (float4*)(sm + RAY_FIXED_DOUBLES + (ws.atom_scratch ? 0 : RAY_ATOM_DOUBLES(NA)));
   __shared__ float s_eps_u, s_eps_t;
 #endif
 
@@ -1305,7 +1329,11 @@ constexpr int WIN_WARPS = 4;
 #endif
 // doubles of shared memory per warp: double4[NA] + r[NA] + class radii/starts + near list + z-stage state +
 // coarse grid values and candidate list (100 + 76), even
-#define WIN_WARP_DOUBLES(NA) ((((NA) * 5 + PWB_MAX_TYPES + 32 + (((NA) + 3) & ~3) / 4 + LB_STORAGE(1) + 176) + 1) & ~(size_t)1)
+// per-atom part: double4[NA] + r[NA] + near-list indices (ushort[NA]); fixed part: class radii / starts, z-stage
+// solver state, coarse grid + candidate list.  Both even, the atom part a multiple of 4 (double4 alignment).
+#define WIN_ATOM_DOUBLES(NA) ((((size_t)(NA) * 5 + (((size_t)(NA) + 3) & ~(size_t)3) / 4) + 3) & ~(size_t)3)
+#define WIN_FIXED_DOUBLES ((size_t)((PWB_MAX_TYPES + 32 + LB_STORAGE(1) + 176 + 3) & ~3))
+#define WIN_WARP_DOUBLES(NA) (WIN_ATOM_DOUBLES(NA) + WIN_FIXED_DOUBLES)
 
 struct DevZObj {   // optimise_z, utilities.py:1174-1188
   WarpAtoms A; double lo;
@@ -1350,20 +1378,19 @@ __device__ __forceinline__ double angle_between(double x0, double x1, double x2,
 #endif
 // one (item, window) on one warp; `smw` is the warp's private shared memory (WIN_WARP_DOUBLES)
 __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, const int item, const int win,
-                                            const int lane, double* smw) {
+                                            const int lane, double* smw, double* atoms_w) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
   double* idv = ws.item_d + (size_t)item * ITEM_D;
   double* rec = b.records + (size_t)item * b.rec_stride;
   double* out = rec + PWB_REC_WIN0 + 4 * win;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  const int NAp = (NA + 3) & ~3;
-  double4* p4 = (double4*)smw;               // x, y, z, |x|^2 (shifted, later rotated)
+  double4* p4 = (double4*)atoms_w;           // x, y, z, |x|^2 (shifted, later rotated)
   double* r = (double*)(p4 + NA);
-  double* cr = r + NA;                       // [PWB_MAX_TYPES]
+  unsigned short* nidx = (unsigned short*)(r + NA);                     // [NA] near-list atom indices
+  double* cr = smw;                          // [PWB_MAX_TYPES]
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
   int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
-  unsigned short* nidx = (unsigned short*)(cr + PWB_MAX_TYPES + 32);   // [NA] near-list atom indices
-  double* hist = cr + PWB_MAX_TYPES + 32 + NAp / 4;                     // [LB_STORAGE(1)] z-stage L-BFGS state
+  double* hist = cr + PWB_MAX_TYPES + 32;                               // [LB_STORAGE(1)] z-stage L-BFGS state
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -1569,7 +1596,14 @@ k_windows(pwb_batch b, Ws ws) {
   const int item = gw / b.win_cap, win = gw - item * b.win_cap;
   if (item >= b.n_items) return;
   if (win >= ws.item_i[(size_t)item * ITEM_I + I_NWIN]) return;
-  window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_WARP_DOUBLES(b.max_atoms));
+  // per-warp shared memory: [atoms | fixed]; huge molecules keep the atom part in the warp's global scratch slot
+  if (ws.atom_scratch)
+    window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_FIXED_DOUBLES,
+                ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)win * WIN_ATOM_DOUBLES(b.max_atoms));
+  else {
+    double* smw = sm + (size_t)w * WIN_WARP_DOUBLES(b.max_atoms);
+    window_slot(b, ws, item, win, lane, smw + WIN_ATOM_DOUBLES(b.max_atoms), smw);
+  }
 }
 
 // final status word (window kernels OR flags into item_i after the record status was written)
@@ -1655,7 +1689,33 @@ void pwb_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); 
 int pwb_abi_version(void) { return PWB_ABI_VERSION; }
 const char* pwb_last_error(void) { return g_err; }
 
-int pwb_workspace_layout(int F, int total_atoms, int ray_cap, int win_cap, pwb_ws_layout* L) {
+// CTAs per item the ray-tiled kernels may use (see tile_ctas): bound used for sizing
+static int tile_ctas_bound(int n_items, int ray_cap, int tile, int num_sms) {
+  const int tiles = (ray_cap + tile - 1) / tile;
+  int want = (2 * num_sms) / (n_items > 0 ? n_items : 1);
+  if (want > tiles) want = tiles;
+  if (want > 128) want = 128;
+  return want < 1 ? 1 : want;
+}
+static size_t rays_smem(int max_atoms) {
+  size_t sm = sizeof(double) * (RAY_FIXED_DOUBLES + RAY_ATOM_DOUBLES((size_t)max_atoms));
+#ifdef RAYS_FP32_FILTER
+  sm += sizeof(float) * 4 * (size_t)max_atoms + 16;
+#endif
+  return sm;
+}
+// huge molecules: the per-atom arrays of k_prepare / k_rays / k_windows go to global scratch
+static bool big_atoms(int max_atoms) { return rays_smem(max_atoms) > PWB_SMEM_LIMIT; }
+static size_t scratch_item_doubles(int n_items, int max_atoms, int ray_cap, int win_cap) {
+  const size_t y = (size_t)tile_ctas_bound(n_items, ray_cap, RAY_TILE, PWB_MAX_SMS);
+  size_t a = y * RAY_ATOM_DOUBLES((size_t)max_atoms), p = y * PREP_ATOM_DOUBLES((size_t)max_atoms);
+  size_t w = (size_t)win_cap * WIN_ATOM_DOUBLES((size_t)max_atoms);
+  size_t m = a > p ? a : p;
+  m = m > w ? m : w;
+  return (m + 3) & ~(size_t)3;
+}
+
+int pwb_workspace_layout(int F, int total_atoms, int max_atoms, int ray_cap, int win_cap, pwb_ws_layout* L) {
   size_t o = 0;
   L->atoms = o; o = align_up(o + (size_t)total_atoms * 4 * sizeof(double));
   L->atom_idx = o; o = align_up(o + (size_t)total_atoms * sizeof(int));
@@ -1669,12 +1729,14 @@ int pwb_workspace_layout(int F, int total_atoms, int ray_cap, int win_cap, pwb_w
   const size_t big = ray_cap > KNN_SMEM_CAP ? (size_t)F * ray_cap : 0;   // large-ray-count scratch
   L->big_pts = o; o = align_up(o + big * 4 * sizeof(double));
   L->big_i = o; o = align_up(o + big * 2 * sizeof(int));
+  L->atom_scratch = o;
+  if (big_atoms(max_atoms)) o = align_up(o + (size_t)F * scratch_item_doubles(F, max_atoms, ray_cap, win_cap) * sizeof(double));
   L->total = o;
   return 0;
 }
-size_t pwb_workspace_bytes(int F, int total_atoms, int ray_cap, int win_cap) {
+size_t pwb_workspace_bytes(int F, int total_atoms, int max_atoms, int ray_cap, int win_cap) {
   pwb_ws_layout L;
-  pwb_workspace_layout(F, total_atoms, ray_cap, win_cap, &L);
+  pwb_workspace_layout(F, total_atoms, max_atoms, ray_cap, win_cap, &L);
   return L.total;
 }
 
@@ -1720,7 +1782,7 @@ long long pwb_launch_count(pwb_ctx* c) { return c->c.launches; }
 static int resolve(const pwb_batch* b, Ws* w) {
   if (!b->workspace) { snprintf(g_err, sizeof g_err, "workspace is null"); return 1; }
   pwb_ws_layout L;
-  pwb_workspace_layout(b->n_items, b->total_atoms, b->ray_cap, b->win_cap, &L);
+  pwb_workspace_layout(b->n_items, b->total_atoms, b->max_atoms, b->ray_cap, b->win_cap, &L);
   if (b->workspace_bytes < L.total) { snprintf(g_err, sizeof g_err, "workspace too small: %zu < %zu", b->workspace_bytes, L.total); return 1; }
   char* p = (char*)b->workspace;
   w->atoms = (double*)(p + L.atoms); w->atom_idx = (int*)(p + L.atom_idx);
@@ -1728,6 +1790,9 @@ static int resolve(const pwb_batch* b, Ws* w) {
   w->clear_k = (int*)(p + L.clear_k); w->clear_pos = (int*)(p + L.clear_pos);
   w->clear_a2 = (double*)(p + L.clear_a2); w->labels = (int*)(p + L.labels); w->win_k = (int*)(p + L.win_k);
   w->big_pts = (double*)(p + L.big_pts); w->big_i = (int*)(p + L.big_i);
+  const bool big = big_atoms(b->max_atoms);
+  w->atom_scratch = big ? (double*)(p + L.atom_scratch) : nullptr;
+  w->scratch_item = big ? (long long)scratch_item_doubles(b->n_items, b->max_atoms, b->ray_cap, b->win_cap) : 0;
   return 0;
 }
 
@@ -1745,15 +1810,10 @@ static int check(const pwb_batch* b) {
 // CTAs per item for the ray-tiled kernels: one for a batch that already fills the GPU, up to the number of ray
 // tiles when a few huge items (config 5: ~1e5 rays on one molecule) would otherwise run on a handful of SMs
 static int tile_ctas(const pwb_ctx* c, const pwb_batch* b, int tile) {
-  const int tiles = (b->ray_cap + tile - 1) / tile;
-  int want = (2 * c->num_sms) / (b->n_items > 0 ? b->n_items : 1);
-  if (want > tiles) want = tiles;
-  if (want > 128) want = 128;
-  return want < 1 ? 1 : want;
+  return tile_ctas_bound(b->n_items, b->ray_cap, tile, c->num_sms < PWB_MAX_SMS ? c->num_sms : PWB_MAX_SMS);
 }
 static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s, int do_avg) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 5 + 64) + sizeof(int) * (64 + b->max_atoms + PWB_MAX_TYPES + 1 + DG_BINS + 2) +
-              sizeof(unsigned short) * DG_BINS * DG_CAP;
+  size_t sm = sizeof(double) * (PREP_FIXED_DOUBLES + (w.atom_scratch ? 0 : PREP_ATOM_DOUBLES((size_t)b->max_atoms)));
   if (set_smem(k_prepare, sm, c->max_smem)) return 1;
   const dim3 grid((unsigned)b->n_items, do_avg ? (unsigned)tile_ctas(c, b, AVG_TILE) : 1u);
   // per-item "tiles done" counters of the multi-CTA paths (k_prepare average diameter, k_rays); self-resetting
@@ -1787,10 +1847,9 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   return 0;
 }
 static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  size_t sm = sizeof(double) * ((size_t)b->max_atoms * 8 + 64 + PWB_MAX_TYPES + RAY_ACAP) +
-              sizeof(int) * (PWB_MAX_TYPES + 1 + 32 + 2 * RAY_TILE + DG_BINS + 2) + sizeof(unsigned short) * DG_BINS * DG_CAP;
+  size_t sm = w.atom_scratch ? sizeof(double) * RAY_FIXED_DOUBLES : rays_smem(b->max_atoms);
 #ifdef RAYS_FP32_FILTER
-  sm += sizeof(float) * 4 * (size_t)b->max_atoms + 16;
+  if (w.atom_scratch) sm += sizeof(float) * 4 * (size_t)b->max_atoms + 16;
 #endif
   if (set_smem(k_rays, sm, c->max_smem)) return 1;
   const dim3 grid((unsigned)b->n_items, (unsigned)tile_ctas(c, b, RAY_TILE));
@@ -1825,7 +1884,7 @@ static int run_cluster(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   return 0;
 }
 static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
-  const size_t per_warp = sizeof(double) * WIN_WARP_DOUBLES((size_t)b->max_atoms);
+  const size_t per_warp = sizeof(double) * (w.atom_scratch ? WIN_FIXED_DOUBLES : WIN_WARP_DOUBLES((size_t)b->max_atoms));
   int wpb = WIN_WARPS;
   while (wpb > 1 && per_warp * wpb + 64 > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb + 64;
@@ -1872,7 +1931,8 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
   if (check(b)) return 1;
   Ws w;
   if (resolve(b, &w)) return 1;
-  const int G = (c->chunks > 1 && b->n_items >= 64 * c->chunks) ? c->chunks : 1;
+  // (huge molecules share one global scratch region sized for the whole batch: not cut into sub-batches)
+  const int G = (c->chunks > 1 && b->n_items >= 64 * c->chunks && !w.atom_scratch) ? c->chunks : 1;
   // item_off lives on the device; the host variant needs atom offsets to cut the copies, which it
   // can only do cheaply for equally sized items (trajectory of one molecule): total_atoms / n_items
   const bool uniform = b->n_items > 0 && b->total_atoms % b->n_items == 0 && b->shared_types;

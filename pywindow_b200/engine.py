@@ -184,7 +184,7 @@ class Engine:
                                                    shared_types, max_atoms, centre_override, stages, adjust,
                                                    increment, increment2, pore_opt, ray_cap, opt_start, opt_bounds)
             layout = _lib.WsLayout()
-            self.lib.pwb_workspace_layout(F, total, b.ray_cap, self.win_cap, ctypes.byref(layout))
+            self.lib.pwb_workspace_layout(F, total, int(max_atoms), b.ray_cap, self.win_cap, ctypes.byref(layout))
             ws = torch.empty(layout.total, dtype=torch.uint8, device=self.device)
             rec = torch.empty((F, self.rec_stride), dtype=torch.float64, device=self.device)
             b.records, b.workspace, b.workspace_bytes = rec.data_ptr(), ws.data_ptr(), layout.total
@@ -316,7 +316,7 @@ class Engine:
                 st["d_coords"] = torch.empty((F * N, 3), dtype=torch.float64, device=self.device)
                 st["d_rec"] = torch.empty((F, self.rec_stride), dtype=torch.float64, device=self.device)
                 layout = _lib.WsLayout()
-                self.lib.pwb_workspace_layout(F, F * N, ray_cap, self.win_cap, ctypes.byref(layout))
+                self.lib.pwb_workspace_layout(F, F * N, N, ray_cap, self.win_cap, ctypes.byref(layout))
                 st["layout"] = layout
                 st["ws"] = torch.empty(layout.total, dtype=torch.uint8, device=self.device)
                 st["h_rec"] = torch.empty((F, self.rec_stride), dtype=torch.float64).pin_memory()
@@ -398,7 +398,7 @@ class FramePipeline:
         eng = self.eng
         self.ray_cap = int(ray_cap)
         with torch.cuda.device(eng.device):
-            eng.lib.pwb_workspace_layout(self.cap, self.cap * self.N, self.ray_cap, eng.win_cap, ctypes.byref(self.layout))
+            eng.lib.pwb_workspace_layout(self.cap, self.cap * self.N, self.N, self.ray_cap, eng.win_cap, ctypes.byref(self.layout))
             for sl in self.slots:
                 sl["ws"] = None
             for sl in self.slots:
@@ -427,7 +427,10 @@ class FramePipeline:
                                               None, p["stages"], p["adjust"], p["increment"], p["increment2"],
                                               p["pore_opt"], self.ray_cap)
             b.n_items, b.total_atoms = n, n * self.N
-            b.workspace, b.workspace_bytes = sl["ws"].data_ptr(), self.layout.total
+            need = eng.lib.pwb_workspace_bytes(n, n * self.N, self.N, self.ray_cap, eng.win_cap)
+            if need > sl["ws"].numel():     # (huge molecules: a short batch spreads each item over more CTAs)
+                sl["ws"] = torch.empty(need, dtype=torch.uint8, device=eng.device)
+            b.workspace, b.workspace_bytes = sl["ws"].data_ptr(), sl["ws"].numel()
             _lib.check(eng.lib.pwb_full_analysis_host_async(
                 eng._ctx, ctypes.byref(b), h_in.data_ptr(), sl["h_rec"].data_ptr(), sl["d_in"].data_ptr(),
                 sl["d_rec"].data_ptr(), n * self.N, stream))

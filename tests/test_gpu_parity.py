@@ -372,3 +372,49 @@ def test_opt_pore_diameter_bounds_and_start_point(eng):
     assert np.array_equal(c, start) and abs(d - O.pore_diameter(r, X, start)[0]) < 1e-12
     with pytest.raises(ValueError):
         U.opt_pore_diameter(el, X, bounds=((1.0, -1.0), (0.0, 1.0), (0.0, 1.0)))
+
+
+def test_molecule_larger_than_shared_memory(eng):
+    """A 5 600-atom shell (the per-atom tiles of k_prepare / k_rays / k_windows no longer fit 227 KB of shared memory
+    and live in the global scratch region): every deterministic quantity against the oracle to 1e-9, windows found
+    from the GPU's pore centre to 1e-3 A -- the reference has no size limit, neither has the GPU path."""
+    from pywindow_b200 import _lib as L
+    from pywindow_b200.engine import record_windows
+    import pw_oracle as O
+    rng = np.random.default_rng(17)
+    n = 6200
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    X = u * rng.uniform(46.0, 48.5, size=(n, 1))
+    X = X[np.abs(u[:, 2]) < 0.955]                         # two polar openings
+    el = np.array(["C", "H", "N", "O"])[rng.integers(0, 4, size=X.shape[0])]
+    assert X.shape[0] > 5000
+    res = eng.analyse_molecules([(el, X)])
+    rec = res.host_records()[0]
+    assert int(rec[L.REC_STATUS]) & ~(L.ST_WIN_NEGATIVE | L.ST_WIN_DROPPED) == 0
+    r, m = O.vdw_of(el), O.masses_of(el)
+    com = O.center_of_mass(m, X)
+    np.testing.assert_allclose(rec[L.REC_COM:L.REC_COM + 3], com, atol=1e-9)
+    i1, i2, D = O.max_dim(r, X)
+    assert abs(rec[L.REC_MAXD] - D) < 1e-9
+    pd_, pa = O.pore_diameter(r, X, com)
+    assert abs(rec[L.REC_PORE_D] - pd_) < 1e-9 and int(rec[L.REC_PORE_ATOM]) == pa
+    assert abs(rec[L.REC_AVGD] - O.find_average_diameter(r, m, X)) < 1e-9
+    c = rec[L.REC_OPT_C:L.REC_OPT_C + 3]
+    assert abs(rec[L.REC_OPT_D] - O.pore_diameter(r, X, c)[0]) < 1e-9
+    det = {}
+    w = O.find_windows(r, m, X, centre=c, detail=det)
+    S = int(rec[L.REC_NCLEAR])
+    assert int(rec[L.REC_NRAYS]) == det["P"] and S == int(det["clear"].sum())
+    assert (res.clear_k.cpu().numpy()[0, :S] == np.nonzero(det["clear"])[0]).all()
+    assert (res.labels.cpu().numpy()[0, :S] == det["labels"]).all()
+    g = record_windows(rec, warn=False)
+    assert w is not None and g is not None and len(g[0]) == len(w[0]) >= 2
+    np.testing.assert_allclose(g[0], w[0], atol=1e-3)
+    np.testing.assert_allclose(g[1], w[1], atol=5e-3)
+    # the same molecule in a batch with small ones (per-item tiles sized by the largest item)
+    small = load_golden("md_frame00")
+    both = eng.analyse_molecules([(small["elements"], small["coords"]), (el, X)]).host_records()
+    one = eng.analyse_molecules([(small["elements"], small["coords"])]).host_records()[0]
+    np.testing.assert_array_equal(both[1], rec)
+    np.testing.assert_array_equal(both[0], one)

@@ -31,8 +31,11 @@ def test_workspace_layout_is_consistent():
     from pywindow_b200 import _lib
     L = _lib.load()
     lay = _lib.WsLayout()
-    L.pwb_workspace_layout(10, 1680, 896, 16, ctypes.byref(lay))
-    assert lay.total == L.pwb_workspace_bytes(10, 1680, 896, 16)
+    L.pwb_workspace_layout(10, 1680, 168, 896, 16, ctypes.byref(lay))
+    assert lay.total == L.pwb_workspace_bytes(10, 1680, 168, 896, 16) and lay.atom_scratch == lay.total
+    big = _lib.WsLayout()
+    L.pwb_workspace_layout(2, 12000, 6000, 1024, 16, ctypes.byref(big))          # atoms beyond shared memory
+    assert big.total > big.atom_scratch >= big.win_k
     offs = [lay.atoms, lay.atom_idx, lay.item_d, lay.item_i, lay.clear_k, lay.clear_pos, lay.clear_a2, lay.labels, lay.win_k]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
 

@@ -25,7 +25,7 @@ d_X = torch.as_tensor(X, device=dev).view(-1, 3)
 off = torch.arange(0, (F + 1) * N, N, dtype=torch.int32, device=dev)
 d_t, d_v, d_m = torch.as_tensor(types, device=dev), torch.as_tensor(vdw, device=dev), torch.as_tensor(mass, device=dev)
 ray_cap = host_ray_capacity(X[:4096], float(vdw.max()))
-lay = L.WsLayout(); eng.lib.pwb_workspace_layout(F, F * N, ray_cap, eng.win_cap, ctypes.byref(lay))
+lay = L.WsLayout(); eng.lib.pwb_workspace_layout(F, F * N, N, ray_cap, eng.win_cap, ctypes.byref(lay))
 ws = torch.empty(lay.total, dtype=torch.uint8, device=dev)
 rec = torch.empty((F, eng.rec_stride), dtype=torch.float64, device=dev)
 sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -7,10 +7,10 @@ from pywindow_b200.engine import Engine
 from pywindow_b200 import _lib as L
 rng = np.random.default_rng(11)
 eng = Engine(0)
-for n in (12, 60, 168, 500, 1200, 2000, 2800):
+for n in (12, 60, 168, 500, 1200, 2000, 2800, 3200, 5000, 10000, 20000):   # > ~2 900: atom tiles in global scratch
     R = 2.2 * np.sqrt(n / 12.0)                     # shell radius so that atoms stay ~3 A apart
     mols = []
-    for k in range(6):
+    for k in range(6 if n <= 5000 else 2):
         v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
         X = v * (R + rng.normal(0, 0.3, size=(n, 1)))
         el = rng.choice(["C", "H", "N", "O", "S", "Cl", "Br"], size=n, p=[.4, .35, .08, .08, .03, .03, .03])
