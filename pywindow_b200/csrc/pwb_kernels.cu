@@ -51,7 +51,10 @@ struct Ctx {
 // =================================================================================================
 // k_prepare
 // =================================================================================================
-constexpr int PREP_THREADS = 256;
+#ifndef PREP_THREADS_N
+#define PREP_THREADS_N 256
+#endif
+constexpr int PREP_THREADS = PREP_THREADS_N;
 constexpr int AVG_TILE = 1024;       // average-diameter rays per tile (4 per thread)
 // doubles of k_prepare's fixed shared-memory part (reductions, class counters, direction grid) and of its
 // per-atom arrays (x, y, z, r, w + int type)
@@ -69,6 +72,9 @@ __device__ __noinline__ ValIdx rare_pair_max(ValIdx mb, double d2, double rr, in
 #ifndef PREP_MINB
 #define PREP_MINB 4
 #endif
+// BIG: the per-atom arrays live in the global scratch region (molecules beyond the shared-memory budget); a
+// separate instantiation, so that the common case keeps pure shared-memory addressing (LDS, not generic loads)
+template <bool BIG>
 __global__ void __launch_bounds__(PREP_THREADS, PREP_MINB)
 k_prepare(pwb_batch b, Ws ws, int do_avg) {
   extern __shared__ double sm[];
@@ -90,8 +96,9 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
   DG.cnt = cnt + PWB_MAX_TYPES + 1;                      // [DG_BINS]
   DG.overflow = DG.cnt + DG_BINS;                        // [1] (+1 pad)
   DG.list = (unsigned short*)(DG.overflow + 2);          // [DG_BINS][DG_CAP]
-  double* abase = ws.atom_scratch ? ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * PREP_ATOM_DOUBLES(NA)
-                                  : sm + PREP_FIXED_DOUBLES;
+  double* abase;
+  if (BIG) abase = ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * PREP_ATOM_DOUBLES(NA);
+  else abase = sm + PREP_FIXED_DOUBLES;
   double* sx = abase;         // original order
   double* sy = sx + NA;
   double* sz = sy + NA;
@@ -131,14 +138,36 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     }
   }
   __syncthreads();
-  // stable bucket scatter to the workspace (x, y, z, r) + original index
-  for (int a = tid; a < n && lead; a += nt) {
-    int t = stype[a], rank = 0;
-    for (int j = 0; j < a; j++) rank += (stype[j] == t);
-    int pos = cnt[t] + rank;
-    double* q = ws.atoms + (size_t)(off + pos) * 4;
-    q[0] = sx[a]; q[1] = sy[a]; q[2] = sz[a]; q[3] = sr[a];
-    ws.atom_idx[off + pos] = a;
+  // stable bucket scatter to the workspace (x, y, z, r) + original index.  Position of atom a = start of its class
+  // + the atoms of that class before it: counted per chunk of `nt` atoms with match_any (equal types inside the
+  // warp) and a small per-warp table (lower warps of the chunk), plus a running count over earlier chunks.
+  if (lead) {
+    __shared__ int wcnt[PREP_THREADS / 32][PWB_MAX_TYPES];
+    __shared__ int run[PWB_MAX_TYPES];
+    const int lane = tid & 31, wd = tid >> 5, nw = nt >> 5;
+    if (tid < PWB_MAX_TYPES) run[tid] = 0;
+    for (int base = 0; base < n; base += nt) {
+      const int a = base + tid;
+      const bool valid = a < n;
+      const int t = valid ? stype[a] : -1;
+      for (int k = tid; k < nw * PWB_MAX_TYPES; k += nt) (&wcnt[0][0])[k] = 0;
+      __syncthreads();
+      const unsigned peers = __match_any_sync(0xffffffffu, t);
+      const int inwarp = __popc(peers & ((1u << lane) - 1u));
+      if (valid && inwarp == 0) wcnt[wd][t] = __popc(peers);
+      __syncthreads();
+      if (valid) {
+        int below = run[t];
+        for (int k = 0; k < wd; k++) below += wcnt[k][t];
+        const int pos = cnt[t] + below + inwarp;
+        double* q = ws.atoms + (size_t)(off + pos) * 4;
+        q[0] = sx[a]; q[1] = sy[a]; q[2] = sz[a]; q[3] = sr[a];
+        ws.atom_idx[off + pos] = a;
+      }
+      __syncthreads();
+      if (tid < PWB_MAX_TYPES) { int tot = 0; for (int k = 0; k < nw; k++) tot += wcnt[k][tid]; run[tid] += tot; }
+      __syncthreads();               // the table is cleared at the top of the next chunk
+    }
   }
   // ---- centre of mass (utilities.py:127-148)
   double mx = 0, my = 0, mz = 0, mt = 0;
@@ -224,41 +253,12 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
     ox += sx[a]; oy += sy[a]; oz += sz[a];
   }
   ox = block_sum(ox, red) / n; oy = block_sum(oy, red) / n; oz = block_sum(oz, red) / n;
-  // atoms re-ordered by |L| + r descending (rank sort): the outermost atoms set the running maximum
-  // early, so the sqrt branch in the ray loop is almost never taken afterwards
-  constexpr int APT = 4;                        // atoms per thread held in registers while sorting
-  const bool sortable = n <= APT * nt;
-  double mx_[APT], my_[APT], mz_[APT], mr_[APT], mk_[APT];
-  int rank[APT];
-  {
-    int c2 = 0;
-    for (int a = tid; a < n; a += nt, c2++) {
-      double lx = sx[a] - ox, ly = sy[a] - oy, lz = sz[a] - oz, ra = sr[a];
-      if (sortable) {
-        mx_[c2] = lx; my_[c2] = ly; mz_[c2] = lz; mr_[c2] = ra;
-        mk_[c2] = sqrt(lx * lx + ly * ly + lz * lz) + ra;
-        sw[a] = mk_[c2];
-      } else { sx[a] = lx; sy[a] = ly; sz[a] = lz; sw[a] = ra * ra - (lx * lx + ly * ly + lz * lz); }
-    }
-  }
-  __syncthreads();
-  if (sortable) {
-    int c2 = 0;
-    for (int a = tid; a < n; a += nt, c2++) {
-      int rk = 0;
-      const double k = mk_[c2];
-      for (int j = 0; j < n; j++) { const double kj = sw[j]; rk += (kj > k) || (kj == k && j < a); }
-      rank[c2] = rk;
-    }
-  }
-  __syncthreads();
-  if (sortable) {
-    int c2 = 0;
-    for (int a = tid; a < n; a += nt, c2++) {
-      const int dst = rank[c2];
-      sx[dst] = mx_[c2]; sy[dst] = my_[c2]; sz[dst] = mz_[c2]; sr[dst] = mr_[c2];
-      sw[dst] = mr_[c2] * mr_[c2] - (mx_[c2] * mx_[c2] + my_[c2] * my_[c2] + mz_[c2] * mz_[c2]);   // r^2 - |L|^2
-    }
+  // centroid-relative positions in place, sw = r^2 - |L|^2.  (Round 1 also rank-sorted the atoms by |L| + r so
+  // that the outermost ones set the running maximum first; with the direction-bin lists deciding the visiting
+  // order that O(n^2) sort only cost 10 % of the kernel's instructions -- max() does not care about the order.)
+  for (int a = tid; a < n; a += nt) {
+    const double lx = sx[a] - ox, ly = sy[a] - oy, lz = sz[a] - oz, ra = sr[a];
+    sx[a] = lx; sy[a] = ly; sz[a] = lz; sw[a] = ra * ra - (lx * lx + ly * ly + lz * lz);
   }
   __syncthreads();
   const int P = n_sampling_points(D, b.adjust);
@@ -520,7 +520,10 @@ k_opt_pore(pwb_batch b, Ws ws) {
 // =================================================================================================
 // k_rays
 // =================================================================================================
-constexpr int RAY_THREADS = 256;
+#ifndef RAY_THREADS_N
+#define RAY_THREADS_N 256
+#endif
+constexpr int RAY_THREADS = RAY_THREADS_N;
 constexpr int RAY_TILE = PWB_RAY_TILE;   // rays per pass (4 per thread, register tiled)
 constexpr int RAY_RPT = RAY_TILE / RAY_THREADS;
 constexpr int RAY_ACAP = RAY_TILE;   // 2*min clearance of the survivors of one tile
@@ -553,6 +556,7 @@ __device__ __forceinline__ void ray_dir(int k, int P, double R, double& px, doub
 #ifndef RAY_MINB
 #define RAY_MINB 4
 #endif
+template <bool BIG>
 __global__ void __launch_bounds__(RAY_THREADS, RAY_MINB)
 k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   extern __shared__ __align__(16) double sm[];
@@ -565,7 +569,8 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   // blockIdx.y > 0: extra CTAs sharing the ray tiles of a huge item (config 5: 1e5 rays on one molecule)
   const bool lead = blockIdx.y == 0;
   const int n = iiv[I_N], off = b.item_off[item], NA = b.max_atoms;
-  double* red = sm;                         // 64
+  // shared memory: [per-atom arrays | fixed part]; BIG: the per-atom arrays are in the global scratch instead
+  double* red = sm + (BIG ? 0 : RAY_ATOM_DOUBLES(b.max_atoms));   // 64
   double* cr = red + 64;                    // [PWB_MAX_TYPES]
   double* sa = cr + PWB_MAX_TYPES;          // [RAY_ACAP] path clearances of the current sub-pass
   int* cls = (int*)(sa + RAY_ACAP);         // [PWB_MAX_TYPES+1]
@@ -577,13 +582,14 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
   DG.overflow = DG.cnt + DG_BINS;           // [1] (+1 pad)
   DG.list = (unsigned short*)(DG.overflow + 2);   // [DG_BINS][DG_CAP]
   // per-atom arrays: shared memory behind the fixed part, or this CTA's slot of the global scratch (huge molecules)
-  double* abase = ws.atom_scratch ? ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * RAY_ATOM_DOUBLES(NA)
-                                  : sm + RAY_FIXED_DOUBLES;
+  double* abase;
+  if (BIG) abase = ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)blockIdx.y * RAY_ATOM_DOUBLES(NA);
+  else abase = sm;
   double4* ap = (double4*)abase;              // [NA] shifted, bucketed atoms: x, y, z, |x|^2
   double* lx = (double*)(ap + NA); double* ly = lx + NA; double* lz = ly + NA; double* lw = lz + NA;  // about the centroid; r^2-|L|^2
 #ifdef RAYS_FP32_FILTER
   // experiment: FP32 copy (Lx, Ly, Lz, r^2 - |L|^2) for a filter in front of the exact FP64 pre-test
-  float4* lf = (float4*)(sm + RAY_FIXED_DOUBLES + (ws.atom_scratch ? 0 : RAY_ATOM_DOUBLES(NA)));
+  float4* lf = (float4*)(red + RAY_FIXED_DOUBLES);
   __shared__ float s_eps_u, s_eps_t;
 #endif
 
@@ -753,6 +759,9 @@ k_rays(pwb_batch b, Ws ws, Ctx ctx) {
     // parabola in j, so min_j is attained at the step nearest to the atom's projection (clamped to the
     // path; an exact half-way projection takes the smaller step, the reference's first arg-min):
     // min_j min_i = min_i d_i(j_i) -- ONE instead of chunks+1 evaluations per atom.
+    // (Splitting each surviving ray over 4 lanes to even out the last, nearly empty round of this loop was
+    // measured 70 % SLOWER: the per-ray set-up -- spiral point, floor division, three divisions -- is paid per
+    // warp round whatever the number of active lanes, so fewer rays per round cost more than the idle tail.)
     for (int s = tid; s < nsurv; s += nt) {
       double px, py, pz, nr;
       ray_dir(surv[s], P, R, px, py, pz, nr);
@@ -1367,7 +1376,7 @@ struct DevXYObj {  // optimise_xy, utilities.py:1164-1171
   }
 };
 
-__device__ __forceinline__ double angle_between(double x0, double x1, double x2, double y0, double y1, double y2) {
+PWB_MATHFN double angle_between(double x0, double x1, double x2, double y0, double y1, double y2) {
   double first = fabs(x0 * y0 + x1 * y1 + x2 * y2) /
                  (sqrt(x0 * x0 + x1 * x1 + x2 * x2) * sqrt(y0 * y0 + y1 * y1 + y2 * y2));
   return acos(first);
@@ -1588,6 +1597,7 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
 
 // Static (item, window) -> warp map: a work queue like k_opt_pore's was measured 45 % SLOWER here (warps
 // of a CTA drift into different phases of this 200 KB kernel and miss in the instruction cache).
+template <bool BIG>
 __global__ void __launch_bounds__(WIN_WARPS * 32, WIN_MINB)
 k_windows(pwb_batch b, Ws ws) {
   extern __shared__ __align__(16) double sm[];
@@ -1596,10 +1606,9 @@ k_windows(pwb_batch b, Ws ws) {
   const int item = gw / b.win_cap, win = gw - item * b.win_cap;
   if (item >= b.n_items) return;
   if (win >= ws.item_i[(size_t)item * ITEM_I + I_NWIN]) return;
-  // per-warp shared memory: [atoms | fixed]; huge molecules keep the atom part in the warp's global scratch slot
-  if (ws.atom_scratch)
-    window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_FIXED_DOUBLES,
-                ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)win * WIN_ATOM_DOUBLES(b.max_atoms));
+  // per-warp shared memory: [atoms | fixed]; huge molecules (BIG) keep the atom part in the warp's global scratch slot
+  if (BIG) window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_FIXED_DOUBLES,
+                       ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)win * WIN_ATOM_DOUBLES(b.max_atoms));
   else {
     double* smw = sm + (size_t)w * WIN_WARP_DOUBLES(b.max_atoms);
     window_slot(b, ws, item, win, lane, smw + WIN_ATOM_DOUBLES(b.max_atoms), smw);
@@ -1814,13 +1823,14 @@ static int tile_ctas(const pwb_ctx* c, const pwb_batch* b, int tile) {
 }
 static int run_prepare(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s, int do_avg) {
   size_t sm = sizeof(double) * (PREP_FIXED_DOUBLES + (w.atom_scratch ? 0 : PREP_ATOM_DOUBLES((size_t)b->max_atoms)));
-  if (set_smem(k_prepare, sm, c->max_smem)) return 1;
+  auto kern = w.atom_scratch ? k_prepare<true> : k_prepare<false>;
+  if (set_smem(kern, sm, c->max_smem)) return 1;
   const dim3 grid((unsigned)b->n_items, do_avg ? (unsigned)tile_ctas(c, b, AVG_TILE) : 1u);
   // per-item "tiles done" counters of the multi-CTA paths (k_prepare average diameter, k_rays); self-resetting
   // afterwards, only ever touched when an item is shared by several CTAs
   if (tile_ctas(c, b, RAY_TILE) > 1)
     CK(cudaMemset2DAsync(w.item_i + I_TILES_PREP, sizeof(int) * ITEM_I, 0, 2 * sizeof(int), (size_t)b->n_items, s));
-  k_prepare<<<grid, PREP_THREADS, sm, s>>>(*b, w, do_avg);
+  kern<<<grid, PREP_THREADS, sm, s>>>(*b, w, do_avg);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1851,9 +1861,10 @@ static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s)
 #ifdef RAYS_FP32_FILTER
   if (w.atom_scratch) sm += sizeof(float) * 4 * (size_t)b->max_atoms + 16;
 #endif
-  if (set_smem(k_rays, sm, c->max_smem)) return 1;
+  auto kern = w.atom_scratch ? k_rays<true> : k_rays<false>;
+  if (set_smem(kern, sm, c->max_smem)) return 1;
   const dim3 grid((unsigned)b->n_items, (unsigned)tile_ctas(c, b, RAY_TILE));
-  k_rays<<<grid, RAY_THREADS, sm, s>>>(*b, w, c->c);
+  kern<<<grid, RAY_THREADS, sm, s>>>(*b, w, c->c);
   c->c.launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1888,9 +1899,10 @@ static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   int wpb = WIN_WARPS;
   while (wpb > 1 && per_warp * wpb + 64 > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb + 64;
-  if (set_smem(k_windows, sm, c->max_smem)) return 1;
+  auto kern = w.atom_scratch ? k_windows<true> : k_windows<false>;
+  if (set_smem(kern, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
-  k_windows<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, sm, s>>>(*b, w);
+  kern<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, sm, s>>>(*b, w);
   k_finish<<<(b->n_items + 255) / 256, 256, 0, s>>>(*b, w);
   c->c.launches += 2;
   CK(cudaGetLastError());
