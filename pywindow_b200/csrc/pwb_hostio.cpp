@@ -16,6 +16,9 @@
 #include <atomic>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -43,12 +46,12 @@ inline bool is_digit(char c) { return (unsigned char)(c - '0') < 10; }
 // exponent -> mantissa < 2^53 and |exp10| <= 22 + 4, i.e. Clinger's exact case, one correctly rounded multiply or
 // divide.  Returns nullptr if the token does not have exactly this shape (the generic parser takes over).
 inline const char* parse_e4(const char* p, const char* end, double* out) {
-  if (end - p < 11) return nullptr;
+  if (end - p < 12) return nullptr;
   const bool neg = *p == '-';
   if (neg || *p == '+') p++;
   if (!(is_digit(p[0]) && p[1] == '.' && is_digit(p[2]) && is_digit(p[3]) && is_digit(p[4]) && is_digit(p[5]) &&
         (p[6] == 'E' || p[6] == 'e') && (p[7] == '-' || p[7] == '+') && is_digit(p[8]) && is_digit(p[9]))) return nullptr;
-  if (p + 10 < end && !(p[10] == ' ' || p[10] == '\n' || p[10] == '\r' || p[10] == '\t')) return nullptr;
+  if (!(p[10] == ' ' || p[10] == '\n' || p[10] == '\r' || p[10] == '\t')) return nullptr;
   const uint64_t mant = (uint64_t)(p[0] - '0') * 10000 + (p[2] - '0') * 1000 + (p[3] - '0') * 100 + (p[4] - '0') * 10 + (p[5] - '0');
   int e = (p[8] - '0') * 10 + (p[9] - '0');
   e = (p[7] == '-' ? -e : e) - 4;
@@ -57,6 +60,18 @@ inline const char* parse_e4(const char* p, const char* end, double* out) {
   v = e < 0 ? v / kPow10[-e] : v * kPow10[e];
   *out = neg ? -v : v;
   return p + 10;
+}
+
+// number of line feeds in [p, p + n)
+inline int64_t count_newlines(const char* p, int64_t n) {
+  int64_t nl = 0, i = 0;
+#if defined(__SSE2__)
+  const __m128i lf = _mm_set1_epi8('\n');
+  for (; i + 16 <= n; i += 16)
+    nl += __builtin_popcount((unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i)), lf)));
+#endif
+  for (; i < n; i++) nl += p[i] == '\n';
+  return nl;
 }
 
 // parse one floating point token starting at p (leading blanks skipped); returns pointer past it
@@ -229,34 +244,82 @@ int64_t pwb_history_index(const char* buf, int64_t len, int64_t* starts, int64_t
 // (trajectory.py:723-726).  Returns 0, or 1 + index of the first malformed frame.
 int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
                            int natoms, int keytrj, int imcon, double* xyz, double* lattice, int threads) {
+  // generic decoder of one frame: walks the lines; optionally records where every coordinate token starts and
+  // where every line of the frame ends (relative to the frame start) -- the TEMPLATE of a fixed-width file
+  auto generic = [&](int64_t f, std::vector<int32_t>* tok, std::vector<int32_t>* eol) -> bool {
+    const char* p0 = buf + starts[f];
+    const char* p = p0;
+    const char* end = buf + (ends[f] <= len ? ends[f] : len);
+    bool ok = true;
+    auto line_done = [&](const char* q) { if (eol) eol->push_back((int32_t)(q - p0)); };
+    p = skip_line(p, end); line_done(p);                     // "timestep ..." record
+    if (imcon >= 1 && imcon <= 3) {
+      double m[9];
+      for (int r = 0; r < 3 && ok; r++) {
+        for (int c = 0; c < 3 && ok; c++) p = parse_double(p, end, &m[3 * r + c], &ok);
+        p = skip_line(p, end); line_done(p);
+      }
+      if (lattice)
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) lattice[f * 9 + 3 * r + c] = m[3 * c + r];
+    }
+    double* o = xyz + (size_t)f * natoms * 3;
+    for (int a = 0; a < natoms && ok; a++) {
+      p = skip_line(p, end); line_done(p);                   // atom key / index / mass / charge
+      for (int c = 0; c < 3 && ok; c++) {
+        while (p < end && (*p == ' ' || *p == '\t')) p++;
+        if (tok) tok->push_back((int32_t)(p - p0));
+        p = parse_double(p, end, &o[3 * a + c], &ok);
+      }
+      p = skip_line(p, end); line_done(p);
+      for (int k = 0; k < keytrj; k++) { p = skip_line(p, end); line_done(p); }
+      if (p > end) ok = false;
+    }
+    return ok;
+  };
+  // Template of the first frame, if the file looks fixed width (all requested frames have its byte length and its
+  // coordinate tokens have the %12.4E shape): every other frame is decoded by reading the 3*natoms tokens at the
+  // template's offsets -- no line scanning.  A frame qualifies only if a newline sits at every line end of the
+  // template, nowhere else between them... (checked per token: the byte before a token is blank and parse_e4
+  // accepts exactly 10-11 characters followed by a blank or newline) -- anything else takes the generic path.
+  std::vector<int32_t> tok, eol;
+  bool templ = false;
+  const bool lat_templ = !(imcon >= 1 && imcon <= 3);      // lattice rows are parsed generically (rarely %12.4E)
+  if (n > 1 && ends[0] - starts[0] < (int64_t)1 << 30) {
+    std::vector<double> scratch;
+    templ = generic(0, &tok, &eol) && (int)tok.size() == 3 * natoms;
+    if (templ) {
+      const char* p0 = buf + starts[0];
+      double v;
+      for (size_t i = 0; i < tok.size() && templ; i++) templ = parse_e4(p0 + tok[i], buf + ends[0], &v) != nullptr;
+      templ = templ && !eol.empty() && eol.back() == ends[0] - starts[0];
+    }
+  }
+  const int64_t flen = templ ? ends[0] - starts[0] : 0;
   std::atomic<int64_t> next(0), bad(0);
   auto work = [&]() {
     while (true) {
       const int64_t f = next.fetch_add(1);
       if (f >= n) break;
-      const char* p = buf + starts[f];
-      const char* end = buf + (ends[f] <= len ? ends[f] : len);
-      bool ok = true;
-      p = skip_line(p, end);                                   // "timestep ..." record
-      if (imcon >= 1 && imcon <= 3) {
-        double m[9];
-        for (int r = 0; r < 3 && ok; r++) {
-          for (int c = 0; c < 3 && ok; c++) p = parse_double(p, end, &m[3 * r + c], &ok);
-          p = skip_line(p, end);
+      bool done = false;
+      if (templ && f > 0 && ends[f] - starts[f] == flen && ends[f] <= len && lat_templ) {
+        const char* p0 = buf + starts[f];
+        const char* end = p0 + flen;
+        double* o = xyz + (size_t)f * natoms * 3;
+        bool ok = true;
+        for (size_t i = 0; i < eol.size() && ok; i++) ok = p0[eol[i] - 1] == '\n';
+        for (size_t i = 0; i < tok.size() && ok; i++) {
+          const char* t = p0 + tok[i];
+          ok = (t[-1] == ' ' || t[-1] == '\n') && parse_e4(t, end, &o[i]) != nullptr;
         }
-        if (lattice)
-          for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) lattice[f * 9 + 3 * r + c] = m[3 * c + r];
+        // the tokens and line ends sit where the template has them; what lies between them must not hold another
+        // line break (a shorter record followed by junk): count the newlines of the frame
+        if (ok) {
+          ok = count_newlines(p0, flen) == (int64_t)eol.size();
+        }
+        done = ok;
       }
-      double* o = xyz + (size_t)f * natoms * 3;
-      for (int a = 0; a < natoms && ok; a++) {
-        p = skip_line(p, end);                                 // atom key / index / mass / charge
-        for (int c = 0; c < 3 && ok; c++) p = parse_double(p, end, &o[3 * a + c], &ok);
-        p = skip_line(p, end);
-        for (int k = 0; k < keytrj; k++) p = skip_line(p, end);
-        if (p > end) ok = false;
-      }
-      if (!ok) { int64_t z = 0; bad.compare_exchange_strong(z, f + 1); }
+      if (!done && !generic(f, nullptr, nullptr)) { int64_t z = 0; bad.compare_exchange_strong(z, f + 1); }
     }
   };
   int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();

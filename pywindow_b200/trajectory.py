@@ -498,7 +498,9 @@ class Trajectory:
             return np.zeros((0, eng.rec_stride)), RecordKeys.single([])
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
         B = max(1, self.batch_frames)
-        chunks = [frames[s:s + B] for s in range(0, len(frames), B)]
+        # a short first batch gets the GPU going after 1/8 of a batch's decode time; the rest are full batches
+        head = min(B, max(256, B // 8)) if len(frames) > B else B
+        chunks = [frames[:head]] + [frames[s:s + B] for s in range(head, len(frames), B)]
         threads = _host_threads()
         pipe = eng.frame_pipeline(elements, B, slots=2, **gpu_kwargs)
         nslots = len(pipe.slots)
