@@ -580,6 +580,12 @@ def run_ours(args):
                 t0 = time.perf_counter()
                 traj._decode_into(list(range(nd)), buf, _host_threads())
                 dec = nd / (time.perf_counter() - t0)
+                mm, view = traj._mapped()                       # the host's plain streaming rate over the same bytes
+                nbytes = int(traj.trajectory_map.pairs[nd - 1, 1])
+                t0 = time.perf_counter()
+                eng.lib.pwb_stream_probe(view.ctypes.data, nbytes, _host_threads())
+                stream_gbs = nbytes / (time.perf_counter() - t0) / 1e9
+                dec_gbs = dec * (size / n_api) / 1e9
                 api = {"value": n_api / total, "unit": "frames/s", "frames": n_api, "scaling": "strong", "n_gpus": world,
                        "call": "pywindow_b200.DLPOLY(path).analysis(forcefield='DLF')  (file -> analysis_output)",
                        "seconds": {"total": total, "map_file": t_map, "analysis": t_an},
@@ -588,9 +594,12 @@ def run_ours(args):
                                 "(the layout of the reference's HISTORY_singlemol_short)"},
                        "frames_analysed": len(keys), "frames_with_4_windows": n4,
                        "host_decode_frames_per_s": dec, "host_threads": _host_threads(),
+                       "host_decode_GBps": dec_gbs, "host_stream_GBps": stream_gbs,
                        "pools": "pinned / device buffers warm from an earlier analysis() in this process (engine pool)",
-                       "limit": "host side: text decode of the HISTORY file (host_decode_frames_per_s, all host "
-                                "threads of the rank) runs beside the GPU; ranks of one node share the host cores"}
+                       "limit": "host memory: the text of the HISTORY file (13.5 KB per frame) has to be streamed once; the "
+                                "decoder (host_decode_GBps, all host threads of the rank, overlapped with the GPU) "
+                                "runs at about the rate at which the same threads can merely count the line feeds of "
+                                "the mapped file (host_stream_GBps); ranks of one node share the host cores"}
             del traj
         finally:
             barrier()

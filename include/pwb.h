@@ -225,6 +225,10 @@ int64_t pwb_xyz_decode(const char* buf, int64_t len, const int64_t* starts, cons
 int64_t pwb_pdb_decode(const char* buf, int64_t len, const int64_t* starts, const int64_t* ends, int64_t n,
                        int natoms, double* xyz, int threads);
 
+/* Measurement utility: line feeds of a mapped file counted by `threads` host threads -- the host's plain streaming
+ * rate over the file, the ceiling of any text decoder (bench.py: api.host_stream_GBps).                       */
+int64_t pwb_stream_probe(const char* buf, int64_t len, int threads);
+
 /* Writer of the same HISTORY layout (keytrj 0; imcon 0 or 3): the synthetic trajectories of bench.py / tests that
  * feed the reference's DLPOLY reader and pwb_history_decode alike.  keys: natoms x 8 blank-padded characters;
  * lattice NULL | [9] | [n_frames][9] row-major (written transposed, as trajectory.py:723-726 reads it); coordinates

@@ -29,7 +29,7 @@ EXPORTS = [
     "pwb_opt_pore", "pwb_ray_search", "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch",
     "pwb_full_analysis_host", "pwb_full_analysis_host_async", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
     "pwb_dm_workspace_layout", "pwb_discrete_molecules", "pwb_dm_compact", "pwb_set_error", "pwb_history_index",
-    "pwb_history_decode", "pwb_xyz_index", "pwb_xyz_decode", "pwb_pdb_decode", "pwb_history_write",
+    "pwb_history_decode", "pwb_xyz_index", "pwb_xyz_decode", "pwb_pdb_decode", "pwb_history_write", "pwb_stream_probe",
 ]
 
 
@@ -106,6 +106,8 @@ def load():
     for name in ("pwb_xyz_decode", "pwb_pdb_decode"):
         getattr(L, name).argtypes = [vp, i64, vp, vp, i64, ci, vp, ci]
         getattr(L, name).restype = i64
+    L.pwb_stream_probe.argtypes = [vp, i64, ci]
+    L.pwb_stream_probe.restype = i64
     L.pwb_history_write.argtypes = [ctypes.c_char_p, ctypes.c_char_p, vp, vp, vp, i64, ci, vp, ci, ci, ci]
     L.pwb_history_write.restype = i64
     L.pwb_fma_peak.argtypes = [vp, ci, vp, ctypes.POINTER(ctypes.c_double)]
