@@ -319,6 +319,13 @@ template <int G> __device__ __forceinline__ ValIdx group_vi_min(unsigned mask, V
   return r;
 }
 
+// |d|^2 with a FIXED operation order (one product, two FMAs): left to the compiler, the contraction of
+// dx*dx + dy*dy + dz*dz depends on the surrounding code and two instantiations of the same source can differ in the
+// last bit -- enough to send the chaotic pore-centre search elsewhere.
+__device__ __forceinline__ double sq3(double dx, double dy, double dz) {
+  return __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+}
+
 struct GroupAtoms {
   const double4* p;      // [n] x, y, z, vdW radius of the type-bucketed atoms (shared or global memory)
   int n, gl;             // atoms, lane index inside the group
@@ -355,7 +362,61 @@ __device__ __forceinline__ void group_min_clear(const GroupAtoms& A, const doubl
 #pragma unroll
         for (int k = 0; k < K; k++) {
           double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
-          m[k] = dmin(m[k], dx * dx + dy * dy + dz * dz);
+          m[k] = dmin(m[k], sq3(dx, dy, dz));
+        }
+      }
+      const int slot = (c - c0) * K;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const double red = group_min_nonneg<G>(A.mask, m[k]);
+        if (A.gl == slot + k) mine = red;
+      }
+    }
+    double v = PWB_INF;
+    if (mine < PWB_INF) v = sqrt(mine) - A.p[A.cls[c0 + A.gl / K]].w;
+#pragma unroll
+    for (int s = K; s < G; s <<= 1) v = dmin(v, __shfl_xor_sync(A.mask, v, s, G));
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = dmin(out[k], __shfl_sync(A.mask, v, k, G));
+  }
+}
+
+// The same with EXACT pruning against a reference evaluation.  a(p) = min_i(|x_i - p| - r_i) is 1-Lipschitz, so for a
+// point within delta of a reference point p_ref the minimiser j obeys |x_j - p_ref| <= a(p_ref) + r_j + 2 delta;
+// every other atom is provably not the minimum and is skipped after ONE comparison of its stored reference distance
+// (squared, float, rounded down) with the class threshold (rounded up).  The surviving atoms are evaluated with the
+// unchanged arithmetic, so the result is bit-identical to group_min_clear.  `store`: evaluate all atoms (thr = inf)
+// and record their squared distances to point 0 as the new reference.  In a line search the trial points crowd
+// around the iterate: ~90 % of the atoms drop out.
+template <int G, int K>
+__device__ __forceinline__ void group_min_clear_pruned(const GroupAtoms& A, const double* px, const double* py,
+                                                       const double* pz, double* out, float* d2ref, double thr_base,
+                                                       bool store) {
+  static_assert(G >= K && (G % K) == 0, "a pass must hold at least one class");
+  constexpr int CPG = G / K;
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = PWB_INF;
+  for (int c0 = 0; c0 < A.ncls; c0 += CPG) {
+    double mine = PWB_INF;
+    const int cend = min(A.ncls, c0 + CPG);
+    for (int c = c0; c < cend; c++) {
+      const int cb = A.cls[c], ce = A.cls[c + 1];
+      if (cb == ce) continue;
+      const double rc = A.p[cb].w;
+      const double th = thr_base + rc;
+      const float thr2 = store ? 3.0e38f : __double2float_ru(th * th);
+      double m[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = PWB_INF;
+      for (int t = cb + A.gl; t < ce; t += G) {
+        if (!store && d2ref[t] > thr2) continue;
+        const double4 q = A.p[t];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+          const double d2 = sq3(dx, dy, dz);
+          if (k == 0 && store) d2ref[t] = __double2float_rd(d2);
+          m[k] = dmin(m[k], d2);
         }
       }
       const int slot = (c - c0) * K;

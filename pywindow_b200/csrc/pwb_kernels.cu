@@ -377,7 +377,18 @@ constexpr int OPT_WARPS = 4;
 #endif
 // doubles of shared memory per problem: double4[NA] atoms (optional), the solver state (incl. bounds), class
 // starts (17 ints, padded to 20); even, so that the double4 tiles stay 16-byte aligned
-#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) ((((SMEM_ATOMS) ? (NA) * 4 : 0) + LB_STORAGE(3) + 10 + 1) & ~(size_t)1)
+// Exact Lipschitz pruning of the objective's atom loop (group_min_clear_pruned): bit-identical records, ~95 % of the
+// atoms skipped in late line-search steps -- and NO change in kernel time (1.956 vs 1.964 ms per 10 000 frames,
+// profiles/r2_opt_pore_variants.md): the kernel is bound by the dependent chain of the solver's bookkeeping, not by
+// the objective.  Kept as an experiment switch, off by default (it costs 0.7 KB of shared memory per problem).
+#ifndef OPT_PRUNE
+#define OPT_PRUNE 0
+#endif
+#ifndef OPT_PRUNE_RBIG
+#define OPT_PRUNE_RBIG 0.5           // re-reference when two consecutive evaluations lie farther than this (A)
+#endif
+// (+ with OPT_PRUNE: reference point [3], its clearance, and float[NA] reference squared distances)
+#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) ((((SMEM_ATOMS) ? (NA) * 4 : 0) + LB_STORAGE(3) + 10 + (OPT_PRUNE ? 4 + ((NA) + 1) / 2 : 0) + 1) & ~(size_t)1)
 
 template <int G, bool GENERAL, bool ATOMS_SMEM>
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)
@@ -391,6 +402,11 @@ k_opt_pore(pwb_batch b, Ws ws) {
   double4* p4 = (double4*)smp;                                        // x, y, z, radius (if ATOMS_SMEM)
   double* hist = smp + (ATOMS_SMEM ? (size_t)b.max_atoms * 4 : 0);    // [LB_STORAGE(3)] solver state
   int* cls = (int*)(hist + LB_STORAGE(3));                            // [PWB_MAX_TYPES+1] class starts
+#if OPT_PRUNE
+  double* pref = (double*)(cls + 20);                                 // [4] reference point and its clearance
+  float* d2ref = (float*)(pref + 4);                                  // [NA] squared distances to the reference point
+  bool have_ref = false, last_far = false;
+#endif
   int* queue = ws.item_i + I_QUEUE;                                   // zeroed by run_opt before the launch
   LbSolver<3, GENERAL ? -1 : 2> S;
   S.st = hist;
@@ -460,6 +476,9 @@ k_opt_pore(pwb_batch b, Ws ws) {
             if (gl == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
           } else if (search) {
             S.init(hist, c, lo3, hi3, nb3);
+#if OPT_PRUNE
+            have_ref = false; last_far = false;
+#endif
             __syncwarp(mask);
             active = true;
           } else {     // forced centre: parked where a finished search leaves its result
@@ -486,7 +505,36 @@ k_opt_pore(pwb_batch b, Ws ws) {
 #pragma unroll
       for (int i = 0; i < 3; i++) h[i] = lb_fd_step(x[i], S.nbd(i), S.lo()[i], S.hi()[i]);
       px[1] = x[0] + h[0]; py[2] = x[1] + h[1]; pz[3] = x[2] + h[2];
+#if OPT_PRUNE
+      {
+        // distance of this evaluation's stencil from the reference point (+ the forward-difference steps)
+        const double ex = x[0] - pref[0], ey = x[1] - pref[1], ez = x[2] - pref[2];
+        const double delta = sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-12) + 4e-8;
+        const bool far = !(delta <= OPT_PRUNE_RBIG);
+        const bool store = !have_ref || (far && last_far);     // two far evaluations in a row: the search has moved
+        last_far = far && !store;
+        __syncwarp(mask);
+        group_min_clear_pruned<G, 4>(A, px, py, pz, m, d2ref, store ? 0.0 : pref[3] + 2.0 * delta, store);
+#ifdef OPT_PRUNE_CHECK
+        {
+          double m2[4];
+          group_min_clear<G, 4>(A, px, py, pz, m2);
+          if (m2[0] != m[0] || m2[1] != m[1] || m2[2] != m[2] || m2[3] != m[3]) {
+            if (gl == 0) printf("prune mismatch item %d store %d delta %.3e aref %.6f m %.17g %.17g m2 %.17g %.17g\n", item, (int)store, delta, pref[3], m[0], m[1], m2[0], m2[1]);
+          }
+        }
+#endif
+        if (store) {
+          __syncwarp(mask);
+          if (gl < 3) pref[gl] = x[gl];
+          if (gl == 3) pref[3] = m[0];
+          have_ref = true;
+        }
+        __syncwarp(mask);
+      }
+#else
       group_min_clear<G, 4>(A, px, py, pz, m);
+#endif
       nfev += 4;
       const double f = -(m[0] * 2.0);
       double* g = S.gs();
