@@ -11,7 +11,7 @@ def num(r, key):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u, 1)
 res = {}
 for r in rows[2:]:
-    name = r[h.index("Kernel Name")].split("(")[0].split("::")[-1]
+    name = r[h.index("Kernel Name")].split("(")[0].split("::")[-1].split("<")[0].replace("void ", "").strip()
     b = num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")
     e = res.setdefault(name, {"bytes_per_launch": 0.0, "frames_per_launch": frames, "duration_ms_under_ncu": 0.0,
                               "launches_summed": 0, "source": os.path.basename(rep)})
