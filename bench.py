@@ -613,7 +613,7 @@ def run_ours(args):
         path4 = os.path.join(d, f"pwb_bench_{tag}_cells.HISTORY")
         if rank == 0:
             Xc = synthetic.noisy_frames(gp["coords"][None], 0, n_cells, decimals=3)
-            size4 = synthetic.write_history_native(path4, [str(e) + "1" for e in gp["elements"]], Xc, lattice=lat)
+            size4 = synthetic.write_history_native(path4, [str(e) + "1" for e in gp["elements"]], Xc, lattice=lat, compact=True)
             del Xc
         barrier()
         try:

@@ -338,10 +338,42 @@ struct GroupAtoms {
 // sqrt scheme as warp_min_clear_rs (bit-identical results for every G): the squared distances of (class c, point
 // k) are reduced over the group, parked in group lane (c - c0)*K + k, rooted once, and a stride-K butterfly
 // finishes the min over the G/K classes of a pass.
+// G < K (one or two lanes per problem): every lane walks its share of each class and the class minima are combined
+// with plain shuffles -- same values, same reduce-before-sqrt order.
+template <int G, int K>
+__device__ __forceinline__ void group_min_clear_narrow(const GroupAtoms& A, const double* px, const double* py,
+                                                       const double* pz, double* out) {
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = PWB_INF;
+  for (int c = 0; c < A.ncls; c++) {
+    const int cb = A.cls[c], ce = A.cls[c + 1];
+    if (cb == ce) continue;
+    double m[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) m[k] = PWB_INF;
+    for (int t = cb + A.gl; t < ce; t += G) {
+      const double4 q = A.p[t];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+        m[k] = dmin(m[k], sq3(dx, dy, dz));
+      }
+    }
+    const double rc = A.p[cb].w;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+#pragma unroll
+      for (int s = 1; s < G; s <<= 1) m[k] = dmin(m[k], __shfl_xor_sync(A.mask, m[k], s, G));
+      out[k] = dmin(out[k], sqrt(m[k]) - rc);
+    }
+  }
+}
+
 template <int G, int K>
 __device__ __forceinline__ void group_min_clear(const GroupAtoms& A, const double* px, const double* py,
                                                 const double* pz, double* out) {
-  static_assert(G >= K && (G % K) == 0, "a pass must hold at least one class");
+  if constexpr (G < K) { group_min_clear_narrow<G, K>(A, px, py, pz, out); return; }
+  static_assert(G < K || (G % K) == 0, "a pass must hold at least one class");
   constexpr int CPG = G / K;
 #pragma unroll
   for (int k = 0; k < K; k++) out[k] = PWB_INF;

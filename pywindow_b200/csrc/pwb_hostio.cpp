@@ -284,7 +284,7 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
   // accepts exactly 10-11 characters followed by a blank or newline) -- anything else takes the generic path.
   std::vector<int32_t> tok, eol;
   bool templ = false;
-  const bool lat_templ = !(imcon >= 1 && imcon <= 3);      // lattice rows are parsed generically (rarely %12.4E)
+  const bool has_lat = imcon >= 1 && imcon <= 3;           // lattice rows are always parsed generically
   if (n > 1 && ends[0] - starts[0] < (int64_t)1 << 30) {
     std::vector<double> scratch;
     templ = generic(0, &tok, &eol) && (int)tok.size() == 3 * natoms;
@@ -302,11 +302,22 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
       const int64_t f = next.fetch_add(1);
       if (f >= n) break;
       bool done = false;
-      if (templ && f > 0 && ends[f] - starts[f] == flen && ends[f] <= len && lat_templ) {
+      if (templ && f > 0 && ends[f] - starts[f] == flen && ends[f] <= len) {
         const char* p0 = buf + starts[f];
         const char* end = p0 + flen;
         double* o = xyz + (size_t)f * natoms * 3;
         bool ok = true;
+        if (has_lat) {
+          const char* p = skip_line(p0, end);
+          double m[9];
+          for (int r = 0; r < 3 && ok; r++) {
+            for (int c = 0; c < 3 && ok; c++) p = parse_double(p, end, &m[3 * r + c], &ok);
+            p = skip_line(p, end);
+          }
+          if (ok && lattice)
+            for (int r = 0; r < 3; r++)
+              for (int c = 0; c < 3; c++) lattice[f * 9 + 3 * r + c] = m[3 * c + r];
+        }
         for (size_t i = 0; i < eol.size() && ok; i++) ok = p0[eol[i] - 1] == '\n';
         for (size_t i = 0; i < tok.size() && ok; i++) {
           const char* t = p0 + tok[i];

@@ -371,7 +371,10 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 #ifndef OPT_ATOMS_SMEM
 #define OPT_ATOMS_SMEM 0             // atom tile of each problem in shared memory (else read through L1 / L2)
 #endif
-constexpr int OPT_WARPS = 4;
+#ifndef OPT_WARPS_N
+#define OPT_WARPS_N 4
+#endif
+constexpr int OPT_WARPS = OPT_WARPS_N;
 #ifndef OPT_MINB
 #define OPT_MINB 6                   // CTAs per SM the register budget must allow (80 registers per thread)
 #endif

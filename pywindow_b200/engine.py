@@ -279,6 +279,16 @@ class Engine:
         flat = np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 3) for _, c in mols])
         return self.analyse(flat, off, types, vdw, mass, shared_types=False, max_atoms=max(sizes), **kw)
 
+    def pinned(self, key, shape, dtype=torch.float64):
+        """Pooled pinned host tensor for ``key`` (grown, never shrunk): page-locking a few hundred MB costs more than
+        analysing the frames they hold, and pageable copies run at a fifth of the PCIe rate."""
+        k = ("pinned",) + tuple(key)
+        t = self._pinned.get(k)
+        need = int(np.prod(shape))
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = self._pinned[k] = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+        return t[:need].view(*shape)
+
     def frame_pipeline(self, elements, cap_frames, ray_cap=0, slots=2, **params):
         """:class:`FramePipeline` bound to this engine (the trajectory front-ends' entry point).  Pipelines are
         pooled: a later trajectory of the same molecule, batch size and parameters reuses the pinned / device buffers

@@ -344,7 +344,8 @@ class AnalysisOutput(dict):
 class Trajectory:
     """Shared machinery: frame selection, batched GPU analysis, result storage."""
 
-    batch_frames = 16384
+    batch_frames = 16384          # molecule-frames per GPU batch of the single-molecule path
+    modular_batch_cells = 2048    # cell-frames per GPU batch of the modular (periodic) path
 
     def __init__(self, filepath):
         self.filepath = pathlib.Path(filepath)
@@ -542,21 +543,36 @@ class Trajectory:
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
         recs, kf, km = [], [], []
         # cells per batch: the flood fill runs one warp per cell and is bound by memory latency, so it wants
-        # thousands of cells in flight (8 192 PUDXES cells: 264 MB of coordinates, ~3 GB of pooled workspace)
-        step = max(1, min(8192, (1 << 24) // max(1, len(elements))))
-        for s in range(0, len(frames), step):
-            chunk = frames[s:s + step]
-            coords, lattice = self._decode_cells(chunk)
-            if rebuild and lattice is None:
-                raise _TrajectoryError("rebuild=True needs periodic frames (no lattice / CRYST1 record found)")
-            r, (fi, mi), _ = analyse_cells(coords, elements, lattice=lattice, rebuild=rebuild, engine=eng, key_arrays=True,
-                                           **gpu_kwargs)
-            recs.append(r)
-            kf.append(np.asarray(chunk, dtype=np.int64)[fi])
-            km.append(mi)
+        # thousands of cells in flight; batch k+1 is decoded on a helper thread (the C++ decoder and the GPU calls
+        # both release the GIL) while batch k is on the GPU
+        step = max(1, min(self.modular_batch_cells, (1 << 24) // max(1, len(elements))))
+        chunks = [frames[s:s + step] for s in range(0, len(frames), step)]
+        from concurrent.futures import ThreadPoolExecutor
+        N = len(elements)
+        slots = [eng.pinned(("cells", i), (step, N, 3)) for i in range(2)]      # decoded straight into pinned memory
+
+        def decode(k):
+            dst = slots[k % 2][:len(chunks[k])]
+            xyz, lat = self._decode_cells(chunks[k], out=dst.numpy())
+            # (a format class without an in-place native decoder returns its own array)
+            return (dst if np.shares_memory(xyz, dst.numpy()) else xyz), lat
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(decode, 0)
+            for k, chunk in enumerate(chunks):
+                coords, lattice = pending.result()
+                if k + 1 < len(chunks):
+                    pending = pool.submit(decode, k + 1)
+                if rebuild and lattice is None:
+                    raise _TrajectoryError("rebuild=True needs periodic frames (no lattice / CRYST1 record found)")
+                r, (fi, mi), _ = analyse_cells(coords, elements, lattice=lattice, rebuild=rebuild, engine=eng,
+                                               key_arrays=True, **gpu_kwargs)
+                recs.append(r)
+                kf.append(np.asarray(chunk, dtype=np.int64)[fi])
+                km.append(mi)
         return np.concatenate(recs), RecordKeys(np.concatenate(kf), np.concatenate(km))
 
-    def _decode_cells(self, frames):
+    def _decode_cells(self, frames, out=None):  # noqa: ARG002  (format classes with a native decoder fill `out`)
         """([F,N,3] coordinates, [F,3,3] lattices | None) for the requested frames."""
         coords, lats = None, []
         with self.filepath.open("rb") as fh, mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) as mm:
@@ -669,8 +685,8 @@ class DLPOLY(Trajectory):
     def _decode_into(self, frames, out, threads=0):
         self._native_decode(frames, False, out=out, threads=threads)
 
-    def _decode_cells(self, frames):
-        return self._native_decode(frames, True)
+    def _decode_cells(self, frames, out=None):
+        return self._native_decode(frames, True, out=out)
 
     def _layout(self, lines):
         info = lines[0].split()
