@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
-#include <emmintrin.h>
+#include <immintrin.h>
 #endif
 
 namespace {
@@ -62,13 +62,107 @@ inline const char* parse_e4(const char* p, const char* end, double* out) {
   return p + 10;
 }
 
+// The same record read from its END, for the template decoder below: e points one past the last exponent digit.  In
+// a fixed-width file the numbers are right aligned, so every token ends where the template frame has it whatever the
+// sign.  The frame's SHAPE has been checked byte by byte against the template before (frame_shape_ok: digits where
+// digits belong, '.', 'E', blanks and line ends in place, sign bytes within [' ', '-'] and ['+', '-']); what is left
+// here is the exact test of the two sign bytes, the exponent range and the conversion -- branch free, `bad`
+// accumulates and the caller tests it once per frame.
+// value = (mantissa * kMul10[k]) / kDiv10[k], k = exp10 + 26: one of the two factors is 1, so there is exactly one
+// rounding (Clinger's exact case) and no branch on the sign of the exponent
+#define P10_ONES_26 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1
+const double kDiv10[64] = {1e26, 1e25, 1e24, 1e23, 1e22, 1e21, 1e20, 1e19, 1e18, 1e17, 1e16, 1e15, 1e14, 1e13, 1e12, 1e11,
+                           1e10, 1e9, 1e8, 1e7, 1e6, 1e5, 1e4, 1e3, 1e2, 1e1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                           1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+const double kMul10[64] = {P10_ONES_26, 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                           1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+inline unsigned parse_e4_end(const char* e, double* out) {
+  uint64_t w;
+  uint16_t ex;
+  memcpy(&w, e - 10, 8);                                        // "d.ddddE+"
+  memcpy(&ex, e - 2, 2);                                        // "dd"
+  const unsigned sg = (unsigned char)e[-11];                    // in [0x20, 0x2D]: ' ', '+', '-' are valid
+  const uint64_t x = w ^ 0x2B45303030302E30ull;                 // digits -> 0..9, '.', 'E', '+' -> 0, ',' -> 7, '-' -> 6
+  const unsigned s7 = (unsigned)(x >> 56);
+  unsigned bad = (s7 & 1u) | (~(0x2801u >> ((sg - 0x20u) & 15u)) & 1u);
+  const unsigned exd = ex ^ 0x3030u;
+  const uint64_t t = (x >> 16) & 0x0F0F0F0Full;                 // d2 d3 d4 d5
+  const uint64_t u = t * 10 + (t >> 8);                         // byte 0: d2 d3, byte 2: d4 d5
+  const uint64_t mant = (x & 0xF) * 10000 + (u & 0xFF) * 100 + ((u >> 16) & 0xFF);
+  const int ea = (int)((exd & 0xF) * 10 + (exd >> 8));
+  const int neg_e = -(int)(s7 >> 2);                            // s7 is 0 or 6 -> 0 or -1
+  const int e10 = ((ea ^ neg_e) - neg_e) - 4;                   // conditional negate without a branch
+  bad |= (unsigned)(e10 + 22) > 44u;
+  const unsigned k = (unsigned)(e10 + 26) & 63u;
+  const double v = ((double)(int64_t)mant * kMul10[k]) / kDiv10[k];
+  uint64_t bits;
+  memcpy(&bits, &v, 8);
+  bits |= (uint64_t)(sg == '-') << 63;                          // (v >= 0 here; "-0.0000E+00" -> -0.0 like float())
+  memcpy(out, &bits, 8);
+  return bad;
+}
+
+// lo[i] <= p[i] <= hi[i] for every byte of a frame (unsigned): 16 or 32 bytes per step
+inline bool frame_shape_ok_scalar(const unsigned char* p, const unsigned char* lo, const unsigned char* hi, int64_t i, int64_t n) {
+  unsigned bad = 0;
+  for (; i < n; i++) bad |= (unsigned)(p[i] < lo[i]) | (unsigned)(p[i] > hi[i]);
+  return bad == 0;
+}
+#if defined(__SSE2__)
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target("avx2"))) bool frame_shape_ok_avx2(const unsigned char* p, const unsigned char* lo,
+                                                         const unsigned char* hi, int64_t n) {
+  __m256i acc = _mm256_set1_epi8((char)0xFF);
+  int64_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    const __m256i v = _mm256_loadu_si256((const __m256i*)(p + i));
+    const __m256i l = _mm256_loadu_si256((const __m256i*)(lo + i)), h = _mm256_loadu_si256((const __m256i*)(hi + i));
+    acc = _mm256_and_si256(acc, _mm256_and_si256(_mm256_cmpeq_epi8(_mm256_max_epu8(v, l), v),
+                                                 _mm256_cmpeq_epi8(_mm256_min_epu8(v, h), v)));
+  }
+  return _mm256_movemask_epi8(acc) == -1 && frame_shape_ok_scalar(p, lo, hi, i, n);
+}
+#define PWB_HAVE_AVX2_DISPATCH 1
+#endif
+inline bool frame_shape_ok_sse2(const unsigned char* p, const unsigned char* lo, const unsigned char* hi, int64_t n) {
+  __m128i acc = _mm_set1_epi8((char)0xFF);
+  int64_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m128i v = _mm_loadu_si128((const __m128i*)(p + i));
+    const __m128i l = _mm_loadu_si128((const __m128i*)(lo + i)), h = _mm_loadu_si128((const __m128i*)(hi + i));
+    acc = _mm_and_si128(acc, _mm_and_si128(_mm_cmpeq_epi8(_mm_max_epu8(v, l), v), _mm_cmpeq_epi8(_mm_min_epu8(v, h), v)));
+  }
+  return _mm_movemask_epi8(acc) == 0xFFFF && frame_shape_ok_scalar(p, lo, hi, i, n);
+}
+#endif
+inline bool frame_shape_ok(const unsigned char* p, const unsigned char* lo, const unsigned char* hi, int64_t n) {
+#if defined(PWB_HAVE_AVX2_DISPATCH)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return frame_shape_ok_avx2(p, lo, hi, n);
+#endif
+#if defined(__SSE2__)
+  return frame_shape_ok_sse2(p, lo, hi, n);
+#else
+  return frame_shape_ok_scalar(p, lo, hi, 0, n);
+#endif
+}
+
 // number of line feeds in [p, p + n)
 inline int64_t count_newlines(const char* p, int64_t n) {
   int64_t nl = 0, i = 0;
 #if defined(__SSE2__)
-  const __m128i lf = _mm_set1_epi8('\n');
-  for (; i + 16 <= n; i += 16)
-    nl += __builtin_popcount((unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i)), lf)));
+  // compare 16 bytes at a time, keep per-byte counts (0xFF = -1 subtracted) and fold them with PSADBW before they
+  // can overflow: two instructions per 16 bytes, no popcount (the host compiler may not assume POPCNT)
+  const __m128i lf = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+  while (i + 16 <= n) {
+    __m128i acc = zero;
+    int64_t blocks = (n - i) / 16;
+    if (blocks > 255) blocks = 255;
+    for (int64_t b = 0; b < blocks; b++, i += 16)
+      acc = _mm_sub_epi8(acc, _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(p + i)), lf));
+    const __m128i sum = _mm_sad_epu8(acc, zero);
+    nl += _mm_cvtsi128_si64(sum) + _mm_cvtsi128_si64(_mm_unpackhi_epi64(sum, sum));
+  }
 #endif
   for (; i < n; i++) nl += p[i] == '\n';
   return nl;
@@ -279,10 +373,13 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
   };
   // Template of the first frame, if the file looks fixed width (all requested frames have its byte length and its
   // coordinate tokens have the %12.4E shape): every other frame is decoded by reading the 3*natoms tokens at the
-  // template's offsets -- no line scanning.  A frame qualifies only if a newline sits at every line end of the
-  // template, nowhere else between them... (checked per token: the byte before a token is blank and parse_e4
-  // accepts exactly 10-11 characters followed by a blank or newline) -- anything else takes the generic path.
+  // template's END offsets (right-aligned numbers end in the same column whatever their sign) -- no line scanning.
+  // A frame qualifies only if every byte lies in the range the template allows at its position: a newline at every
+  // line end and nowhere else, " [ +-]d.ddddE[+-]dd" + the template's own terminator around every token end, anything
+  // but a line break in between (frame_shape_ok; the sign bytes are tested exactly in parse_e4_end) -- any other frame
+  // takes the generic path.
   std::vector<int32_t> tok, eol;
+  std::vector<unsigned char> shape_lo, shape_hi;
   bool templ = false;
   const bool has_lat = imcon >= 1 && imcon <= 3;           // lattice rows are always parsed generically
   if (n > 1 && ends[0] - starts[0] < (int64_t)1 << 30) {
@@ -291,8 +388,36 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
     if (templ) {
       const char* p0 = buf + starts[0];
       double v;
-      for (size_t i = 0; i < tok.size() && templ; i++) templ = parse_e4(p0 + tok[i], buf + ends[0], &v) != nullptr;
+      for (size_t i = 0; i < tok.size() && templ; i++) {
+        const char* q = parse_e4(p0 + tok[i], buf + ends[0], &v);
+        templ = q != nullptr && tok[i] >= 2;
+        if (templ) tok[i] = (int32_t)(q - p0);              // from here on: where the token ENDS
+      }
       templ = templ && !eol.empty() && eol.back() == ends[0] - starts[0];
+      if (templ) {
+        const int64_t L = ends[0] - starts[0];
+        shape_lo.assign((size_t)L + 32, 0x0B);                // default: anything above '\n' (no stray line breaks)
+        shape_hi.assign((size_t)L + 32, 0xFF);
+        auto lit = [&](int64_t i, unsigned char c) { shape_lo[(size_t)i] = shape_hi[(size_t)i] = c; };
+        auto range = [&](int64_t i, unsigned char a, unsigned char b) { shape_lo[(size_t)i] = a; shape_hi[(size_t)i] = b; };
+        for (int32_t q : eol) lit(q - 1, '\n');
+        for (size_t i = 0; i < tok.size() && templ; i++) {
+          const int64_t e = tok[i];
+          const char term = p0[e], sg = p0[e - 11];
+          templ = e >= 12 && e < L && p0[e - 12] == ' ' && (sg == ' ' || sg == '-' || sg == '+') && p0[e - 4] == 'E';
+          if (!templ) break;
+          lit(e - 12, ' ');
+          range(e - 11, 0x20, 0x2D);
+          range(e - 10, '0', '9');
+          lit(e - 9, '.');
+          for (int k = 5; k <= 8; k++) range(e - k, '0', '9');
+          lit(e - 4, 'E');
+          range(e - 3, '+', '-');
+          range(e - 2, '0', '9');
+          range(e - 1, '0', '9');
+          lit(e, (unsigned char)term);                        // ' ' between tokens, the line end after the last
+        }
+      }
     }
   }
   const int64_t flen = templ ? ends[0] - starts[0] : 0;
@@ -318,15 +443,13 @@ int64_t pwb_history_decode(const char* buf, int64_t len, const int64_t* starts, 
             for (int r = 0; r < 3; r++)
               for (int c = 0; c < 3; c++) lattice[f * 9 + 3 * r + c] = m[3 * c + r];
         }
-        for (size_t i = 0; i < eol.size() && ok; i++) ok = p0[eol[i] - 1] == '\n';
-        for (size_t i = 0; i < tok.size() && ok; i++) {
-          const char* t = p0 + tok[i];
-          ok = (t[-1] == ' ' || t[-1] == '\n') && parse_e4(t, end, &o[i]) != nullptr;
-        }
-        // the tokens and line ends sit where the template has them; what lies between them must not hold another
-        // line break (a shorter record followed by junk): count the newlines of the frame
+        ok = ok && frame_shape_ok((const unsigned char*)p0, shape_lo.data(), shape_hi.data(), flen);
         if (ok) {
-          ok = count_newlines(p0, flen) == (int64_t)eol.size();
+          unsigned badtok = 0;
+          const int32_t* te = tok.data();
+          const size_t nt3 = tok.size();
+          for (size_t i = 0; i < nt3; i++) badtok |= parse_e4_end(p0 + te[i], &o[i]);
+          ok = badtok == 0;
         }
         done = ok;
       }

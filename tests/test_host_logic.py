@@ -160,6 +160,85 @@ def test_native_history_decoder_is_bit_exact(tmp_path):
     np.testing.assert_array_equal(t._decode_coordinates([3, 0]), xyz[[3, 0]])
 
 
+def test_fixed_width_template_decoder_and_its_fallbacks(tmp_path):
+    """DL_POLY's own %12.4E layout takes the template path of pwb_history_decode (tokens read at the END offsets of
+    frame 0, frame shape checked byte by byte).  Signs, '+' signs and exponents differ from frame 0; frames damaged
+    WITHOUT changing their length (a moved line break, a letter for a digit, ',' for the exponent sign, '!' for the
+    sign, a tab) must not be mis-read: they go to the generic parser, which decodes them like float() or reports them."""
+    from pywindow_b200.trajectory import DLPOLY, _TrajectoryError
+    rng = np.random.default_rng(5)
+    n, F = 23, 40
+    X = rng.normal(0, 8, size=(F, n, 3)) * 10.0 ** rng.integers(-6, 4, size=(F, n, 1))
+    X[0] = np.abs(X[0])                                        # the template frame has no minus sign at all
+    X[3, 2] = 0.0
+
+    def frame_text(f, x):
+        out = ["timestep %9d %9d %9d %9d %11.6f\n" % (f + 1, n, 0, 0, 0.001)]
+        for a in range(n):
+            out.append("%-8s%10d%12.6f%12.6f\n" % ("C%d" % (a % 3), a + 1, 12.011, 0.0))
+            out.append("%12.4E%12.4E%12.4E\n" % tuple(x[a]))
+        return "".join(out)
+
+    frames = [frame_text(f, X[f]) for f in range(F)]
+    frames[5] = frames[5].replace(" 0.", "+0.", 1) if " 0." in frames[5] else frames[5]
+    lens = {len(t) for t in frames}
+    assert len(lens) == 1
+    head = "title\n%10d%10d%10d\n" % (0, 0, n)
+
+    def decode(fr):
+        path = tmp_path / "HISTORY"
+        path.write_text(head + "".join(fr))
+        t = DLPOLY(path)
+        ref = [t._decode_frame(t._frame_bytes(f))["coordinates"] for f in range(len(fr))] if fr is frames else None
+        return t._decode_coordinates(list(range(len(fr)))), ref
+
+    xyz, ref = decode(frames)
+    for f in range(F):
+        np.testing.assert_array_equal(xyz[f], ref[f])           # bit-identical to float(), -0.0 included
+    assert (np.signbit(xyz) == np.signbit(np.array(ref))).all()
+
+    def damaged(f, old, new, which=3):
+        """same-length replacement inside coordinate line `which` of frame f"""
+        lines = frames[f].split("\n")
+        k = 2 * which + 2
+        assert old in lines[k] and len(old) == len(new)
+        lines[k] = lines[k].replace(old, new, 1)
+        fr = list(frames)
+        fr[f] = "\n".join(lines)
+        return fr
+
+    for old, new in (("E+", "E,"), ("E-", "E,"), ("E", "F"), (".", ","), (" ", "!"), (" ", "\t")):
+        f = next(f for f in range(1, F) if old in frames[f].split("\n")[8] and (old != " " or frames[f].split("\n")[8][1] == " "))
+        fr = damaged(f, old, new) if old != " " else None
+        if fr is None:                                          # the sign column of the first token
+            lines = frames[f].split("\n"); lines[8] = " " + new + lines[8][2:]; fr = list(frames); fr[f] = "\n".join(lines)
+        if new == "\t":                                         # a tab is white space to float(): still decodes, equal
+            got, _ = decode(fr)
+            np.testing.assert_array_equal(got, xyz)
+        else:
+            with pytest.raises(_TrajectoryError):
+                decode(fr)
+    # a line break moved inside a header line: same length, same number of lines
+    fr = list(frames)
+    lines = fr[7].split("\n")
+    lines[3] = lines[3][:5] + "\n" + lines[3][5:-1]            # breaks the header in two, drops its last character
+    fr[7] = "\n".join(lines)
+    assert len(fr[7]) == len(frames[7])
+    path = tmp_path / "HISTORY"
+    path.write_text(head + "".join(fr))
+    t = DLPOLY(path)
+    try:
+        want = np.asarray(t._decode_frame(t._frame_bytes(7))["coordinates"], dtype=np.float64)   # line-based, like the reference
+    except Exception:
+        want = None
+    if want is None or want.shape != (n, 3):
+        with pytest.raises(_TrajectoryError):
+            t._decode_coordinates([0, 7])
+    else:
+        np.testing.assert_array_equal(t._decode_coordinates([0, 7])[1], want)
+        assert not np.array_equal(want, xyz[7])                 # (the shifted columns were not read silently)
+
+
 def test_direction_bin_formula_matches_atan2():
     """csrc/pwb_device.cuh:dg_bin locates the phi bin of a direction with three comparisons against tan(k pi/16)
     per quadrant instead of atan2; the restatement here must agree with floor((atan2(y, x) + pi) / (pi/16))."""

@@ -10,7 +10,8 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.environ.get("PWB_SO", os.path.join(root, "pywindow_b200", "csrc", "libpwb.so"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.startswith("pwb_kernels") and f.endswith(".cubin") and "periodic" not in f][0]
+unit = os.environ.get("PWB_CUBIN", "pwb_kernels")     # translation unit holding the kernel (pwb_kernels | pwb_periodic)
+cub = [f for f in os.listdir(tmp) if f.startswith(unit + ".") and f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
 lines, cur, infn, seq = dis.split("\n"), None, False, []
 for ln in lines:
