@@ -137,7 +137,7 @@ __device__ __forceinline__ void dm_pair_images(const DmArgs& A, const double (&L
         if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
           int ka = (int)ma + 4, kb = (int)mb + 4, kc = (int)mc + 4;
           if (ka < 0 || ka > 8 || kb < 0 || kb > 8 || kc < 0 || kc > 8) continue;   // > 4 cells away: unreachable
-          unsigned key = ((unsigned)(ka * 81 + kb * 9 + kc) << 20) | (unsigned)bb;
+          unsigned key = ((unsigned)((ka << 8) | (kb << 4) | kc) << 20) | (unsigned)bb;   // sorts like (ka, kb, kc)
           if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
         }
       }
@@ -317,7 +317,7 @@ k_dm_bonds(DmArgs A, double max_dist) {
         double dx = ax - sx[j], dy = ay - sy[j], dz = az - sz[j];
         double d = sqrt(dx * dx + dy * dy + dz * dz);
         if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
-          if (n < DM_ADJ_CAP) list[n++] = ((unsigned)(4 * 81 + 4 * 9 + 4) << 20) | (unsigned)bb; else overflow = 1;
+          if (n < DM_ADJ_CAP) list[n++] = ((unsigned)((4 << 8) | (4 << 4) | 4) << 20) | (unsigned)bb; else overflow = 1;
         }
         continue;
       }
@@ -334,36 +334,50 @@ k_dm_bonds(DmArgs A, double max_dist) {
 // atoms that are still unassigned (ascending index) and then its other bonded images (ascending supercell index),
 // the first occurrence of a node winning (utilities.py:985-1044, restated in oracle/pw_periodic_oracle.py).  Every
 // candidate therefore has the order key (parent rank, pass, adjacency slot) and a node goes to the candidate with
-// the SMALLEST key.  Parents are processed 32 at a time, one per lane: the lanes enter their candidates into a small
-// shared-memory hash table node -> min key (atomicMin), the winners are compacted in key order by a warp scan and
-// marked visited before the next 32 parents run, so later parents (larger keys) see them as taken.
+// the SMALLEST key.  Parents are processed 32 at a time, one per lane:
+//   1. each lane walks its parent's bond list ONCE: node id, pass, visited test; the survivors are cached in shared
+//      memory and entered into a small hash table node -> min key (atomicMin);
+//   2. the lanes look their candidates up again: the one whose key is in the table owns the node;
+//   3. the winners are compacted in key order by a warp scan -- straight into the output list, whose tail IS the
+//      next frontier (levels are contiguous in breadth-first order) -- and marked visited; every lane wipes the
+//      table slots it used.  Later parents (larger keys) see the winners as taken.
+// A node is (image << 20 | atom); its visited bit is image * N + atom.  With SMEM_STATE the visited bits and the
+// "still unassigned" bytes of the frame live in shared memory (4.4 bytes per atom and warp).
+#ifndef DM_FILL_STATE_SMEM_MAX
+#define DM_FILL_STATE_SMEM_MAX (56 * 1024)
+#endif
 constexpr int DM_FILL_WARPS = 4;
-constexpr int DM_HASH = 1024;                    // >= 32 parents x 24 candidate slots, power of two
+constexpr int DM_HASH = 512;                     // > 32 parents x 12 bond slots, power of two
+constexpr int DM_CAND_STRIDE = 13;               // per-lane row of the candidate cache (odd: no bank conflicts)
 constexpr unsigned DM_EMPTY = 0xffffffffu;
+constexpr int DM_FILL_FIXED_WORDS = 2 * DM_HASH + 32 * DM_CAND_STRIDE + 32 * DM_CAND_STRIDE / 2;
 
-__device__ __forceinline__ unsigned dm_hash_slot(unsigned node) { return (node * 2654435761u) >> 22; }   // 10 bits
+__device__ __forceinline__ unsigned dm_hash_slot(unsigned node) { return (node * 2654435761u) >> 23; }   // 9 bits
+__host__ __device__ inline int dm_vis_words(int N, int rebuild) { return ((rebuild ? 27 : 1) * N + 31) / 32; }
+__host__ __device__ inline size_t dm_fill_warp_words(int N, int rebuild, bool smem_state) {
+  return (size_t)DM_FILL_FIXED_WORDS + (smem_state ? (size_t)dm_vis_words(N, rebuild) + (size_t)(N + 3) / 4 : 0);
+}
 
+template <bool SMEM_STATE>
 __global__ void __launch_bounds__(DM_FILL_WARPS * 32)
 k_dm_fill(DmArgs A) {
-  __shared__ __align__(16) unsigned h_node[DM_FILL_WARPS][DM_HASH];
-  __shared__ __align__(16) unsigned h_key[DM_FILL_WARPS][DM_HASH];
+  extern __shared__ __align__(16) unsigned dm_sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.x * DM_FILL_WARPS + wid;
   if (f >= A.F) return;
-  unsigned* hn = h_node[wid];
-  unsigned* hk = h_key[wid];
   const int N = A.N;
+  unsigned* hn = dm_sm + (size_t)wid * dm_fill_warp_words(N, A.rebuild, SMEM_STATE);
+  unsigned* hk = hn + DM_HASH;
+  int* cnode = (int*)(hk + DM_HASH) + lane * DM_CAND_STRIDE;
+  unsigned short* cslot = (unsigned short*)((int*)(hk + DM_HASH) + 32 * DM_CAND_STRIDE) + lane * DM_CAND_STRIDE;
   const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
   const double* xr = A.xr + (size_t)f * N * 3;
   const double* frac = A.frac + (size_t)f * N * 3;
   const unsigned* adj = A.adj + (size_t)f * N * DM_ADJ_CAP;
   const int* deg = A.deg + (size_t)f * N;
-  const int nimg = A.rebuild ? 27 : 1;
-  const int vis_words = (nimg * N + 31) / 32;
-  unsigned* vis = A.vis + (size_t)f * ((27 * N + 31) / 32);
-  unsigned char* rem = A.rem + (size_t)f * N;
-  int* fr0 = A.front + (size_t)f * 2 * A.out_cap;
-  int* fr1 = fr0 + A.out_cap;
+  const int vis_words = dm_vis_words(N, A.rebuild);
+  unsigned* vis = SMEM_STATE ? hn + DM_FILL_FIXED_WORDS : A.vis + (size_t)f * ((27 * N + 31) / 32);
+  unsigned char* rem = SMEM_STATE ? (unsigned char*)(vis + vis_words) : A.rem + (size_t)f * N;
   int* osrc = A.out_src + (size_t)f * A.out_cap;
   double* oxyz = A.out_xyz + (size_t)f * A.out_cap * 3;
   int* moff = A.mol_off + (size_t)f * (A.mol_cap + 1);
@@ -381,28 +395,11 @@ k_dm_fill(DmArgs A) {
     double xx = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), xx), yy);
     sd[a] = A.type_terminal[A.atom_type[a]] ? PWB_INF : sqrt(fmax(d2, 0.0));     // terminal atoms never seed
+    if (SMEM_STATE) rem[a] = 1;                  // (the global copy is set by k_dm_prepare)
   }
   for (int w = lane; w < vis_words; w += 32) vis[w] = 0u;
-  const uint4 empty4 = make_uint4(DM_EMPTY, DM_EMPTY, DM_EMPTY, DM_EMPTY);
-  for (int t = lane; t < DM_HASH / 4; t += 32) { ((uint4*)hn)[t] = empty4; ((uint4*)hk)[t] = empty4; }
+  for (int t = lane; t < 2 * DM_HASH; t += 32) hn[t] = DM_EMPTY;       // hn and hk are adjacent
   __syncwarp();
-  // candidate (pass, slot e) of parent node p -> node id, or -1
-  auto candidate = [&](int a, int sa, int sb, int sc, unsigned k, int pass) -> int {
-    const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
-    int node;
-    bool central;
-    if (A.rebuild) {
-      const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
-      if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) return -1;
-      const int im = (ma + 1) * 9 + (mb + 1) * 3 + (mc + 1);
-      node = im * N + b;
-      central = im == 13;
-    } else { node = b; central = true; }
-    const bool cellpath = central && rem[b];
-    if ((pass == 0) != cellpath) return -1;          // pass 0: remaining cell atoms; pass 1: the rest
-    if (vis[node >> 5] & (1u << (node & 31))) return -1;
-    return node;
-  };
   while (true) {
     // ---- seed: remaining non-terminal atom closest to the pseudo origin, first arg-min
     ValIdx best; best.v = PWB_INF; best.i = 0x7fffffff;
@@ -414,111 +411,100 @@ k_dm_fill(DmArgs A) {
     best = warp_vi_min(best);
     if (best.i == 0x7fffffff) break;
     const int start = nout;
+    if (start >= A.out_cap) { st |= 2; break; }
     int overflow = 0;
-    int* cur = fr0; int* nxt = fr1;
-    int ncur = 1;
     {
-      const int seed = cimg * N + best.i;
-      if (lane == 0) { cur[0] = seed; vis[seed >> 5] |= 1u << (seed & 31); }
+      const int seed = (cimg << 20) | best.i, bit = cimg * N + best.i;
+      if (lane == 0) { osrc[start] = seed; vis[bit >> 5] |= 1u << (bit & 31); }
     }
     __syncwarp();
-    while (ncur > 0) {
-      // the level's nodes leave the frontier in order
-      for (int q = lane; q < ncur; q += 32) { if (nout + q < A.out_cap) osrc[nout + q] = cur[q]; else overflow = 1; }
-      nout += ncur;
-      int nn = 0;
-      const int npass = A.rebuild ? 2 : 1;
-      for (int q0 = 0; q0 < ncur; q0 += 32) {
+    int lvl0 = start, lvl1 = start + 1;          // the current level = osrc[lvl0, lvl1)
+    while (lvl1 > lvl0) {
+      int nn = lvl1;                             // children are appended behind the level
+      for (int q0 = lvl0; q0 < lvl1; q0 += 32) {
         const int q = q0 + lane;
         int a = 0, sa = 0, sb = 0, sc = 0, dg = 0;
-        if (q < ncur) {
-          const int p = cur[q];
-          a = p % N;
-          const int img = p / N;
+        if (q < lvl1) {
+          const int p = osrc[q];
+          a = p & 0xfffff;
+          const int img = p >> 20;
           if (A.rebuild) { sa = img / 9 - 1; sb = (img / 3) % 3 - 1; sc = img % 3 - 1; }
-          dg = A.type_terminal[A.atom_type[a]] ? 0 : deg[a];
+          dg = deg[a];                           // (0 for terminal atoms)
         }
-        // 1. enter the candidates: node -> smallest key (lane, pass, slot)
-        for (int pass = 0; pass < npass; pass++)
-          for (int e = 0; e < dg; e++) {
-            const int node = candidate(a, sa, sb, sc, adj[(size_t)a * DM_ADJ_CAP + e], pass);
-            if (node < 0) continue;
-            const unsigned key = (unsigned)(lane * 24 + pass * 12 + e);
-            unsigned h = dm_hash_slot((unsigned)node);
-            while (true) {
-              const unsigned old = atomicCAS(&hn[h], DM_EMPTY, (unsigned)node);
-              if (old == DM_EMPTY || old == (unsigned)node) { atomicMin(&hk[h], key); break; }
-              h = (h + 1) & (DM_HASH - 1);
-            }
+        // 1. candidates of this lane's parent: node -> smallest key (lane, pass, slot)
+        unsigned valid = 0, pass1 = 0;
+        for (int e = 0; e < dg; e++) {
+          const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
+          const int b = (int)(k & 0xfffffu);
+          int im = 0;
+          if (A.rebuild) {
+            const int ik = (int)(k >> 20);
+            const int ma = (ik >> 8) - 3 + sa, mb = ((ik >> 4) & 15) - 3 + sb, mc = (ik & 15) - 3 + sc;   // image + 1
+            if ((unsigned)ma > 2u || (unsigned)mb > 2u || (unsigned)mc > 2u) continue;    // outside the supercell
+            im = ma * 9 + mb * 3 + mc;
           }
+          const int bit = im * N + b;
+          if (vis[bit >> 5] & (1u << (bit & 31))) continue;
+          const unsigned pass = (im == cimg && rem[b]) ? 0u : 1u;     // pass 0: remaining cell atoms; 1: the rest
+          const unsigned node = ((unsigned)im << 20) | (unsigned)b;
+          const unsigned key = (unsigned)(lane * 24) + pass * 12u + (unsigned)e;
+          unsigned h = dm_hash_slot(node);
+          while (true) {
+            const unsigned old = atomicCAS(&hn[h], DM_EMPTY, node);
+            if (old == DM_EMPTY || old == node) { atomicMin(&hk[h], key); break; }
+            h = (h + 1) & (DM_HASH - 1);
+          }
+          cnode[e] = (int)node; cslot[e] = (unsigned short)h;
+          valid |= 1u << e; pass1 |= pass << e;
+        }
         __syncwarp();
-        // 2. winners per lane, in slot order
+        // 2. winners of this lane, as a bit mask over (pass, slot)
         unsigned keep = 0;
-        for (int pass = 0; pass < npass; pass++)
-          for (int e = 0; e < dg; e++) {
-            const int node = candidate(a, sa, sb, sc, adj[(size_t)a * DM_ADJ_CAP + e], pass);
-            if (node < 0) continue;
-            const unsigned key = (unsigned)(lane * 24 + pass * 12 + e);
-            unsigned h = dm_hash_slot((unsigned)node);
-            while (hn[h] != (unsigned)node) h = (h + 1) & (DM_HASH - 1);
-            if (hk[h] == key) keep |= 1u << (pass * 12 + e);
-          }
-        // 3. ordered compaction into the next frontier
-        int cnt = __popc(keep), inc = cnt;
+        for (unsigned v = valid; v; v &= v - 1) {
+          const int e = __ffs(v) - 1;
+          const unsigned pe = ((pass1 >> e) & 1u) * 12u + (unsigned)e;
+          if (hk[cslot[e]] == (unsigned)(lane * 24) + pe) keep |= 1u << pe;
+        }
+        // 3. ordered compaction behind the level, visited marks, table wipe
+        const int cnt = __popc(keep);
+        int inc = cnt;
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
         int pos = nn + inc - cnt;
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        nn += __shfl_sync(0xffffffffu, inc, 31);
         __syncwarp();
-        for (int pass = 0; pass < npass; pass++)
-          for (int e = 0; e < dg; e++) {
-            if (!(keep & (1u << (pass * 12 + e)))) continue;
-            const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
-            const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
-            int node = b;
-            if (A.rebuild) {
-              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
-              node = ((ma + 1) * 9 + (mb + 1) * 3 + (mc + 1)) * N + b;
-            }
-            if (pos < A.out_cap) nxt[pos] = node; else overflow = 1;
-            pos++;
-          }
-        __syncwarp();
-        // 4. mark the winners visited and wipe the table entries this chunk used
-        for (int pass = 0; pass < npass; pass++)
-          for (int e = 0; e < dg; e++) {
-            const unsigned k = adj[(size_t)a * DM_ADJ_CAP + e];
-            const int b = (int)(k & 0xfffffu), ik = (int)(k >> 20);
-            int node = b;
-            if (A.rebuild) {
-              const int ma = ik / 81 - 4 + sa, mb = (ik / 9) % 9 - 4 + sb, mc = ik % 9 - 4 + sc;
-              if (ma < -1 || ma > 1 || mb < -1 || mb > 1 || mc < -1 || mc > 1) continue;
-              node = ((ma + 1) * 9 + (mb + 1) * 3 + (mc + 1)) * N + b;
-            }
-            if (keep & (1u << (pass * 12 + e))) atomicOr(&vis[node >> 5], 1u << (node & 31));
-          }
-        nn += total;
-        __syncwarp();
-        if (total) for (int t = lane; t < DM_HASH / 4; t += 32) { ((uint4*)hn)[t] = empty4; ((uint4*)hk)[t] = empty4; }
+        for (unsigned kbits = keep; kbits; kbits &= kbits - 1) {
+          const int pe = __ffs(kbits) - 1;
+          const int node = cnode[pe >= 12 ? pe - 12 : pe];
+          if (pos < A.out_cap) osrc[pos] = node; else overflow = 1;
+          pos++;
+          const int bit = (node >> 20) * N + (node & 0xfffff);
+          atomicOr(&vis[bit >> 5], 1u << (bit & 31));
+        }
+        for (unsigned v = valid; v; v &= v - 1) {
+          const int h = cslot[__ffs(v) - 1];
+          hn[h] = DM_EMPTY; hk[h] = DM_EMPTY;
+        }
         __syncwarp();
       }
       // the level is done: its cell atoms are assigned now (utilities.py:1040-1044)
-      for (int q = lane; q < ncur; q += 32) {
-        const int p = cur[q];
-        if (p / N == cimg) rem[p % N] = 0;
+      for (int q = lvl0 + lane; q < lvl1; q += 32) {
+        const int p = osrc[q];
+        if ((p >> 20) == cimg) rem[p & 0xfffff] = 0;
       }
+      overflow = __any_sync(0xffffffffu, overflow);
+      if (overflow || nn > A.out_cap) { overflow = 1; break; }
       __syncwarp();
-      int* t = cur; cur = nxt; nxt = t;
-      ncur = min(nn, A.out_cap);
-      if (nn > A.out_cap) overflow = 1;
+      lvl0 = lvl1; lvl1 = nn;
     }
-    overflow = __any_sync(0xffffffffu, overflow);
-    if (overflow || nout > A.out_cap) { st |= 2; break; }
+    if (overflow) { st |= 2; break; }
+    nout = lvl1;
     // ---- resolve nodes to (source atom, coordinates); centre of mass for the filter
     double mx = 0, my = 0, mz = 0, mt = 0;
     for (int q = start + lane; q < nout; q += 32) {
       const int p = osrc[q];
-      vis[p >> 5] = 0u;                            // every set bit belongs to a node of this molecule
-      const int a = p % N, img = p / N;
+      const int a = p & 0xfffff, img = p >> 20;
+      const int bit = img * N + a;
+      vis[bit >> 5] = 0u;                          // every set bit belongs to a node of this molecule
       double X, Y, Z;
       if (!A.rebuild || img == 13) { X = xr[3 * a]; Y = xr[3 * a + 1]; Z = xr[3 * a + 2]; }
       else {
@@ -693,7 +679,19 @@ int pwb_discrete_molecules(int F, int N, int rebuild, double tol, double max_cov
     dim3 g((N + DM_TILE - 1) / DM_TILE, F);
     k_dm_bonds<<<g, DM_TILE, 0, s>>>(A, 2 * max_cov + tol);
   }
-  k_dm_fill<<<(F + DM_FILL_WARPS - 1) / DM_FILL_WARPS, DM_FILL_WARPS * 32, 0, s>>>(A);
+  {
+    // visited bits + "unassigned" bytes of the frame in shared memory while four CTAs still fit on an SM
+    const size_t with_state = sizeof(unsigned) * DM_FILL_WARPS * dm_fill_warp_words(N, rebuild, true);
+    const size_t without = sizeof(unsigned) * DM_FILL_WARPS * dm_fill_warp_words(N, rebuild, false);
+    const int grid = (F + DM_FILL_WARPS - 1) / DM_FILL_WARPS;
+    if (with_state <= DM_FILL_STATE_SMEM_MAX) {
+      if (with_state > 48 * 1024)
+        cudaFuncSetAttribute(k_dm_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_state);
+      k_dm_fill<true><<<grid, DM_FILL_WARPS * 32, with_state, s>>>(A);
+    } else {
+      k_dm_fill<false><<<grid, DM_FILL_WARPS * 32, without, s>>>(A);
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pwb_set_error(cudaGetErrorString(e)); return 1; }
   return 0;
