@@ -168,10 +168,11 @@ int pwb_full_analysis_batch(pwb_ctx*, const pwb_batch*, void* stream);
 int pwb_full_analysis_host(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                            double* d_coords, double* d_records, int total_atoms, void* stream);
 /* Same without the final synchronisation (h_coords / h_records must be pinned): the records are valid once
- * `stream` has been synchronised.  `d_coords` must be idle when the call is made (no earlier queued work still
- * reads it): the input copies go to an internal copy stream and do NOT wait for work already queued on `stream`,
- * so with two sets of staging buffers used alternately the copies of batch i+1 overlap the kernels of batch i --
- * which is how a trajectory reader that decodes batch i+1 while batch i is analysed uses it
+ * `stream` has been synchronised.  `d_coords`, `d_records` and the workspace must be idle when the call is made
+ * (no earlier queued work still uses them): the input copies go to an internal copy stream and the sub-batches to
+ * the internal streams WITHOUT waiting for work already queued on `stream`, so with two sets of buffers used
+ * alternately the copies of batch i+1 overlap the kernels of batch i and the tail of batch i overlaps the head of
+ * batch i+1 -- which is how a trajectory reader that decodes batch i+1 while batch i is analysed uses it
  * (pywindow_b200.engine.FramePipeline).                                                              */
 int pwb_full_analysis_host_async(pwb_ctx*, const pwb_batch* b, const double* h_coords, double* h_records,
                                  double* d_coords, double* d_records, int total_atoms, void* stream);

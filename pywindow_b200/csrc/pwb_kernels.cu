@@ -2033,7 +2033,10 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       u.win_k += (size_t)first * b->win_cap;
       if (b->ray_cap > KNN_SMEM_CAP) { u.big_pts += (size_t)first * b->ray_cap * 4; u.big_i += (size_t)first * b->ray_cap * 2; }
       cudaStream_t sg = c->streams[g];
-      CK(cudaStreamWaitEvent(sg, c->fork, 0));
+      // (`staging_idle`: the batch depends on nothing queued on `s` -- its input comes from the host and its
+      // buffers are idle -- so sub-batch g simply follows sub-batch g of the previous call on its own stream and the
+      // tail of one batch overlaps the head of the next instead of ending in a barrier)
+      if (!staging_idle) CK(cudaStreamWaitEvent(sg, c->fork, 0));
       if (chunk_copies) {
         // The copies go to their own stream so that, with two calls in flight, the next batch's input
         // arrives while this batch's kernels still occupy the chunk streams.

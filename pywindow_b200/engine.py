@@ -358,7 +358,8 @@ def host_ray_capacity(coords, vdw_max, adjust=1.0, margin=64, sample=512):
         return 64 + margin
     if c.shape[0] > sample:
         c = c[:: -(-c.shape[0] // sample)]
-    ext = c.max(axis=1) - c.min(axis=1)
+    c = np.ascontiguousarray(c.transpose(0, 2, 1))          # [F, 3, N]: the reductions run over contiguous rows
+    ext = c.max(axis=2) - c.min(axis=2)
     D = float(np.sqrt((ext * ext).sum(axis=1)).max()) + 2.0 * float(vdw_max)
     P = int(np.log10(4.0 * np.pi * D * D) * 250.0 * float(adjust)) + 1
     return max(64, (P + margin + 63) // 64 * 64)

@@ -499,27 +499,46 @@ class Trajectory:
             return np.zeros((0, eng.rec_stride)), RecordKeys.single([])
         elements = self._elements_of(frames[0], swap_atoms, forcefield)
         B = max(1, self.batch_frames)
-        # a short first batch gets the GPU going after 1/8 of a batch's decode time; the rest are full batches
-        head = min(B, max(256, B // 8)) if len(frames) > B else B
-        chunks = [frames[:head]] + [frames[s:s + B] for s in range(head, len(frames), B)]
+        # a short first batch gets the GPU going after 1/8 of a batch's decode time; the rest are full batches.  A
+        # frame list shorter than two batches (a rank's shard of a strongly scaled run) is cut in four, so that its
+        # decode still overlaps the kernels
+        n = len(frames)
+        step = B if n >= 2 * B else min(B, max(2048, -(-n // 4)))
+        head = min(step, max(256, step // 8)) if n > step else step
+        chunks = [frames[:head]] + [frames[s:s + step] for s in range(head, n, step)]
         threads = _host_threads()
         pipe = eng.frame_pipeline(elements, B, slots=2, **gpu_kwargs)
         nslots = len(pipe.slots)
         records = np.empty((len(frames), eng.rec_stride), dtype=np.float64)
-        done = 0
-        for k, chunk in enumerate(chunks):
-            self._decode_into(chunk, pipe.buffer(k % nslots), threads)
-            if k == 0:      # ray-list capacity for the whole trajectory from the first batch's bounding boxes
-                pipe.ensure_ray_capacity(host_ray_capacity(pipe.buffer(0)[:len(chunk)], pipe.vdw_max,
-                                                           float(gpu_kwargs.get("adjust", 1.0))))
-            pipe.submit(k % nslots, len(chunk))
-            if k + 1 >= nslots:                      # the slot the next batch will be decoded into must be free
-                j = k + 1 - nslots
-                records[done:done + len(chunks[j])] = pipe.collect(j % nslots)
-                done += len(chunks[j])
-        for j in range(max(0, len(chunks) - nslots + 1), len(chunks)):
-            records[done:done + len(chunks[j])] = pipe.collect(j % nslots)
-            done += len(chunks[j])
+        starts = np.concatenate([[0], np.cumsum([len(c) for c in chunks])])
+        # the records of a finished batch leave their pinned slot on a helper thread (the copy into fresh pageable
+        # memory is page-fault bound, ~0.2 ms/MB, and would otherwise delay the decode of the next batch)
+        from concurrent.futures import ThreadPoolExecutor
+        copies = {}
+
+        def take(j):
+            src = pipe.collect(j % nslots)
+            lo = int(starts[j])
+
+            def job():
+                records[lo:lo + len(chunks[j])] = src
+            copies[j % nslots] = mover.submit(job)
+
+        with ThreadPoolExecutor(max_workers=1) as mover:
+            for k, chunk in enumerate(chunks):
+                self._decode_into(chunk, pipe.buffer(k % nslots), threads)
+                if k == 0:      # ray-list capacity for the whole trajectory from the first batch's bounding boxes
+                    pipe.ensure_ray_capacity(host_ray_capacity(pipe.buffer(0)[:len(chunk)], pipe.vdw_max,
+                                                               float(gpu_kwargs.get("adjust", 1.0))))
+                if k % nslots in copies:                 # the slot's previous records must have left it
+                    copies.pop(k % nslots).result()
+                pipe.submit(k % nslots, len(chunk))
+                if k + 1 >= nslots:                      # the slot the next batch will be decoded into must be free
+                    take(k + 1 - nslots)
+            for j in range(max(0, len(chunks) - nslots + 1), len(chunks)):
+                take(j)
+            for fut in copies.values():
+                fut.result()
         records = self._redo_overflowed(records, frames, elements, gpu_kwargs)
         return records, RecordKeys.single(frames)
 
