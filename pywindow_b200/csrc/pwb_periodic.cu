@@ -105,11 +105,12 @@ k_dm_prepare(DmArgs A) {
 // Periodic images of atom b bonded to atom a: the minimum image offset m0, then the offsets around it that can
 // be within the cut-off at all -- |delta f_c| <= |delta x| * |row c of inv(lattice)|, so an image needs
 // |df_c - m_c| <= tau_c on every axis; for ordinary cells that leaves at most the minimum image and rejects
-// > 99 % of the pairs after three subtractions.  Appends (image key << 20 | b) to list.
+// > 99 % of the pairs after three subtractions.  Calls emit(image key << 20 | b) for every bond found.
+template <class Emit>
 __device__ __forceinline__ void dm_pair_images(const DmArgs& A, const double (&L)[9], double taux, double tauy, double tauz,
                                                double max_dist, double ax, double ay, double az, double afx, double afy,
                                                double afz, double rs, double bx, double by, double bz, double bfx,
-                                               double bfy, double bfz, int bb, unsigned* list, int& n, int& overflow) {
+                                               double bfy, double bfz, int bb, Emit emit) {
   const double dfx = afx - bfx, dfy = afy - bfy, dfz = afz - bfz;
   const double m0x = rint(dfx), m0y = rint(dfy), m0z = rint(dfz);
   const double ex = dfx - m0x, ey = dfy - m0y, ez = dfz - m0z;
@@ -137,8 +138,7 @@ __device__ __forceinline__ void dm_pair_images(const DmArgs& A, const double (&L
         if (d > 0.1 && d < max_dist && rs - A.tol < d && d < rs + A.tol) {
           int ka = (int)ma + 4, kb = (int)mb + 4, kc = (int)mc + 4;
           if (ka < 0 || ka > 8 || kb < 0 || kb > 8 || kc < 0 || kc > 8) continue;   // > 4 cells away: unreachable
-          unsigned key = ((unsigned)((ka << 8) | (kb << 4) | kc) << 20) | (unsigned)bb;   // sorts like (ka, kb, kc)
-          if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1;
+          emit(((unsigned)((ka << 8) | (kb << 4) | kc) << 20) | (unsigned)bb);   // sorts like (ka, kb, kc)
         }
       }
     }
@@ -167,7 +167,7 @@ constexpr int DM_CL_THREADS = 256, DM_CL_MAXG = 12;
 constexpr int DM_CL_NB = DM_CL_MAXG * DM_CL_MAXG * DM_CL_MAXG;
 // shared memory: bin starts + cursors, then the atoms SORTED BY BIN (7 doubles + index each), so that the
 // candidate loop streams contiguous shared memory instead of chasing indices through global memory
-#define DM_CL_SMEM(N) (sizeof(int) * (2 * DM_CL_NB + 2) + (size_t)(N) * (7 * sizeof(double) + sizeof(int)) + 16)
+#define DM_CL_SMEM(N) (sizeof(int) * (2 * DM_CL_NB + 2) + (size_t)(N) * (7 * sizeof(double) + 2 * sizeof(int)) + 16)
 __global__ void __launch_bounds__(DM_CL_THREADS, 2)
 k_dm_bonds_cells(DmArgs A, double max_dist) {
   extern __shared__ __align__(16) double smd[];
@@ -178,6 +178,8 @@ k_dm_bonds_cells(DmArgs A, double max_dist) {
   int* qi = (int*)(qc + N);                                              // atom index
   int* bstart = qi + N;                    // [NB + 1]
   int* bcur = bstart + DM_CL_NB + 1;       // [NB]
+  int* nts = bcur + DM_CL_NB;              // [N] sorted slots of the non-terminal atoms
+  __shared__ int nnt;
   __shared__ int G[3];
   __shared__ double tau[3];
   const double* fd = A.frame_d + (size_t)f * DM_FRAME_D;
@@ -240,32 +242,49 @@ k_dm_bonds_cells(DmArgs A, double max_dist) {
     qi[pos] = a;
   }
   __syncthreads();
-  // one thread per sorted slot: its own data is already in shared memory
+  // Pair phase: one thread per NON-TERMINAL atom (their sorted slots are compacted first, so the lanes of a warp all
+  // have work), walking the <= 9 (x, y) bin columns around it; the <= 3 z bins of a column are adjacent in the sorted
+  // order, i.e. one contiguous range of candidates (two if the column wraps around the cell).
+  if (tid == 0) nnt = 0;
+  __syncthreads();
   for (int sa = tid; sa < N; sa += nt) {
+    if (!A.type_terminal[A.atom_type[qi[sa]]]) nts[atomicAdd(&nnt, 1)] = sa;
+    else A.deg[(size_t)f * N + qi[sa]] = 0;
+  }
+  __syncthreads();
+  for (int it = tid; it < nnt; it += nt) {
+    const int sa = nts[it];
     const int a = qi[sa];
     unsigned list[DM_ADJ_CAP];
     int n = 0, overflow = 0;
-    if (!A.type_terminal[A.atom_type[a]]) {
-      const double ax = qx[sa], ay = qy[sa], az = qz[sa], afx = qfx[sa], afy = qfy[sa], afz = qfz[sa], acov = qc[sa];
-      const int bin = bin_of(afx, afy, afz);
-      const int bz = bin % Gz, by = (bin / Gz) % Gy, bx = bin / (Gz * Gy);
-      // (no unrolling: with the 27-image test inlined, unrolled bin loops made a 1.5 MB kernel that spent
-      // 92 % of its time waiting for instructions)
-#pragma unroll 1
-      for (int ox = (Gx > 1 ? -1 : 0); ox <= (Gx > 1 ? 1 : 0); ox++)
-#pragma unroll 1
-        for (int oy = (Gy > 1 ? -1 : 0); oy <= (Gy > 1 ? 1 : 0); oy++) {
-          const int cx = (bx + ox + Gx) % Gx, cy = (by + oy + Gy) % Gy;
-#pragma unroll 1
-          for (int oz = (Gz > 1 ? -1 : 0); oz <= (Gz > 1 ? 1 : 0); oz++) {
-            const int c = (cx * Gy + cy) * Gz + (bz + oz + Gz) % Gz;
-#pragma unroll 1
-            for (int t = bstart[c]; t < bstart[c + 1]; t++)
-              dm_pair_images(A, L, taux, tauy, tauz, max_dist, ax, ay, az, afx, afy, afz, acov + qc[t],
-                             qx[t], qy[t], qz[t], qfx[t], qfy[t], qfz[t], qi[t], list, n, overflow);
-          }
-        }
+    const double ax = qx[sa], ay = qy[sa], az = qz[sa], afx = qfx[sa], afy = qfy[sa], afz = qfz[sa], acov = qc[sa];
+    const int bin = bin_of(afx, afy, afz);
+    const int bz = bin % Gz, by = (bin / Gz) % Gy, bx = bin / (Gz * Gy);
+    // z bins bz-1 .. bz+1 (mod Gz) as one or two contiguous bin ranges [lo, hi]
+    int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;
+    if (Gz > 1) {
+      lo1 = bz - 1; hi1 = bz + 1;
+      if (lo1 < 0) { lo1 = 0; lo2 = hi2 = Gz - 1; }
+      else if (hi1 >= Gz) { hi1 = Gz - 1; lo2 = hi2 = 0; }
     }
+    auto emit = [&](unsigned key) { if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1; };
+    // (no unrolling: with the 27-image test inlined, unrolled bin loops made a 1.5 MB kernel that spent
+    // 92 % of its time waiting for instructions)
+#pragma unroll 1
+    for (int ox = (Gx > 1 ? -1 : 0); ox <= (Gx > 1 ? 1 : 0); ox++)
+#pragma unroll 1
+      for (int oy = (Gy > 1 ? -1 : 0); oy <= (Gy > 1 ? 1 : 0); oy++) {
+        const int c0 = (((bx + ox + Gx) % Gx) * Gy + (by + oy + Gy) % Gy) * Gz;
+#pragma unroll 1
+        for (int r = 0; r < 2; r++) {
+          const int lo = r ? lo2 : lo1, hi = r ? hi2 : hi1;
+          if (lo > hi) continue;
+#pragma unroll 1
+          for (int t = bstart[c0 + lo]; t < bstart[c0 + hi + 1]; t++)
+            dm_pair_images(A, L, taux, tauy, tauz, max_dist, ax, ay, az, afx, afy, afz, acov + qc[t],
+                           qx[t], qy[t], qz[t], qfx[t], qfy[t], qfz[t], qi[t], emit);
+        }
+      }
     dm_store_bonds(A, f, a, list, n, overflow);
   }
 }
@@ -322,7 +341,8 @@ k_dm_bonds(DmArgs A, double max_dist) {
         continue;
       }
       dm_pair_images(A, L, taux, tauy, tauz, max_dist, ax, ay, az, afx, afy, afz, rs,
-                     sx[j], sy[j], sz[j], sfx[j], sfy[j], sfz[j], bb, list, n, overflow);
+                     sx[j], sy[j], sz[j], sfx[j], sfy[j], sfz[j], bb,
+                     [&](unsigned key) { if (n < DM_ADJ_CAP) list[n++] = key; else overflow = 1; });
     }
   }
   if (a >= A.N) return;

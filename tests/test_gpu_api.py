@@ -142,3 +142,43 @@ def test_xyz_and_pdb_trajectory_analysis_matches_per_frame(tmp_path):
             p = t.get_frames(f)[f].system_to_molecule().full_analysis()
             assert pw.compare_properties_dict(p, t.analysis_output[f]["0"]) == (True, "none"), (type(t).__name__, f)
             assert len(p["windows"]["diameters"]) == 4
+
+
+def test_pipelined_trajectory_batches_equal_one_batch(tmp_path):
+    """Trajectory.analysis over several pipeline batches (short head batch, two pinned slots used alternately,
+    records leaving the slots on the helper thread, a last partial batch) gives exactly the records of ONE device
+    batch over the same frames, in frame order."""
+    import pywindow_b200 as pw
+    from pywindow_b200 import synthetic
+    from pywindow_b200.engine import default_engine
+    gs = [load_golden(f"md_frame{i:02d}") for i in range(5)]
+    seeds = np.stack([g["coords"] for g in gs])
+    el = [str(e) for e in gs[0]["elements"]]
+    F = 5000
+    X = synthetic.noisy_frames(seeds, 0, F)
+    path = tmp_path / "HISTORY"
+    synthetic.write_history_native(str(path), [e + "1" for e in el], X, compact=True)
+    t = pw.DLPOLY(path)
+    t.batch_frames = 700                                     # head 87 + 7 full batches + 13 frames
+    t.analysis(forcefield="DLF")
+    tab, keys = t.analysis_output.record_table()
+    assert tab.shape[0] == F and list(keys.frames) == list(range(F))
+    Xd = t._decode_coordinates(list(range(F)))               # what the file holds (4 significant decimals)
+    ref = default_engine().analyse_frames(Xd, el).host_records()
+    np.testing.assert_array_equal(tab, ref)
+
+
+def test_bounce_buffer_readback_is_exact():
+    """distributed._device_to_host (pinned bounce buffers + helper threads) == Tensor.cpu() for float64 and int64
+    tensors larger than the buffers, including a ragged last chunk."""
+    import torch
+    from pywindow_b200.distributed import _device_to_host, _BOUNCE_DOUBLES
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((3 * _BOUNCE_DOUBLES + 12345) // 92, 92, dtype=torch.float64, device="cuda", generator=g)
+    np.testing.assert_array_equal(_device_to_host(a), a.cpu().numpy())
+    k = torch.randint(-5, 1 << 40, (2, _BOUNCE_DOUBLES + 77), dtype=torch.int64, device="cuda", generator=g)
+    out = _device_to_host(k)
+    assert out.dtype == np.int64 and out.shape == (2, _BOUNCE_DOUBLES + 77)
+    np.testing.assert_array_equal(out, k.cpu().numpy())
+    small = torch.arange(10, dtype=torch.float64, device="cuda")
+    np.testing.assert_array_equal(_device_to_host(small), np.arange(10.0))
