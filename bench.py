@@ -596,10 +596,12 @@ def run_ours(args):
                        "host_decode_frames_per_s": dec, "host_threads": _host_threads(),
                        "host_decode_GBps": dec_gbs, "host_stream_GBps": stream_gbs,
                        "pools": "pinned / device buffers warm from an earlier analysis() in this process (engine pool)",
-                       "limit": "host memory: the text of the HISTORY file (13.5 KB per frame) has to be streamed once; the "
-                                "decoder (host_decode_GBps, all host threads of the rank, overlapped with the GPU) "
-                                "runs at about the rate at which the same threads can merely count the line feeds of "
-                                "the mapped file (host_stream_GBps); ranks of one node share the host cores"}
+                       "limit": "the GPU at the reader's batch size (16 384 frames per batch, two sub-batches each: "
+                                "about 1.4e6 frames/s from pinned buffers against 1.6e6 at 100 000 frames per batch) "
+                                "plus the head (map, first decode) and tail (last batch, record read-back) of a 0.1 s "
+                                "job; the decoder (host_decode_frames_per_s on all host threads of the rank; "
+                                "host_stream_GBps = the same threads merely counting line feeds) runs under the "
+                                "kernels; ranks of one node share the host cores"}
             del traj
         finally:
             barrier()
