@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PWB_ABI_VERSION 3
+#define PWB_ABI_VERSION 4
 #define PWB_MAX_TYPES 16
 
 /* ---- result record: `rec_stride` doubles per item (>= PWB_REC_WIN0 + 4*win_cap) --------------- */
@@ -131,6 +131,7 @@ typedef struct pwb_ws_layout {
   size_t big_i;      /* int32[F][2][ray_cap]: union-find scratch of the large-ray-count path      */
   size_t atom_scratch; /* per-CTA / per-warp atom arrays of molecules too large for shared memory
                           (> ~2 900 atoms; empty otherwise)                                        */
+  size_t opt_hist;   /* double[F][60]: (s, y) rings of the pore-centre searches (k_opt_pore)       */
   size_t total;
 } pwb_ws_layout;
 

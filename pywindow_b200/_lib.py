@@ -51,7 +51,7 @@ class Batch(ctypes.Structure):
 class WsLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in
                 ("atoms", "atom_idx", "item_d", "item_i", "clear_k", "clear_pos", "clear_a2", "labels",
-                 "win_k", "big_pts", "big_i", "atom_scratch", "total")]
+                 "win_k", "big_pts", "big_i", "atom_scratch", "opt_hist", "total")]
 
 
 class PwbLibraryError(RuntimeError):
@@ -114,7 +114,7 @@ def load():
     L.pwb_fma_peak.restype = ci
     L.pwb_launch_count.argtypes = [vp]
     L.pwb_launch_count.restype = ctypes.c_longlong
-    if L.pwb_abi_version() != 3:
+    if L.pwb_abi_version() != 4:
         raise PwbLibraryError("libpwb.so ABI version mismatch")
     _lib = L
     return L

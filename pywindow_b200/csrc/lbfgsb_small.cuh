@@ -50,7 +50,9 @@ PWB_HD double lb_sqrt(double a) { return sqrt(a); }
 constexpr int LB_M = 10;
 // doubles of caller storage lbfgsb_minimize<N> needs: (s, y) ring, z / d / t / r, line-search record
 // and the small work arrays of the Cauchy / subspace steps (x, g, iwhere: 3N; B: N*N; scratch: 4N + 3N*N)
-#define LB_STORAGE(N) (2 * pwb::LB_M * (N) + 4 * (N) + 20 + 10 * (N) + 4 * (N) * (N) + 8)   /* = LbSolver<N>::SIZE */
+#define LB_HISTORY(N) (2 * pwb::LB_M * (N))                                      /* the (s, y) ring */
+#define LB_STATE(N) (4 * (N) + 20 + 10 * (N) + 4 * (N) * (N) + 8)                /* everything else = LbSolver<N>::STATE */
+#define LB_STORAGE(N) (LB_STATE(N) + LB_HISTORY(N))                              /* = LbSolver<N>::SIZE */
 constexpr double LB_EPSMCH = 2.220446049250313e-16;
 constexpr double LB_FD_STEP = 1e-8;
 
@@ -205,18 +207,34 @@ PWB_HD void lb_build_B(const LbHistory<N>& H, double theta, double* Bm) {
   double B[N][N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) B[i][j] = (i == j) ? theta : 0.0;
+#ifdef LB_READ_AHEAD
+  // the next pair is read while the current one is applied (for a ring kept in global memory)
+  double sn[N], yn[N];
+  if (H.col > 0)
+    for (int i = 0; i < N; i++) { sn[i] = H.S[H.head][i]; yn[i] = H.Y[H.head][i]; }
+#endif
   for (int k = 0; k < H.col; k++) {
-    int p = (H.head + k) % LB_M;
+    double s[N], y[N];
+#ifdef LB_READ_AHEAD
+    for (int i = 0; i < N; i++) { s[i] = sn[i]; y[i] = yn[i]; }
+    if (k + 1 < H.col) {
+      const int pn = (H.head + k + 1) % LB_M;
+      for (int i = 0; i < N; i++) { sn[i] = H.S[pn][i]; yn[i] = H.Y[pn][i]; }
+    }
+#else
+    const int p = (H.head + k) % LB_M;
+    for (int i = 0; i < N; i++) { s[i] = H.S[p][i]; y[i] = H.Y[p][i]; }
+#endif
     double Bs[N], sBs = 0, ys = 0;
     for (int i = 0; i < N; i++) {
       double a = 0;
-      for (int j = 0; j < N; j++) a += B[i][j] * H.S[p][j];
+      for (int j = 0; j < N; j++) a += B[i][j] * s[j];
       Bs[i] = a;
     }
-    for (int i = 0; i < N; i++) { sBs += H.S[p][i] * Bs[i]; ys += H.Y[p][i] * H.S[p][i]; }
+    for (int i = 0; i < N; i++) { sBs += s[i] * Bs[i]; ys += y[i] * s[i]; }
     const double iys = lb_div(1.0, ys), isBs = lb_div(1.0, sBs);
     for (int i = 0; i < N; i++)
-      for (int j = 0; j < N; j++) B[i][j] += H.Y[p][i] * H.Y[p][j] * iys - Bs[i] * Bs[j] * isBs;
+      for (int j = 0; j < N; j++) B[i][j] += y[i] * y[j] * iys - Bs[i] * Bs[j] * isBs;
   }
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) Bm[i * N + j] = B[i][j];
@@ -435,13 +453,16 @@ PWB_HD bool lb_subsm(const double* x, const double* g, const double* lo, const d
 // NBD >= 0: every variable has that bound type, known at compile time (the bound-type tests fold away).
 template <int N, int NBD = -1>
 struct LbSolver {
-  double* st;     // caller storage, LB_STORAGE(N) doubles: the WHOLE state lives there (on the device: shared memory,
-                  // so a kernel that interleaves several searches keeps one pointer per search in registers)
-  // layout: (s, y) ring | z d t r | line-search record (20) | x g | B | iwhere (N ints in N doubles) | scratch |
-  //         lo hi | nbd (N ints in N doubles) | scalars
-  static constexpr int O_Z = 2 * LB_M * N, O_LS = O_Z + 4 * N, O_X = O_LS + 20, O_G = O_X + N, O_B = O_G + N,
+  double* st;     // caller storage, LB_STATE(N) doubles: the state touched on every call lives there (on the device:
+                  // shared memory, so a kernel that interleaves several searches keeps one pointer per search)
+  double* hs;     // the (s, y) ring, LB_HISTORY(N) doubles: read once per iteration (lb_build_B), one pair written;
+                  // behind the state by default, or anywhere else (a kernel short of shared memory keeps it in
+                  // global memory: the ring is 36 % of the storage and is read ahead of its use)
+  // layout: z d t r | line-search record (20) | x g | B | iwhere (N ints in N doubles) | scratch |
+  //         lo hi | nbd (N ints in N doubles) | scalars [| (s, y) ring]
+  static constexpr int O_Z = 0, O_LS = O_Z + 4 * N, O_X = O_LS + 20, O_G = O_X + N, O_B = O_G + N,
                        O_IW = O_B + N * N, O_SCR = O_IW + N, O_LO = O_SCR + 4 * N + 3 * N * N, O_HI = O_LO + N,
-                       O_NBD = O_HI + N, O_SC = O_NBD + N, SIZE = O_SC + 8;
+                       O_NBD = O_HI + N, O_SC = O_NBD + N, STATE = O_SC + 8, SIZE = STATE + 2 * LB_M * N;
   // scalars: doubles theta, sbgnrm, fold, gdold, stp, f; ints (in two doubles) iter, ifun, col+head, flags
   enum { F_CNSTND = 1, F_BOXED = 2, F_STARTED = 4, F_RUNNING = 8 };
 
@@ -464,7 +485,12 @@ struct LbSolver {
 
   // x0 is projected into the box; the caller then evaluates (f, g) at xs()
   PWB_HD void init(double* storage, const double* x0, const double* lo_, const double* hi_, const int* nbd_in) {
-    st = storage;
+    init(storage, storage + STATE, x0, lo_, hi_, nbd_in);
+  }
+  PWB_HD void init(double* state, double* history, const double* x0, const double* lo_, const double* hi_,
+                   const int* nbd_in) {
+    st = state;
+    hs = history;
     double* const x = st + O_X;
     double* const lo = st + O_LO; double* const hi = st + O_HI;
     int* const nb = reinterpret_cast<int*>(st + O_NBD);
@@ -500,8 +526,8 @@ struct LbSolver {
     LbLineSearch* const ls = reinterpret_cast<LbLineSearch*>(st + O_LS);
     const int* const nb = reinterpret_cast<const int*>(st + O_NBD);
     LbHistory<N> H;
-    H.S = reinterpret_cast<double (*)[N]>(st);
-    H.Y = reinterpret_cast<double (*)[N]>(st + LB_M * N);
+    H.S = reinterpret_cast<double (*)[N]>(hs);
+    H.Y = reinterpret_cast<double (*)[N]>(hs + LB_M * N);
     H.col = colhead() & 255; H.head = colhead() >> 8;
     int fl = flags();
     const bool cnstnd = fl & F_CNSTND, boxed = fl & F_BOXED;
@@ -614,7 +640,8 @@ struct LbSolver {
   }
 };
 
-static_assert(LbSolver<3>::SIZE == LB_STORAGE(3) && LbSolver<1>::SIZE == LB_STORAGE(1), "LB_STORAGE out of step with LbSolver");
+static_assert(LbSolver<3>::SIZE == LB_STORAGE(3) && LbSolver<1>::SIZE == LB_STORAGE(1) &&
+              LbSolver<3>::STATE == LB_STATE(3), "LB_STORAGE / LB_STATE out of step with LbSolver");
 
 // Obj must provide:  void fg(const double* x, double& f, double* g);
 // (f and the bound-aware forward-difference gradient; on device it is warp-cooperative and every

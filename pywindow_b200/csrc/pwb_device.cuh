@@ -351,7 +351,20 @@ __device__ __forceinline__ void group_min_clear_narrow(const GroupAtoms& A, cons
     double m[K];
 #pragma unroll
     for (int k = 0; k < K; k++) m[k] = PWB_INF;
-    for (int t = cb + A.gl; t < ce; t += G) {
+    // four atoms per step, loaded before any of them is used: with one or two lanes per problem the tile comes from
+    // L1 / L2 and the loop is bound by the latency of these loads
+    int t = cb + A.gl;
+    for (; t + 3 * G < ce; t += 4 * G) {
+      const double4 q[4] = {A.p[t], A.p[t + G], A.p[t + 2 * G], A.p[t + 3 * G]};
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          double dx = q[u].x - px[k], dy = q[u].y - py[k], dz = q[u].z - pz[k];
+          m[k] = dmin(m[k], sq3(dx, dy, dz));
+        }
+    }
+    for (; t < ce; t += G) {
       const double4 q = A.p[t];
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -464,6 +477,132 @@ __device__ __forceinline__ void group_min_clear_pruned(const GroupAtoms& A, cons
     for (int s = K; s < G; s <<= 1) v = dmin(v, __shfl_xor_sync(A.mask, v, s, G));
 #pragma unroll
     for (int k = 0; k < K; k++) out[k] = dmin(out[k], __shfl_sync(A.mask, v, k, G));
+  }
+}
+
+// ---- survivor lists: the objective of a search that stays near a reference point ------------------------------
+// a(p) = min_i(|x_i - p| - r_i) is 1-Lipschitz: for every p within R of a reference point p_ref with clearance
+// a_ref, an atom with |x_i - p_ref| - r_i > a_ref + 2R has |x_i - p| - r_i > a_ref + R >= a(p) and cannot attain the
+// minimum.  group_build_list keeps the indices of the other atoms (ascending); group_min_list evaluates a stencil of
+// K points over them.  Per atom sqrt(d2) - r instead of per class sqrt(min d2) - r_c: the same doubles, because sqrt
+// is monotone -- so the result is bit-identical to group_min_clear for every point of the ball.
+template <int G>
+__device__ __forceinline__ int group_build_list(const GroupAtoms& A, double cx, double cy, double cz, double a_ref,
+                                                double two_r, unsigned short* lst, unsigned short* lcls, int cap) {
+  const int gbase_bit = (threadIdx.x & 31) & ~(G - 1);
+  int n = 0;
+  for (int c = 0; c < A.ncls; c++) {
+    if (A.gl == 0) lcls[c] = (unsigned short)min(n, cap);      // where class c starts in the list
+    const int cb = A.cls[c], ce = A.cls[c + 1];
+    if (cb == ce) continue;
+    const double th = a_ref + A.p[cb].w + two_r + 1e-9;          // margin >> the rounding of d2 and of the sum
+    const double th2 = th >= 0.0 ? th * th * (1.0 + 1e-12) : -1.0;
+    for (int t0 = cb; t0 < ce; t0 += G) {
+      const int t = t0 + A.gl;
+      bool keep = false;
+      if (t < ce) {
+        const double4 q = A.p[t];
+        const double dx = q.x - cx, dy = q.y - cy, dz = q.z - cz;
+        keep = sq3(dx, dy, dz) <= th2;
+      }
+      const unsigned bits = (__ballot_sync(A.mask, keep) >> gbase_bit) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u));
+      if (keep) {
+        const int pos = n + __popc(bits & ((1u << A.gl) - 1u));
+        if (pos < cap) lst[pos] = (unsigned short)t;
+      }
+      n += __popc(bits);
+    }
+  }
+  if (A.gl == 0) lcls[A.ncls] = (unsigned short)min(n, cap);
+  return n <= cap ? n : -1;
+}
+
+// group_min_clear over the list: the list is ascending, i.e. sorted by class like the atoms, and lcls[c] is where
+// class c starts in it -- same class-wise reduce-before-sqrt scheme, one sqrt per (class, point).
+template <int G, int K>
+__device__ __forceinline__ void group_min_clear_list(const GroupAtoms& A, const unsigned short* lst,
+                                                     const unsigned short* lcls, const double* px, const double* py,
+                                                     const double* pz, double* out) {
+#pragma unroll
+  for (int k = 0; k < K; k++) out[k] = PWB_INF;
+  if constexpr (G < K) {
+    for (int c = 0; c < A.ncls; c++) {
+      const int lb = lcls[c], le = lcls[c + 1];
+      if (lb == le) continue;
+      double m[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) m[k] = PWB_INF;
+      for (int t = lb + A.gl; t < le; t += G) {
+        const double4 q = A.p[lst[t]];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+          m[k] = dmin(m[k], sq3(dx, dy, dz));
+        }
+      }
+      const double rc = A.p[A.cls[c]].w;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int s = 1; s < G; s <<= 1) m[k] = dmin(m[k], __shfl_xor_sync(A.mask, m[k], s, G));
+        out[k] = dmin(out[k], sqrt(m[k]) - rc);
+      }
+    }
+  } else {
+    constexpr int CPG = G / K;
+    for (int c0 = 0; c0 < A.ncls; c0 += CPG) {
+      double mine = PWB_INF;
+      const int cend = min(A.ncls, c0 + CPG);
+      for (int c = c0; c < cend; c++) {
+        const int lb = lcls[c], le = lcls[c + 1];
+        if (lb == le) continue;
+        double m[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) m[k] = PWB_INF;
+        for (int t = lb + A.gl; t < le; t += G) {
+          const double4 q = A.p[lst[t]];
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+            m[k] = dmin(m[k], sq3(dx, dy, dz));
+          }
+        }
+        const int slot = (c - c0) * K;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const double red = group_min_nonneg<G>(A.mask, m[k]);
+          if (A.gl == slot + k) mine = red;
+        }
+      }
+      double v = PWB_INF;
+      if (mine < PWB_INF) v = sqrt(mine) - A.p[A.cls[min(A.ncls - 1, c0 + A.gl / K)]].w;
+#pragma unroll
+      for (int s = K; s < G; s <<= 1) v = dmin(v, __shfl_xor_sync(A.mask, v, s, G));
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = dmin(out[k], __shfl_sync(A.mask, v, k, G));
+    }
+  }
+}
+
+template <int G, int K>
+__device__ __forceinline__ void group_min_list(const GroupAtoms& A, const unsigned short* lst, int nl, const double* px,
+                                               const double* py, const double* pz, double* out) {
+  double m[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) m[k] = PWB_INF;
+  for (int e = A.gl; e < nl; e += G) {
+    const double4 q = A.p[lst[e]];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
+      m[k] = dmin(m[k], sqrt(sq3(dx, dy, dz)) - q.w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+#pragma unroll
+    for (int s = 1; s < G; s <<= 1) m[k] = dmin(m[k], __shfl_xor_sync(A.mask, m[k], s, G));
+    out[k] = m[k];
   }
 }
 

@@ -30,6 +30,7 @@ struct Ws {   // resolved workspace pointers
   // Molecules whose atom tiles do not fit the 227 KB of shared memory (> ~2 900 atoms): the per-CTA / per-warp
   // atom arrays of k_prepare, k_rays and k_windows live here instead (read through L1 / L2); nullptr otherwise.
   double* atom_scratch;
+  double* opt_hist;      // [F][LB_HISTORY(3)] (s, y) rings of k_opt_pore when they are not kept in shared memory
   long long scratch_item;   // doubles of scratch per item
 };
 
@@ -366,7 +367,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 // G = 16 / 8 with shared tiles 2.56 / 3.28 (same 32 problems, fewer warps to hide latency); G = 8 with the tiles
 // read through L1 / L2 (1.3 KB of state per problem in shared memory, 96 problems per SM at 80 registers) 1.96.
 #ifndef OPT_G
-#define OPT_G 8                      // lanes per problem (4, 8, 16 or 32)
+#define OPT_G 4                      // lanes per problem (1 ... 32)
 #endif
 #ifndef OPT_ATOMS_SMEM
 #define OPT_ATOMS_SMEM 0             // atom tile of each problem in shared memory (else read through L1 / L2)
@@ -376,7 +377,7 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 #endif
 constexpr int OPT_WARPS = OPT_WARPS_N;
 #ifndef OPT_MINB
-#define OPT_MINB 6                   // CTAs per SM the register budget must allow (80 registers per thread)
+#define OPT_MINB 4                   // CTAs per SM the register budget must allow (112 registers per thread)
 #endif
 // doubles of shared memory per problem: double4[NA] atoms (optional), the solver state (incl. bounds), class
 // starts (17 ints, padded to 20); even, so that the double4 tiles stay 16-byte aligned
@@ -391,7 +392,34 @@ constexpr int OPT_WARPS = OPT_WARPS_N;
 #define OPT_PRUNE_RBIG 0.5           // re-reference when two consecutive evaluations lie farther than this (A)
 #endif
 // (+ with OPT_PRUNE: reference point [3], its clearance, and float[NA] reference squared distances)
-#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) ((((SMEM_ATOMS) ? (NA) * 4 : 0) + LB_STORAGE(3) + 10 + (OPT_PRUNE ? 4 + ((NA) + 1) / 2 : 0) + 1) & ~(size_t)1)
+#ifndef OPT_HIST_GLOBAL
+#define OPT_HIST_GLOBAL 0            // 1: (s, y) ring of every search in global memory, 0.9 instead of 1.4 KB of shared
+                                     // memory per problem (pays only with one or two lanes per problem)
+#endif
+#define OPT_SOLVER_DOUBLES (OPT_HIST_GLOBAL ? LB_STATE(3) : LB_STORAGE(3))
+#ifndef OPT_LIST
+#define OPT_LIST 1                   // survivor list of the atoms that can attain the minimum near a reference point
+#endif
+#ifndef OPT_LIST_CAP
+#define OPT_LIST_CAP 64              // entries (16-bit atom indices)
+#endif
+#ifndef OPT_LIST_CLASSWISE
+#define OPT_LIST_CLASSWISE 0
+#endif
+#ifndef OPT_LIST_EAGER
+#define OPT_LIST_EAGER 0             // 1: re-reference at the first evaluation outside the ball
+#endif
+#ifndef OPT_LIST_R
+#define OPT_LIST_R 0.5               // radius (A) of the ball around the reference point the list is valid for
+#endif
+#define OPT_PROB_RAW(NA, SMEM_ATOMS) (((SMEM_ATOMS) ? (NA) * 4 : 0) + OPT_SOLVER_DOUBLES + 10 + (OPT_PRUNE ? 4 + ((NA) + 1) / 2 : 0) + (OPT_LIST ? 4 + OPT_LIST_CAP / 4 + 5 : 0))
+// The lanes of a warp address the SAME offset in 32 / G different problems: the per-problem stride is padded to
+// OPT_STRIDE_REM (mod 16 doubles) so that those addresses fall into different shared-memory banks
+// (2: up to 8 problems per warp two banks apart ... ; 1: 16 problems)
+#ifndef OPT_STRIDE_REM
+#define OPT_STRIDE_REM ((OPT_G <= 2 && !OPT_ATOMS_SMEM) ? 1 : 2)
+#endif
+#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) (OPT_PROB_RAW(NA, SMEM_ATOMS) + ((OPT_STRIDE_REM + 16 - OPT_PROB_RAW(NA, SMEM_ATOMS) % 16) % 16))
 
 template <int G, bool GENERAL, bool ATOMS_SMEM>
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)
@@ -403,16 +431,24 @@ k_opt_pore(pwb_batch b, Ws ws) {
   const unsigned mask = group_mask<G>(lane);
   double* smp = sm + (size_t)(w * PPW + lane / G) * OPT_PROB_DOUBLES(b.max_atoms, ATOMS_SMEM);
   double4* p4 = (double4*)smp;                                        // x, y, z, radius (if ATOMS_SMEM)
-  double* hist = smp + (ATOMS_SMEM ? (size_t)b.max_atoms * 4 : 0);    // [LB_STORAGE(3)] solver state
-  int* cls = (int*)(hist + LB_STORAGE(3));                            // [PWB_MAX_TYPES+1] class starts
+  double* hist = smp + (ATOMS_SMEM ? (size_t)b.max_atoms * 4 : 0);    // [OPT_SOLVER_DOUBLES] solver state
+  int* cls = (int*)(hist + OPT_SOLVER_DOUBLES);                       // [PWB_MAX_TYPES+1] class starts
 #if OPT_PRUNE
   double* pref = (double*)(cls + 20);                                 // [4] reference point and its clearance
   float* d2ref = (float*)(pref + 4);                                  // [NA] squared distances to the reference point
   bool have_ref = false, last_far = false;
 #endif
+#if OPT_LIST
+  double* lref = (double*)(cls + 20);                                 // [4] reference point (the clearance there is in a register)
+  unsigned short* lst = (unsigned short*)(lref + 4);                  // [OPT_LIST_CAP] atoms that can attain the minimum
+  unsigned short* lcls = lst + OPT_LIST_CAP;                          // [PWB_MAX_TYPES+1] class starts inside the list
+  int nl = -2;                                                        // -2 no list yet, -1 too many survivors
+  bool last_far = false;
+#endif
   int* queue = ws.item_i + I_QUEUE;                                   // zeroed by run_opt before the launch
   LbSolver<3, GENERAL ? -1 : 2> S;
   S.st = hist;
+  S.hs = OPT_HIST_GLOBAL ? nullptr : hist + LB_STATE(3);
   GroupAtoms A;
   A.gl = gl; A.mask = mask; A.cls = cls; A.ncls = b.n_types; A.n = 0; A.p = p4;
   const int* orig = nullptr;
@@ -449,6 +485,9 @@ k_opt_pore(pwb_batch b, Ws ws) {
           int nb3[3] = {2, 2, 2};
           bool search = true, bad = false;
           nfev = 0;
+#if OPT_LIST
+          nl = -2; last_far = false;
+#endif
           if (b.centre_override) {
             const double* o = b.centre_override + (size_t)item * 3;
             c[0] = o[0]; c[1] = o[1]; c[2] = o[2];
@@ -478,7 +517,7 @@ k_opt_pore(pwb_batch b, Ws ws) {
           if (bad) {   // scipy raises on inverted bounds; the reference has no handler
             if (gl == 0) { iiv[I_STATUS] |= PWB_ST_OPT_BOUNDS; rec[PWB_REC_STATUS] = iiv[I_STATUS]; }
           } else if (search) {
-            S.init(hist, c, lo3, hi3, nb3);
+            S.init(hist, OPT_HIST_GLOBAL ? ws.opt_hist + (size_t)item * LB_HISTORY(3) : hist + LB_STATE(3), c, lo3, hi3, nb3);
 #if OPT_PRUNE
             have_ref = false; last_far = false;
 #endif
@@ -512,7 +551,8 @@ k_opt_pore(pwb_batch b, Ws ws) {
       {
         // distance of this evaluation's stencil from the reference point (+ the forward-difference steps)
         const double ex = x[0] - pref[0], ey = x[1] - pref[1], ez = x[2] - pref[2];
-        const double delta = sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-12) + 4e-8;
+        const double hmax = fmax(fabs(h[0]), fmax(fabs(h[1]), fabs(h[2])));
+        const double delta = (sqrt(ex * ex + ey * ey + ez * ez) + hmax) * (1.0 + 1e-12) + 1e-12;
         const bool far = !(delta <= OPT_PRUNE_RBIG);
         const bool store = !have_ref || (far && last_far);     // two far evaluations in a row: the search has moved
         last_far = far && !store;
@@ -534,6 +574,42 @@ k_opt_pore(pwb_batch b, Ws ws) {
           have_ref = true;
         }
         __syncwarp(mask);
+      }
+#elif OPT_LIST
+      {
+        double delta = PWB_INF;
+        if (nl != -2) {
+          const double ex = x[0] - lref[0], ey = x[1] - lref[1], ez = x[2] - lref[2];
+          // every point of the stencil is within |x - ref| + max |h| of the reference point
+          const double hmax = fmax(fabs(h[0]), fmax(fabs(h[1]), fabs(h[2])));
+          delta = (sqrt(ex * ex + ey * ey + ez * ez) + hmax) * (1.0 + 1e-12) + 1e-12;
+        }
+        const bool far = !(delta <= OPT_LIST_R);
+        // (per atom for >= 4 lanes per problem: more square roots but no reduction per class in the dependent chain
+        // -- 1.50 against 1.78 ms; class-wise below that)
+        if (nl >= 0 && !far) {
+          if (G >= 4 && !OPT_LIST_CLASSWISE) group_min_list<G, 4>(A, lst, nl, px, py, pz, m);
+          else group_min_clear_list<G, 4>(A, lst, lcls, px, py, pz, m);
+          last_far = false;
+        }
+        else {
+          group_min_clear<G, 4>(A, px, py, pz, m);
+          if (nl == -2 || (far && (last_far || OPT_LIST_EAGER))) {   // first evaluation, or two far ones in a row: the search moved
+            __syncwarp(mask);
+            for (int i = gl; i < 3; i += G) lref[i] = x[i];
+            nl = group_build_list<G>(A, x[0], x[1], x[2], m[0], 2.0 * OPT_LIST_R, lst, lcls, OPT_LIST_CAP);
+            last_far = false;
+            __syncwarp(mask);
+          } else last_far = far;
+        }
+#ifdef OPT_LIST_CHECK
+        {
+          double m2[4];
+          group_min_clear<G, 4>(A, px, py, pz, m2);
+          if (m2[0] != m[0] || m2[1] != m[1] || m2[2] != m[2] || m2[3] != m[3])
+            if (gl == 0) printf("list mismatch item %d nl %d delta %.3e m %.17g %.17g m2 %.17g %.17g\n", item, nl, delta, m[0], m[1], m2[0], m2[1]);
+        }
+#endif
       }
 #else
       group_min_clear<G, 4>(A, px, py, pz, m);
@@ -1791,6 +1867,7 @@ int pwb_workspace_layout(int F, int total_atoms, int max_atoms, int ray_cap, int
   L->big_i = o; o = align_up(o + big * 2 * sizeof(int));
   L->atom_scratch = o;
   if (big_atoms(max_atoms)) o = align_up(o + (size_t)F * scratch_item_doubles(F, max_atoms, ray_cap, win_cap) * sizeof(double));
+  L->opt_hist = o; o = align_up(o + (size_t)F * LB_HISTORY(3) * sizeof(double));
   L->total = o;
   return 0;
 }
@@ -1853,6 +1930,7 @@ static int resolve(const pwb_batch* b, Ws* w) {
   const bool big = big_atoms(b->max_atoms);
   w->atom_scratch = big ? (double*)(p + L.atom_scratch) : nullptr;
   w->scratch_item = big ? (long long)scratch_item_doubles(b->n_items, b->max_atoms, b->ray_cap, b->win_cap) : 0;
+  w->opt_hist = (double*)(p + L.opt_hist);
   return 0;
 }
 
@@ -2031,6 +2109,7 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
       u.clear_k += (size_t)first * b->ray_cap; u.clear_pos += (size_t)first * b->ray_cap;
       u.clear_a2 += (size_t)first * b->ray_cap; u.labels += (size_t)first * b->ray_cap;
       u.win_k += (size_t)first * b->win_cap;
+      u.opt_hist += (size_t)first * LB_HISTORY(3);
       if (b->ray_cap > KNN_SMEM_CAP) { u.big_pts += (size_t)first * b->ray_cap * 4; u.big_i += (size_t)first * b->ray_cap * 2; }
       cudaStream_t sg = c->streams[g];
       // (`staging_idle`: the batch depends on nothing queued on `s` -- its input comes from the host and its

@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     lib.pwb_abi_version.restype = ctypes.c_int
-    assert lib.pwb_abi_version() == 3
+    assert lib.pwb_abi_version() == 4
     from pywindow_b200 import _lib
     assert set(_lib.EXPORTS) <= declared
 
@@ -32,10 +32,12 @@ def test_workspace_layout_is_consistent():
     L = _lib.load()
     lay = _lib.WsLayout()
     L.pwb_workspace_layout(10, 1680, 168, 896, 16, ctypes.byref(lay))
-    assert lay.total == L.pwb_workspace_bytes(10, 1680, 168, 896, 16) and lay.atom_scratch == lay.total
+    assert lay.total == L.pwb_workspace_bytes(10, 1680, 168, 896, 16)
+    assert lay.atom_scratch == lay.opt_hist                    # no atom scratch for molecules that fit shared memory
+    assert lay.total - lay.opt_hist >= 10 * 60 * 8             # the (s, y) rings of the pore-centre searches
     big = _lib.WsLayout()
     L.pwb_workspace_layout(2, 12000, 6000, 1024, 16, ctypes.byref(big))          # atoms beyond shared memory
-    assert big.total > big.atom_scratch >= big.win_k
+    assert big.total > big.opt_hist > big.atom_scratch >= big.win_k
     offs = [lay.atoms, lay.atom_idx, lay.item_d, lay.item_i, lay.clear_k, lay.clear_pos, lay.clear_a2, lay.labels, lay.win_k]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
 
