@@ -413,13 +413,13 @@ constexpr int OPT_WARPS = OPT_WARPS_N;
 #define OPT_LIST_R 0.5               // radius (A) of the ball around the reference point the list is valid for
 #endif
 #define OPT_PROB_RAW(NA, SMEM_ATOMS) (((SMEM_ATOMS) ? (NA) * 4 : 0) + OPT_SOLVER_DOUBLES + 10 + (OPT_PRUNE ? 4 + ((NA) + 1) / 2 : 0) + (OPT_LIST ? 4 + OPT_LIST_CAP / 4 + 5 : 0))
-// The lanes of a warp address the SAME offset in 32 / G different problems: the per-problem stride is padded to
-// OPT_STRIDE_REM (mod 16 doubles) so that those addresses fall into different shared-memory banks
-// (2: up to 8 problems per warp two banks apart ... ; 1: 16 problems)
-#ifndef OPT_STRIDE_REM
-#define OPT_STRIDE_REM ((OPT_G <= 2 && !OPT_ATOMS_SMEM) ? 1 : 2)
-#endif
+// The lanes of a warp address the SAME offset in 32 / G different problems; OPT_STRIDE_REM pads the per-problem stride
+// to that remainder (mod 16 doubles) to spread those addresses over the shared-memory banks
+#ifdef OPT_STRIDE_REM
 #define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) (OPT_PROB_RAW(NA, SMEM_ATOMS) + ((OPT_STRIDE_REM + 16 - OPT_PROB_RAW(NA, SMEM_ATOMS) % 16) % 16))
+#else      // (measured: no effect -- the accesses are not bank-conflict bound; even, so that double4 tiles stay aligned)
+#define OPT_PROB_DOUBLES(NA, SMEM_ATOMS) ((OPT_PROB_RAW(NA, SMEM_ATOMS) + 1) & ~(size_t)1)
+#endif
 
 template <int G, bool GENERAL, bool ATOMS_SMEM>
 __global__ void __launch_bounds__(OPT_WARPS * 32, OPT_MINB)

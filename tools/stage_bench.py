@@ -50,4 +50,5 @@ h = rec.cpu().numpy()
 fp = hashlib.sha1(np.ascontiguousarray(h).tobytes()).hexdigest()[:12]
 print(os.environ.get("PWB_LIBRARY", "default"), "ms/10k:", " ".join(f"{n}={v:.3f}" for (n, _), v in zip(stages, ms)),
       f"sum={ms.sum():.3f}", "records", fp, "opt_d_sum %.9f" % h[:, L.REC_OPT_D].sum(), "nfev_mean %.1f" % h[:, L.REC_OPT_NFEV].mean(),
+      "nfev p50/p99/p999/max %d/%d/%d/%d" % tuple(np.percentile(h[:, L.REC_OPT_NFEV], [50, 99, 99.9, 100])),
       "win4 %.4f" % (h[:, L.REC_NWIN] == 4).mean())
