@@ -142,6 +142,11 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap);
 int pwb_ctx_destroy(pwb_ctx* ctx);
 /* Cut batches into `chunks` (1..8) sub-batches pipelined over internal streams (default 1).      */
 int pwb_ctx_set_chunks(pwb_ctx* ctx, int chunks);
+/* Test switches.  PWB_OPTION_OPT_NO_LIST = 1: the pore-centre search (pwb_opt_pore) evaluates its objective over every
+ * atom at every point instead of over its survivor lists -- the results must be bit-identical either way
+ * (tests/test_gpu_parity.py).                                                                                   */
+#define PWB_OPTION_OPT_NO_LIST 1
+int pwb_ctx_set_option(pwb_ctx* ctx, int option, int value);
 
 /* bytes of workspace for a batch of n_items with total_atoms atoms, the largest item having max_atoms */
 size_t pwb_workspace_bytes(int n_items, int total_atoms, int max_atoms, int ray_cap, int win_cap);

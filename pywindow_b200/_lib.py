@@ -22,9 +22,10 @@ REC_WIN0 = 28
 ST_OPT_BOUNDS, ST_NO_CLEAR_RAY, ST_RAY_CAP, ST_WIN_CAP, ST_WIN_DROPPED, ST_WIN_NEGATIVE, ST_BAD_ITEM = 1, 2, 4, 8, 16, 32, 64
 RAY_TILE = 1024
 STAGE_SCALARS, STAGE_AVGD, STAGE_OPT, STAGE_RAYS, STAGE_CLUSTER, STAGE_WINDOWS, STAGE_ALL = 1, 2, 4, 8, 16, 32, 63
+OPTION_OPT_NO_LIST = 1          # PWB_OPTION_OPT_NO_LIST
 
 EXPORTS = [
-    "pwb_abi_version", "pwb_last_error", "pwb_ctx_create", "pwb_ctx_destroy", "pwb_ctx_set_chunks", "pwb_workspace_bytes",
+    "pwb_abi_version", "pwb_last_error", "pwb_ctx_create", "pwb_ctx_destroy", "pwb_ctx_set_chunks", "pwb_ctx_set_option", "pwb_workspace_bytes",
     "pwb_workspace_layout", "pwb_ray_capacity", "pwb_frame_scalars", "pwb_average_diameter",
     "pwb_opt_pore", "pwb_ray_search", "pwb_cluster", "pwb_window_refine", "pwb_full_analysis_batch",
     "pwb_full_analysis_host", "pwb_full_analysis_host_async", "pwb_launch_count", "pwb_fma_peak", "pwb_dm_workspace_bytes",
@@ -77,6 +78,8 @@ def load():
     L.pwb_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     L.pwb_ctx_destroy.argtypes = [vp]
     L.pwb_ctx_set_chunks.argtypes = [vp, ci]
+    L.pwb_ctx_set_option.argtypes = [vp, ci, ci]
+    L.pwb_ctx_set_option.restype = ci
     L.pwb_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
     L.pwb_workspace_bytes.restype = ctypes.c_size_t
     L.pwb_workspace_layout.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(WsLayout)]

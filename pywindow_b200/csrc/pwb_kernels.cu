@@ -32,6 +32,7 @@ struct Ws {   // resolved workspace pointers
   double* atom_scratch;
   double* opt_hist;      // [F][LB_HISTORY(3)] (s, y) rings of k_opt_pore when they are not kept in shared memory
   long long scratch_item;   // doubles of scratch per item
+  int opt_no_list;          // test switch (pwb_ctx_set_option): k_opt_pore evaluates every atom at every point
 };
 
 // shared-memory need of k_rays, the largest of the three, decides: host and layout code agree through these
@@ -587,7 +588,7 @@ k_opt_pore(pwb_batch b, Ws ws) {
         const bool far = !(delta <= OPT_LIST_R);
         // (per atom for >= 4 lanes per problem: more square roots but no reduction per class in the dependent chain
         // -- 1.50 against 1.78 ms; class-wise below that)
-        if (nl >= 0 && !far) {
+        if (nl >= 0 && !far && !ws.opt_no_list) {
           if (G >= 4 && !OPT_LIST_CLASSWISE) group_min_list<G, 4>(A, lst, nl, px, py, pz, m);
           else group_min_clear_list<G, 4>(A, lst, lcls, px, py, pz, m);
           last_far = false;
@@ -1797,6 +1798,7 @@ constexpr int PWB_MAX_CHUNKS = 8;
 struct pwb_ctx {
   Ctx c; int* d_tmp; int max_smem, num_sms;
   int chunks;                                   // sub-batches pipelined over internal streams
+  int opt_no_list;                              // pwb_ctx_set_option(PWB_OPTION_OPT_NO_LIST)
   cudaStream_t streams[PWB_MAX_CHUNKS];
   cudaEvent_t fork, join[PWB_MAX_CHUNKS];
   cudaStream_t copy_stream;                    // host -> device copies of the *_host entry points
@@ -1891,6 +1893,7 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
   CK(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   c->chunks = 1;
+  c->opt_no_list = 0;
   for (int g = 0; g < PWB_MAX_CHUNKS; g++) {
     CK(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->join[g], cudaEventDisableTiming));
@@ -1900,6 +1903,12 @@ int pwb_ctx_create(pwb_ctx** out, int device, int ray_table_cap) {
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   *out = c;
   return 0;
+}
+int pwb_ctx_set_option(pwb_ctx* c, int option, int value) {
+  if (!c) { snprintf(g_err, sizeof g_err, "null context"); return 1; }
+  if (option == PWB_OPTION_OPT_NO_LIST) { c->opt_no_list = value != 0; return 0; }
+  snprintf(g_err, sizeof g_err, "unknown option %d", option);
+  return 1;
 }
 int pwb_ctx_set_chunks(pwb_ctx* c, int chunks) {
   c->chunks = chunks < 1 ? 1 : (chunks > PWB_MAX_CHUNKS ? PWB_MAX_CHUNKS : chunks);
@@ -2072,6 +2081,7 @@ static int batch_impl(pwb_ctx* c, const pwb_batch* b, cudaStream_t s, const doub
   if (check(b)) return 1;
   Ws w;
   if (resolve(b, &w)) return 1;
+  w.opt_no_list = c->opt_no_list;
   // (huge molecules share one global scratch region sized for the whole batch: not cut into sub-batches)
   const int G = (c->chunks > 1 && b->n_items >= 64 * c->chunks && !w.atom_scratch) ? c->chunks : 1;
   // item_off lives on the device; the host variant needs atom offsets to cut the copies, which it

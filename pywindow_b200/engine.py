@@ -106,6 +106,10 @@ class Engine:
         self.chunks = int(chunks)
         self.lib.pwb_ctx_set_chunks(self._ctx, self.chunks)
 
+    def set_option(self, option, value):
+        """Test switches of the library (``_lib.OPTION_*``, include/pwb.h)."""
+        _lib.check(self.lib.pwb_ctx_set_option(self._ctx, int(option), int(value)))
+
     def close(self):
         if self._ctx:
             self.lib.pwb_ctx_destroy(self._ctx)

@@ -418,3 +418,47 @@ def test_molecule_larger_than_shared_memory(eng):
     one = eng.analyse_molecules([(small["elements"], small["coords"])]).host_records()[0]
     np.testing.assert_array_equal(both[1], rec)
     np.testing.assert_array_equal(both[0], one)
+
+
+def test_survivor_lists_of_the_pore_search_are_exact(eng):
+    """k_opt_pore evaluates its objective over the atoms that CAN attain the minimum within 0.5 A of a reference point
+    (1-Lipschitz bound, csrc/pwb_device.cuh: group_build_list).  With the lists switched off (every atom at every
+    point) the records must be bit-identical: MD frames, the same frames 150 A from the origin (forward-difference
+    steps 100 x larger), user bounds / start points (the second instantiation of the kernel), a 12-atom molecule and a
+    5 900-atom shell whose list overflows."""
+    from pywindow_b200 import _lib as L, synthetic
+    from pywindow_b200.engine import Engine
+    import torch
+    gs = [load_golden(f"md_frame{i:02d}") for i in range(4)]
+    seeds = np.stack([g["coords"] for g in gs])
+    el = [str(e) for e in gs[0]["elements"]]
+    X = synthetic.noisy_frames(seeds, 0, 3000)
+    rng = np.random.default_rng(23)
+    n = 6200
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    shell = (u * rng.uniform(46.0, 48.5, size=(n, 1)))[np.abs(u[:, 2]) < 0.955]
+    shell_el = list(np.array(["C", "H", "N", "O"])[rng.integers(0, 4, size=shell.shape[0])])
+    tiny = (["C"] * 6 + ["H"] * 6, np.concatenate([2.0 * np.eye(3), -2.0 * np.eye(3), 3.1 * np.eye(3), -3.1 * np.eye(3)]))
+    com = X[:200].mean(axis=1)
+    start = com + rng.normal(0, 0.3, size=com.shape)
+    bounds = np.stack([np.stack([start[:, i] - rng.uniform(0.2, 2.0, 200), start[:, i] + rng.uniform(0.2, 2.0, 200)], axis=1)
+                       for i in range(3)], axis=1)                      # [200, 3, 2]
+    e2 = Engine(0)
+    try:
+        out = {}
+        for no_list in (0, 1):
+            e2.set_option(L.OPTION_OPT_NO_LIST, no_list)
+            stages = L.STAGE_SCALARS | L.STAGE_OPT
+            out[no_list] = [
+                e2.analyse_frames(X, el, stages=stages).host_records(),
+                e2.analyse_frames(X[:500] + np.array([150.0, -90.0, 40.0]), el, stages=stages).host_records(),
+                e2.analyse_frames(X[:200], el, stages=stages, opt_start=start, opt_bounds=bounds.reshape(200, 6)).host_records(),
+                e2.analyse_molecules([tiny, (shell_el, shell)], stages=stages).host_records(),
+            ]
+        for a, b in zip(out[0], out[1]):
+            assert (a[:, L.REC_OPT_NFEV] > 0).all()
+            np.testing.assert_array_equal(a, b)
+        assert out[0][0][:, L.REC_OPT_NFEV].mean() > 100          # the searches really ran
+    finally:
+        e2.close()
+        torch.cuda.synchronize()
