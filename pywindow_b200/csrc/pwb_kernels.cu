@@ -366,7 +366,11 @@ k_prepare(pwb_batch b, Ws ws, int do_avg) {
 // latency bound (one instruction per ~10 cycles per warp), so what counts is problems in flight per SM times
 // work shared per instruction.  G = 32 with atom tiles in shared memory (round 1: 32 problems per SM) 2.21;
 // G = 16 / 8 with shared tiles 2.56 / 3.28 (same 32 problems, fewer warps to hide latency); G = 8 with the tiles
-// read through L1 / L2 (1.3 KB of state per problem in shared memory, 96 problems per SM at 80 registers) 1.96.
+// read through L1 / L2 (1.3 KB of state per problem in shared memory, 96 problems per SM at 80 registers) 1.96;
+// G = 4 with the objective evaluated over an exact survivor list (OPT_LIST below: the <= 64 atoms that can attain the
+// minimum within 0.5 A of a reference point, group_build_list / group_min_list) 1.52 -- what the list shortens is the
+// latency of an evaluation (a dozen loads instead of 42 per lane); 1.39 in the limit of long launches, the rest is
+// the tail of the slowest searches (5 x the mean number of evaluations).
 #ifndef OPT_G
 #define OPT_G 4                      // lanes per problem (1 ... 32)
 #endif
@@ -382,10 +386,10 @@ constexpr int OPT_WARPS = OPT_WARPS_N;
 #endif
 // doubles of shared memory per problem: double4[NA] atoms (optional), the solver state (incl. bounds), class
 // starts (17 ints, padded to 20); even, so that the double4 tiles stay 16-byte aligned
-// Exact Lipschitz pruning of the objective's atom loop (group_min_clear_pruned): bit-identical records, ~95 % of the
-// atoms skipped in late line-search steps -- and NO change in kernel time (1.956 vs 1.964 ms per 10 000 frames,
-// profiles/r2_opt_pore_variants.md): the kernel is bound by the dependent chain of the solver's bookkeeping, not by
-// the objective.  Kept as an experiment switch, off by default (it costs 0.7 KB of shared memory per problem).
+// First pruning experiment, superseded by OPT_LIST: per-atom flags (group_min_clear_pruned) -- bit-identical records,
+// ~95 % of the atoms skipped in late line-search steps and NO change in kernel time (1.956 vs 1.964 ms per 10 000
+// frames, profiles/r2_opt_pore_variants.md): the loop still visits every atom.  Off by default (0.7 KB of shared
+// memory per problem).
 #ifndef OPT_PRUNE
 #define OPT_PRUNE 0
 #endif
@@ -1571,6 +1575,10 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
     }
     return;
   }
+#if defined(WIN_STOP) && WIN_STOP == 1      // (phase timing experiment, profiles/r2_opt_pore_variants.md)
+  if (lane == 0) out[0] = bj.v;
+  return;
+#endif
   const double qx = cxs * bj.i, qy = cys * bj.i, qz = czs * bj.i;
   const double new_z = sqrt(qx * qx + qy * qy + qz * qz);
   // ---- rotation angles, octant table (utilities.py:1235-1259)
@@ -1606,6 +1614,10 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   DevZObj zo{A, -new_z};
   lbfgsb_minimize<1, DevZObj, 1>(zo, zc, zlo, zhi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
   const double wz = zc[0];
+#if defined(WIN_STOP) && WIN_STOP == 2
+  if (lane == 0) out[0] = wz;
+  return;
+#endif
   // ---- xy stage: 20x20 brute grid (first arg-min, row-major) + Nelder-Mead (utilities.py:1307-1316)
   const double glo = -d0 / 2, ghi = d0 / 2;
   const double gstep = (ghi - glo) / 19.0;
@@ -1670,6 +1682,10 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
   const double x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo), y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+#if defined(WIN_STOP) && WIN_STOP == 3
+  if (lane == 0) out[0] = x0 + y0;
+  return;
+#endif
   DevXYObj xo{A, NL, wz, x0, y0, -1.0, 0.0, 0.0, 0.0, 0.0, false};
   {
     // same 1-Lipschitz argument as warp_build_near, radius WIN_TIGHT_RHO around the grid optimum
@@ -1725,6 +1741,10 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
 
 // Static (item, window) -> warp map: a work queue like k_opt_pore's was measured 45 % SLOWER here (warps
 // of a CTA drift into different phases of this 200 KB kernel and miss in the instruction cache).
+// (Measured and rejected: running the Nelder-Mead searches of a CTA's four windows together on one warp, eight lanes
+// each, the other warps waiting at a barrier -- bit-identical records, 2.25 instead of 1.63 ms per 10 000 frames.
+// The kernel is latency bound with idle issue slots; sharing the scalar simplex bookkeeping saves instructions nobody
+// was waiting for and lengthens every evaluation: four atoms per lane in series, group shuffles, divergent groups.)
 template <bool BIG>
 __global__ void __launch_bounds__(WIN_WARPS * 32, WIN_MINB)
 k_windows(pwb_batch b, Ws ws) {
