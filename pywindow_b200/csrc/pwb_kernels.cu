@@ -1517,7 +1517,17 @@ PWB_MATHFN double angle_between(double x0, double x1, double x2, double y0, doub
 #ifndef WIN_MINB
 #define WIN_MINB 6
 #endif
-// one (item, window) on one warp; `smw` is the warp's private shared memory (WIN_WARP_DOUBLES)
+#ifndef WIN_SPLIT
+#define WIN_SPLIT 2                  // 2: window search in two kernels, cut behind the grid search (4: behind the z
+                                     // stage; 3: three kernels; 0: one)
+#endif
+// one (item, window) on one warp; `smw` is the warp's private shared memory (WIN_WARP_DOUBLES).
+// PARTS is a bit mask of what this instantiation runs: 1 = rescan + rotation + z stage, 2 = 20 x 20 grid search,
+// 4 = tight list + Nelder-Mead + output; 7 = the whole window in one kernel.  With WIN_SPLIT the function is cut into
+// two or three kernels so that the warps resident on an SM walk the same part of this large function (instruction
+// cache): a kernel that does not finish the window leaves (x0, y0, wz, new_z) in the window's record slot; the next
+// one loads and rotates the atoms again (same expressions, same values), rebuilds d0 and the near list and goes on.
+template <int PARTS>
 __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, const int item, const int win,
                                             const int lane, double* smw, double* atoms_w) {
   int* iiv = ws.item_i + (size_t)item * ITEM_I;
@@ -1532,6 +1542,12 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   int* cls = (int*)(cr + PWB_MAX_TYPES);     // [PWB_MAX_TYPES+1]
   int* ncs = cls + PWB_MAX_TYPES + 1;        // [PWB_MAX_TYPES+1] near-list class starts
   double* hist = cr + PWB_MAX_TYPES + 32;                               // [LB_STORAGE(1)] z-stage L-BFGS state
+  double h_x0 = 0, h_y0 = 0, h_wz = 0, h_newz = 0;
+  if (!(PARTS & 1)) {
+    h_x0 = out[0]; h_y0 = out[1]; h_wz = out[2]; h_newz = out[3];
+    if (h_x0 != h_x0) return;                                           // dropped in phase 1 (NaNs stay)
+    __syncwarp();
+  }
   const double shx = idv[D_SHIFT], shy = idv[D_SHIFT + 1], shz = idv[D_SHIFT + 2];
   for (int a = lane; a < n; a += 32) {
     const double* q = ws.atoms + (size_t)(off + a) * 4;
@@ -1552,6 +1568,8 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   const double cxs = vx / chunks, cys = vy / chunks, czs = vz / chunks;
   // same bracketing argument as in k_rays: two candidate steps per atom, lanes stride over atoms
   ValIdx bj; bj.v = PWB_INF; bj.i = 0x7fffffff;
+  double new_z = h_newz;
+  if (PARTS & 1) {
   {
     const double cc = cxs * cxs + cys * cys + czs * czs, icc = 1.0 / cc;
     const double jmax = (double)(chunks > 0 ? chunks - 1 : 0);
@@ -1580,7 +1598,8 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   return;
 #endif
   const double qx = cxs * bj.i, qy = cys * bj.i, qz = czs * bj.i;
-  const double new_z = sqrt(qx * qx + qy * qy + qz * qz);
+  new_z = sqrt(qx * qx + qy * qy + qz * qz);
+  }
   // ---- rotation angles, octant table (utilities.py:1235-1259)
   double a1 = angle_between(vx, vy, 0.0, 1.0, 0.0, 0.0);
   double a2 = angle_between(vx, vy, vz, 0.0, 0.0, 1.0);
@@ -1610,10 +1629,13 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   warp_min_clear<1>(A, &zero, &zero, &zero, m0);
   const double d0 = m0[0] * 2.0;
   // ---- z stage: L-BFGS-B from 0 with lower bound -new_z (utilities.py:1296-1305)
-  double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nitz;
-  DevZObj zo{A, -new_z};
-  lbfgsb_minimize<1, DevZObj, 1>(zo, zc, zlo, zhi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
-  const double wz = zc[0];
+  double wz = h_wz;
+  if (PARTS & 1) {
+    double zc[1] = {0.0}, zlo[1] = {-new_z}, zhi[1] = {0.0}, fz; int nitz;
+    DevZObj zo{A, -new_z};
+    lbfgsb_minimize<1, DevZObj, 1>(zo, zc, zlo, zhi, nullptr, 2.220446049250313e-09, 1e-5, 20, 15000, &fz, &nitz, hist);
+    wz = zc[0];
+  }
 #if defined(WIN_STOP) && WIN_STOP == 2
   if (lane == 0) out[0] = wz;
   return;
@@ -1630,6 +1652,8 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   // that distance.  Only those candidates (the cap of the clearance cone, typically 20-40 points) are
   // evaluated; every evaluated value is computed exactly as before and the arg-min rule (value, then
   // row-major index) does not depend on the evaluation order.
+  double x0 = h_x0, y0 = h_y0;
+  if (PARTS & 2) {
   double* cgrid = hist + LB_STORAGE(1);                        // [100] coarse clearances
   unsigned short* clist = (unsigned short*)(cgrid + 100);      // [300] candidate grid indices
   ValIdx gb; gb.v = PWB_INF; gb.i = 0x7fffffff;
@@ -1681,7 +1705,12 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
   }
   gb = warp_vi_min(gb);
   const int ix = gb.i / 20, iy = gb.i - ix * 20;
-  const double x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo), y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+  x0 = __dadd_rn(__dmul_rn((double)ix, gstep), glo); y0 = __dadd_rn(__dmul_rn((double)iy, gstep), glo);
+  }
+  if (!(PARTS & 4)) {                                          // hand over to the next kernel through the record slot
+    if (lane == 0) { out[0] = x0; out[1] = y0; out[2] = wz; out[3] = new_z; }
+    return;
+  }
 #if defined(WIN_STOP) && WIN_STOP == 3
   if (lane == 0) out[0] = x0 + y0;
   return;
@@ -1745,7 +1774,7 @@ __device__ __forceinline__ void window_slot(const pwb_batch& b, const Ws& ws, co
 // each, the other warps waiting at a barrier -- bit-identical records, 2.25 instead of 1.63 ms per 10 000 frames.
 // The kernel is latency bound with idle issue slots; sharing the scalar simplex bookkeeping saves instructions nobody
 // was waiting for and lengthens every evaluation: four atoms per lane in series, group shuffles, divergent groups.)
-template <bool BIG>
+template <bool BIG, int PARTS>
 __global__ void __launch_bounds__(WIN_WARPS * 32, WIN_MINB)
 k_windows(pwb_batch b, Ws ws) {
   extern __shared__ __align__(16) double sm[];
@@ -1755,11 +1784,11 @@ k_windows(pwb_batch b, Ws ws) {
   if (item >= b.n_items) return;
   if (win >= ws.item_i[(size_t)item * ITEM_I + I_NWIN]) return;
   // per-warp shared memory: [atoms | fixed]; huge molecules (BIG) keep the atom part in the warp's global scratch slot
-  if (BIG) window_slot(b, ws, item, win, lane, sm + (size_t)w * WIN_FIXED_DOUBLES,
+  if (BIG) window_slot<PARTS>(b, ws, item, win, lane, sm + (size_t)w * WIN_FIXED_DOUBLES,
                        ws.atom_scratch + (size_t)item * ws.scratch_item + (size_t)win * WIN_ATOM_DOUBLES(b.max_atoms));
   else {
     double* smw = sm + (size_t)w * WIN_WARP_DOUBLES(b.max_atoms);
-    window_slot(b, ws, item, win, lane, smw + WIN_ATOM_DOUBLES(b.max_atoms), smw);
+    window_slot<PARTS>(b, ws, item, win, lane, smw + WIN_ATOM_DOUBLES(b.max_atoms), smw);
   }
 }
 
@@ -2057,10 +2086,30 @@ static int run_windows(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t
   int wpb = WIN_WARPS;
   while (wpb > 1 && per_warp * wpb + 64 > (size_t)c->max_smem) wpb >>= 1;
   size_t sm = per_warp * wpb + 64;
-  auto kern = w.atom_scratch ? k_windows<true> : k_windows<false>;
-  if (set_smem(kern, sm, c->max_smem)) return 1;
   long long warps = (long long)b->n_items * b->win_cap;
-  kern<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, sm, s>>>(*b, w);
+  const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+#if WIN_SPLIT == 2 || WIN_SPLIT == 4
+  constexpr int P1 = WIN_SPLIT == 2 ? 3 : 1, P2 = 7 - P1;       // cut behind the grid search / behind the z stage
+  auto k1 = w.atom_scratch ? k_windows<true, P1> : k_windows<false, P1>;
+  auto k2 = w.atom_scratch ? k_windows<true, P2> : k_windows<false, P2>;
+  if (set_smem(k1, sm, c->max_smem) || set_smem(k2, sm, c->max_smem)) return 1;
+  k1<<<grid, wpb * 32, sm, s>>>(*b, w);
+  k2<<<grid, wpb * 32, sm, s>>>(*b, w);
+  c->c.launches++;
+#elif WIN_SPLIT == 3
+  auto k1 = w.atom_scratch ? k_windows<true, 1> : k_windows<false, 1>;
+  auto k2 = w.atom_scratch ? k_windows<true, 2> : k_windows<false, 2>;
+  auto k3 = w.atom_scratch ? k_windows<true, 4> : k_windows<false, 4>;
+  if (set_smem(k1, sm, c->max_smem) || set_smem(k2, sm, c->max_smem) || set_smem(k3, sm, c->max_smem)) return 1;
+  k1<<<grid, wpb * 32, sm, s>>>(*b, w);
+  k2<<<grid, wpb * 32, sm, s>>>(*b, w);
+  k3<<<grid, wpb * 32, sm, s>>>(*b, w);
+  c->c.launches += 2;
+#else
+  auto kern = w.atom_scratch ? k_windows<true, 7> : k_windows<false, 7>;
+  if (set_smem(kern, sm, c->max_smem)) return 1;
+  kern<<<grid, wpb * 32, sm, s>>>(*b, w);
+#endif
   k_finish<<<(b->n_items + 255) / 256, 256, 0, s>>>(*b, w);
   c->c.launches += 2;
   CK(cudaGetLastError());
