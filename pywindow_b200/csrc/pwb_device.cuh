@@ -484,8 +484,9 @@ __device__ __forceinline__ void group_min_clear_pruned(const GroupAtoms& A, cons
 // a(p) = min_i(|x_i - p| - r_i) is 1-Lipschitz: for every p within R of a reference point p_ref with clearance
 // a_ref, an atom with |x_i - p_ref| - r_i > a_ref + 2R has |x_i - p| - r_i > a_ref + R >= a(p) and cannot attain the
 // minimum.  group_build_list keeps the indices of the other atoms (ascending); group_min_list evaluates a stencil of
-// K points over them.  Per atom sqrt(d2) - r instead of per class sqrt(min d2) - r_c: the same doubles, because sqrt
-// is monotone -- so the result is bit-identical to group_min_clear for every point of the ball.
+// K points over them.  Each lane takes sqrt(min d2) - r over its own RUNS of equal radius instead of one reduction per
+// class over the group: the same doubles, because sqrt is monotone -- so the result is bit-identical to
+// group_min_clear for every point of the ball.
 template <int G>
 __device__ __forceinline__ int group_build_list(const GroupAtoms& A, double cx, double cy, double cz, double a_ref,
                                                 double two_r, unsigned short* lst, unsigned short* lcls, int cap) {
@@ -590,13 +591,29 @@ __device__ __forceinline__ void group_min_list(const GroupAtoms& A, const unsign
   double m[K];
 #pragma unroll
   for (int k = 0; k < K; k++) m[k] = PWB_INF;
+  // the list is sorted by class, so the atoms of one lane come in runs of equal radius: min d2 over a run, one sqrt
+  // per run and point (sqrt is monotone: the same doubles as one sqrt per atom)
+  double run[K], rr = -1.0;
+#pragma unroll
+  for (int k = 0; k < K; k++) run[k] = PWB_INF;
   for (int e = A.gl; e < nl; e += G) {
     const double4 q = A.p[lst[e]];
+    if (q.w != rr) {
+      if (rr >= 0.0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) { m[k] = dmin(m[k], sqrt(run[k]) - rr); run[k] = PWB_INF; }
+      }
+      rr = q.w;
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const double dx = q.x - px[k], dy = q.y - py[k], dz = q.z - pz[k];
-      m[k] = dmin(m[k], sqrt(sq3(dx, dy, dz)) - q.w);
+      run[k] = dmin(run[k], sq3(dx, dy, dz));
     }
+  }
+  if (rr >= 0.0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) m[k] = dmin(m[k], sqrt(run[k]) - rr);
   }
 #pragma unroll
   for (int k = 0; k < K; k++) {

@@ -596,13 +596,22 @@ k_opt_pore(pwb_batch b, Ws ws) {
           if (G >= 4 && !OPT_LIST_CLASSWISE) group_min_list<G, 4>(A, lst, nl, px, py, pz, m);
           else group_min_clear_list<G, 4>(A, lst, lcls, px, py, pz, m);
           last_far = false;
+#ifdef OPT_LIST_STATS
+          if (gl == 0) { atomicAdd(&queue[1], 1); atomicAdd(&queue[4], nl); }
+#endif
         }
         else {
           group_min_clear<G, 4>(A, px, py, pz, m);
+#ifdef OPT_LIST_STATS
+          if (gl == 0) atomicAdd(&queue[2], 1);
+#endif
           if (nl == -2 || (far && (last_far || OPT_LIST_EAGER))) {   // first evaluation, or two far ones in a row: the search moved
             __syncwarp(mask);
             for (int i = gl; i < 3; i += G) lref[i] = x[i];
             nl = group_build_list<G>(A, x[0], x[1], x[2], m[0], 2.0 * OPT_LIST_R, lst, lcls, OPT_LIST_CAP);
+#ifdef OPT_LIST_STATS
+            if (gl == 0) atomicAdd(&queue[3], 1);
+#endif
             last_far = false;
             __syncwarp(mask);
           } else last_far = far;
@@ -2032,7 +2041,11 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   size_t sm = per_warp * wpb;
   auto kern = b->opt_bounds ? k_opt_pore<OPT_G, true, SA> : k_opt_pore<OPT_G, false, SA>;
   if (set_smem(kern, sm, c->max_smem)) return 1;
+#ifdef OPT_LIST_STATS
+  CK(cudaMemsetAsync(w.item_i + I_QUEUE, 0, 5 * sizeof(int), s));      // (slots 27..30 of the first item are free)
+#else
   CK(cudaMemsetAsync(w.item_i + I_QUEUE, 0, sizeof(int), s));
+#endif
   int ctas = (b->n_items + wpb * PPW - 1) / (wpb * PPW);
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, sm));
@@ -2041,6 +2054,15 @@ static int run_opt(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) 
   kern<<<ctas, wpb * 32, sm, s>>>(*b, w);
   c->c.launches++;
   CK(cudaGetLastError());
+#ifdef OPT_LIST_STATS
+  {
+    int st[5];
+    CK(cudaMemcpyAsync(st, w.item_i + I_QUEUE, sizeof st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    fprintf(stderr, "k_opt_pore stencils: %d over the list (mean length %.1f), %d over all atoms, %d list builds\n",
+            st[1], st[1] ? (double)st[4] / st[1] : 0.0, st[2], st[3]);
+  }
+#endif
   return 0;
 }
 static int run_rays(pwb_ctx* c, const pwb_batch* b, const Ws& w, cudaStream_t s) {
