@@ -2009,6 +2009,9 @@ static int check(const pwb_batch* b) {
   if (b->n_types < 1 || b->n_types > PWB_MAX_TYPES) { snprintf(g_err, sizeof g_err, "n_types out of range"); return 1; }
   if (b->rec_stride < PWB_REC_WIN0 + 4 * b->win_cap) { snprintf(g_err, sizeof g_err, "rec_stride too small"); return 1; }
   if (b->ray_cap > (1 << 22)) { snprintf(g_err, sizeof g_err, "ray_cap > 4M rays not supported"); return 1; }
+  if (b->max_atoms < 1 || b->max_atoms > 65535) {   // 16-bit atom indices: near lists (k_windows), survivor lists (k_opt_pore)
+    snprintf(g_err, sizeof g_err, "max_atoms %d outside 1..65535 atoms per molecule", b->max_atoms); return 1;
+  }
   return 0;
 }
 

@@ -462,3 +462,14 @@ def test_survivor_lists_of_the_pore_search_are_exact(eng):
     finally:
         e2.close()
         torch.cuda.synchronize()
+
+
+def test_more_than_65535_atoms_per_molecule_is_refused(eng):
+    """Atom indices inside the kernels are 16 bit (near lists, survivor lists): a larger molecule must fail loudly."""
+    from pywindow_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    n = 70000
+    u = rng.normal(size=(n, 3))
+    X = u / np.linalg.norm(u, axis=1)[:, None] * 160.0
+    with pytest.raises(L.PwbLibraryError, match="65535"):
+        eng.analyse_molecules([(["C"] * n, X)])
